@@ -1,0 +1,85 @@
+"""ctypes binding of libflowk.so (the C ABI declared in include/flowk.h).
+
+There is NO fallback: if the shared library is missing the import fails, and every op
+below refuses non-CUDA tensors.  Build it with `python __graft_entry__.py build`
+(or `make -C <package>/csrc`)."""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflowk.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "flowk.h")
+
+FLOWK_OK = 0
+FLOWK_ERR_SHAPE = 1
+FLOWK_ERR_ALIGN = 2
+FLOWK_ERR_ARG = 3
+FLOWK_ERR_CUDA_BASE = 1000
+
+_fp = ctypes.c_void_p     # device pointers travel as integers
+_i = ctypes.c_int
+_f = ctypes.c_float
+_st = ctypes.c_void_p     # cudaStream_t
+
+SIGNATURES = {
+    "flowk_abi_version": ([], _i),
+    "flowk_error_string": ([_i], ctypes.c_char_p),
+    "flowk_ldj_workspace_bytes": ([_i], ctypes.c_size_t),
+    "flowk_squeeze2d": ([_fp, _fp, _i, _i, _i, _i, _i, _st], _i),
+    "flowk_unsqueeze2d": ([_fp, _fp, _i, _i, _i, _i, _i, _st], _i),
+    "flowk_actnorm_init": ([_fp, _fp, _fp, _i, _i, _i, _f, _f, _st], _i),
+    "flowk_channel_scale": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
+    "flowk_channel_mix": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _st], _i),
+    "flowk_affine_coupling_fwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
+    "flowk_affine_coupling_inv": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
+    "flowk_affine_coupling_bwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
+    "flowk_mixlogcdf_fwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _st], _i),
+    "flowk_mixlogcdf_inv": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _st], _i),
+    "flowk_mixlogcdf_bwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _st], _i),
+    "flowk_mixture_log_cdf": ([_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
+    "flowk_mixture_log_pdf": ([_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
+    "flowk_mixture_inv_cdf": ([_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
+}
+
+
+def declared_symbols(header_path=HEADER_PATH):
+    """Names of every function include/flowk.h declares (used by the ABI test)."""
+    with open(header_path) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(flowk_[a-z0-9_]+)\s*\(", text)))
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libflowk.so not found at %s - the CUDA extension is the product and there is no fallback; "
+            "build it with `python __graft_entry__.py build`" % LIB_PATH)
+    import torch  # noqa: F401  (makes sure libcudart is resolvable / already mapped)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    return lib
+
+
+lib = _load()
+LAUNCHES = 0          # number of kernel-launching C-ABI calls made by this process
+
+
+def check(status, what=""):
+    """0 -> ok; shape errors surface as AssertionError like the reference's asserts
+    (common_modules.py:21,38), everything else as RuntimeError."""
+    if status == FLOWK_OK:
+        return
+    msg = "%s: %s (flowk status %d)" % (what, lib.flowk_error_string(status).decode(), status)
+    if status == FLOWK_ERR_SHAPE:
+        raise AssertionError(msg)
+    raise RuntimeError(msg)
+
+
+def call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    check(getattr(lib, name)(*args), name)

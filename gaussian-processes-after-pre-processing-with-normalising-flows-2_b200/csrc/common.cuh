@@ -1,0 +1,111 @@
+// Shared device/host helpers for libflowk (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "flowk.h"
+
+namespace flowk {
+
+constexpr int kMaxParts = 64;        // max CTAs that cooperate on one sample's log-det sum
+constexpr int kThreads = 128;        // CTA size of the coupling kernels
+
+#define FLOWK_CUDA_OK(expr)                                          \
+  do {                                                               \
+    cudaError_t e_ = (expr);                                         \
+    if (e_ != cudaSuccess) return FLOWK_ERR_CUDA_BASE + (int)e_;     \
+  } while (0)
+
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? FLOWK_OK : FLOWK_ERR_CUDA_BASE + (int)e;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+// Workspace layout: one slot of (1 + kMaxParts) words per sample: { unsigned ticket; float partial[kMaxParts] }.
+// The slot of sample b sits at the same address whatever B is, so calls with different batch sizes can
+// share a workspace: partials never land on another call's ticket word.
+constexpr int kSlotWords = kMaxParts + 1;
+struct LdjWs {
+  unsigned* base;
+  __host__ __device__ unsigned* ticket(int b) const { return base + (size_t)b * kSlotWords; }
+  __host__ __device__ float* partial(int b) const { return reinterpret_cast<float*>(base + (size_t)b * kSlotWords + 1); }
+};
+inline LdjWs carve_ws(void* ws, int /*B*/) {
+  LdjWs w;
+  w.base = reinterpret_cast<unsigned*>(ws);
+  return w;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Streaming (read-once) loads/stores: keep the 126 MB L2 for tensors that are re-read.
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+// fast transcendental building blocks (MUFU.EX2 / MUFU.RCP / MUFU.LG2)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// Per-sample log-det reduction, deterministic.
+//   grid = (parts <= kMaxParts, B); every thread passes its local sum.
+//   CTA sum -> ws.partial[b][part]; the CTA that takes the last ticket adds the partials in
+//   index order and writes ldj_out[b] = (ldj_in ? ldj_in[b] : 0) + sign * total, then re-arms
+//   the ticket counter so the workspace is clean for the next launch on this stream.
+template <int THREADS>
+__device__ __forceinline__ void finish_sample_ldj(float local, const float* __restrict__ ldj_in,
+                                                  float* __restrict__ ldj_out, float sign, LdjWs ws) {
+  __shared__ float warp_part[THREADS / 32];
+  __shared__ bool is_last;
+  const int b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) s += warp_part[w];
+    if (parts == 1) {
+      ldj_out[b] = (ldj_in ? ldj_in[b] : 0.f) + sign * s;
+      is_last = false;
+    } else {
+      __stcg(ws.partial(b) + part, s);
+      __threadfence();
+      unsigned ticket = atomicAdd(ws.ticket(b), 1u);
+      is_last = (ticket == (unsigned)parts - 1u);
+    }
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    float tot = 0.f;
+    for (int p = 0; p < parts; ++p) tot += __ldcg(ws.partial(b) + p);
+    ldj_out[b] = (ldj_in ? ldj_in[b] : 0.f) + sign * tot;
+    *ws.ticket(b) = 0u;
+  }
+}
+
+inline int parts_for(long long work_items, int per_cta) {
+  long long p = (work_items + per_cta - 1) / per_cta;
+  if (p < 1) p = 1;
+  if (p > kMaxParts) p = kMaxParts;
+  return (int)p;
+}
+
+}  // namespace flowk

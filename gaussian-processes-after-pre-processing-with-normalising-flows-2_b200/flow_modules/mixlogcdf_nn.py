@@ -1,0 +1,215 @@
+"""Flow++ conditioner network with the reference's module tree and state-dict keys
+(flow_modules/mixlogcdf_nn.py:8-276): weight-normalised convs, gated conv + gated 4-head
+self-attention residual blocks with LayerNorm in NHWC.
+
+Weight norm is the old `weight_g` / `weight_v` parametrisation, stated explicitly here instead of
+through the deprecated torch hook, so the normalised weight can be cached in no-grad mode.
+`NN.forward_raw` returns the un-split out_conv tensor [B,(2+3K)c,H,W] that the fused coupling
+kernel reads in place; `NN.forward` applies the reference's post-processing for API parity.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def concat_elu(x, dim=1):
+    return F.elu(torch.cat((x, -x), dim=dim))
+
+
+class _WeightNormed(nn.Module):
+    """Holds weight_g / weight_v (/ bias) and yields w = g * v / ||v||, norm over all dims but 0."""
+
+    def __init__(self, weight, bias):
+        super().__init__()
+        with torch.no_grad():
+            norm = weight.reshape(weight.shape[0], -1).norm(dim=1).view(-1, *([1] * (weight.dim() - 1)))
+        self.weight_g = nn.Parameter(norm.clone())
+        self.weight_v = nn.Parameter(weight.detach().clone())
+        if bias is None:
+            self.register_parameter("bias", None)
+        else:
+            self.bias = nn.Parameter(bias.detach().clone())
+        self._cache = None
+
+    def normed_weight(self):
+        v, g = self.weight_v, self.weight_g
+        track = torch.is_grad_enabled() and (v.requires_grad or g.requires_grad)
+        if not track:
+            key = (v.data_ptr(), v._version, g.data_ptr(), g._version)
+            if self._cache is not None and self._cache[0] == key:
+                return self._cache[1]
+        norm = v.reshape(v.shape[0], -1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+        w = v * (g / norm)
+        if not track:
+            self._cache = (key, w)
+        return w
+
+
+class _WNConvCore(_WeightNormed):
+    def __init__(self, in_channels, out_channels, kernel_size, padding, bias):
+        ref = nn.Conv2d(in_channels, out_channels, kernel_size, padding=padding, bias=bias)   # default init
+        super().__init__(ref.weight, ref.bias)
+        self.padding = padding
+
+    def forward(self, x):
+        return F.conv2d(x, self.normed_weight(), self.bias, padding=self.padding)
+
+
+class _WNLinear(_WeightNormed):
+    def __init__(self, in_features, out_features, bias=True):
+        ref = nn.Linear(in_features, out_features, bias=bias)
+        super().__init__(ref.weight, ref.bias)
+
+    def forward(self, x):
+        return F.linear(x, self.normed_weight(), self.bias)
+
+
+class WNConv2d(nn.Module):
+    """Weight-normalised conv; parameters live under `.conv.` as in the reference (mixlogcdf_nn.py:12-29)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, padding, bias=True):
+        super().__init__()
+        self.conv = _WNConvCore(in_channels, out_channels, kernel_size, padding, bias)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class GatedConv(nn.Module):
+    """concat_elu -> WN conv3x3 (2C->C) -> concat_elu -> Dropout2d -> WN conv1x1 (2C->2C) -> GLU."""
+
+    def __init__(self, num_channels, drop_prob=0., aux_channels=None):
+        super().__init__()
+        self.nlin = concat_elu
+        self.conv = WNConv2d(2 * num_channels, num_channels, kernel_size=3, padding=1)
+        self.drop = nn.Dropout2d(drop_prob)
+        self.gate = WNConv2d(2 * num_channels, 2 * num_channels, kernel_size=1, padding=0)
+        self.aux_conv = (WNConv2d(2 * aux_channels, num_channels, kernel_size=1, padding=0)
+                         if aux_channels is not None else None)
+
+    def forward(self, x, aux=None):
+        x = self.conv(self.nlin(x))
+        if aux is not None:
+            x = x + self.aux_conv(self.nlin(aux))
+        x = self.gate(self.drop(self.nlin(x)))
+        a, b = x.chunk(2, dim=1)
+        return a * torch.sigmoid(b)
+
+
+class GatedAttn(nn.Module):
+    """Gated multi-head self-attention over the H*W positions of an NHWC tensor (mixlogcdf_nn.py:105-224)."""
+
+    def __init__(self, d_model, num_heads=4, drop_prob=0.):
+        super().__init__()
+        self.d_model = d_model
+        self.num_heads = num_heads
+        self.drop_prob = drop_prob
+        self.in_proj = _WNLinear(d_model, 3 * d_model, bias=False)
+        self.gate = _WNLinear(d_model, 2 * d_model)
+        self._pos = {}
+
+    @staticmethod
+    def get_pos_enc(seq_len, num_channels, device):
+        half = num_channels // 2
+        inc = math.log(10000.) / (half - 1)
+        inv = torch.exp(torch.arange(half, dtype=torch.float32, device=device) * -inc)
+        t = torch.arange(seq_len, dtype=torch.float32, device=device).unsqueeze(1) * inv.unsqueeze(0)
+        enc = torch.cat([t.sin(), t.cos()], dim=1)
+        enc = F.pad(enc, [0, num_channels % 2, 0, 0])
+        return enc.view(1, seq_len, num_channels)
+
+    def _pos_enc(self, seq_len, ch, device):
+        key = (seq_len, ch, str(device))
+        if key not in self._pos:
+            self._pos[key] = self.get_pos_enc(seq_len, ch, device)
+        return self._pos[key]
+
+    def forward(self, x):
+        b, h, w, c = x.shape
+        seq, heads, d = h * w, self.num_heads, c // self.num_heads
+        t = x.reshape(b, seq, c) + self._pos_enc(seq, c, x.device)
+        proj = self.in_proj(t)
+        # in_proj output order is (k | v | q): memory = first 2C, query = last C (mixlogcdf_nn.py:136-139)
+        k, v, q = proj[..., :c], proj[..., c:2 * c], proj[..., 2 * c:]
+
+        def heads_first(m):
+            return m.reshape(b, seq, heads, d).permute(0, 2, 1, 3)
+
+        q = heads_first(q) * (d ** -0.5)
+        weights = torch.softmax(q @ heads_first(k).transpose(-1, -2), dim=-1)
+        weights = F.dropout(weights, self.drop_prob, self.training)
+        att = (weights @ heads_first(v)).permute(0, 2, 1, 3).reshape(b, h, w, c)
+        a, gate = self.gate(att).chunk(2, dim=-1)
+        return a * torch.sigmoid(gate)
+
+
+class ConvAttnBlock(nn.Module):
+    def __init__(self, num_channels, drop_prob, use_attn, aux_channels):
+        super().__init__()
+        self.conv = GatedConv(num_channels, drop_prob, aux_channels)
+        self.norm_1 = nn.LayerNorm(num_channels)
+        if use_attn:
+            self.attn = GatedAttn(num_channels, drop_prob=drop_prob)
+            self.norm_2 = nn.LayerNorm(num_channels)
+        else:
+            self.attn = None
+
+    def forward(self, x, aux=None):
+        x = self.conv(x, aux) + x
+        x = self.norm_1(x.permute(0, 2, 3, 1))
+        if self.attn:
+            x = self.norm_2(self.attn(x) + x)
+        return x.permute(0, 3, 1, 2)
+
+
+class Rescale(nn.Module):
+    """Per-channel multiplier, wrapped in weight norm by NN (mixlogcdf_nn.py:63,263-276)."""
+
+    def __init__(self, num_channels):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(num_channels, 1, 1))
+
+    def forward(self, x):
+        return self.weight * x
+
+
+class _WNRescale(_WeightNormed):
+    """weight_norm(Rescale(c)): keys `rescale.weight_g`, `rescale.weight_v`, both [c,1,1]."""
+
+    def __init__(self, num_channels):
+        super().__init__(torch.ones(num_channels, 1, 1), None)
+
+    def forward(self, x):
+        return self.normed_weight() * x
+
+
+class NN(nn.Module):
+    """Conditioner of the MixLogCDF coupling (mixlogcdf_nn.py:32-78)."""
+
+    def __init__(self, in_channels, num_channels, num_blocks, num_components, drop_prob, use_attn=True,
+                 aux_channels=None):
+        super().__init__()
+        self.k = num_components
+        self.in_conv = WNConv2d(in_channels, num_channels, kernel_size=3, padding=1)
+        self.mid_convs = nn.ModuleList([ConvAttnBlock(num_channels, drop_prob, use_attn, aux_channels)
+                                        for _ in range(num_blocks)])
+        self.out_conv = WNConv2d(num_channels, in_channels * (2 + 3 * self.k), kernel_size=3, padding=1)
+        self.rescale = _WNRescale(in_channels)
+
+    def forward_raw(self, x, aux=None):
+        x = self.in_conv(x)
+        for block in self.mid_convs:
+            x = block(x, aux)
+        return self.out_conv(x)
+
+    def rescale_weight(self):
+        return self.rescale.normed_weight().reshape(-1)
+
+    def forward(self, x, aux=None):
+        b, c, h, w = x.size()
+        raw = self.forward_raw(x, aux).view(b, -1, c, h, w)
+        s, t, pi, mu, scales = raw.split((1, 1, self.k, self.k, self.k), dim=1)
+        s = self.rescale(torch.tanh(s.squeeze(1)))
+        return s, t.squeeze(1), pi, mu, scales.clamp(min=-7)

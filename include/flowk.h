@@ -1,0 +1,123 @@
+/* flowk.h - C ABI of libflowk.so: the sm_100a kernels behind the mAR-SCF flow-step path.
+ *
+ * The reference has no FFI layer of its own: its boundary is the
+ * torch.nn.Module contract `layer(x, logdet, reverse) -> (x', logdet')`.  Each entry point
+ * below replaces the eager ATen launch sequence of one such module's forward / reverse
+ * branch (cited as file:line of the reference repository) and is what a reference-side
+ * binding would load (ctypes stub in INTEGRATION.md).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float32, NCHW contiguous ("HW" = H*W, flattened);
+ *   - the caller owns all memory; kernels never allocate, free or keep state between calls;
+ *   - work is enqueued on `stream` and the call returns immediately (stream-ordered, re-entrant);
+ *   - return value: FLOWK_OK, a FLOWK_ERR_* code, or FLOWK_ERR_CUDA_BASE + cudaError_t;
+ *   - `ldj_in` may be NULL (treated as zeros); `ldj_out` NULL skips the log-det output, like the
+ *     reference's `logdet=None`; ldj_in == ldj_out (in place) is allowed;
+ *   - `ws` is a reduction workspace of flowk_ldj_workspace_bytes(B) bytes that must be zero
+ *     when first used and is left zeroed-where-needed by every call; one workspace per stream.
+ *     Per-sample log-det sums are reduced in a fixed order (bit-reproducible run to run).
+ */
+#ifndef FLOWK_H_
+#define FLOWK_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* flowk_stream_t;   /* == cudaStream_t */
+
+enum {
+  FLOWK_OK = 0,
+  FLOWK_ERR_SHAPE = 1,      /* reference: AssertionError (common_modules.py:21,38) */
+  FLOWK_ERR_ALIGN = 2,      /* pointer not 4-byte aligned / vector path precondition */
+  FLOWK_ERR_ARG = 3,        /* NULL where data is required, unsupported K, ... */
+  FLOWK_ERR_CUDA_BASE = 1000
+};
+
+int flowk_abi_version(void);
+const char* flowk_error_string(int status);
+size_t flowk_ldj_workspace_bytes(int B);
+
+/* squeeze2d / unsqueeze2d, flow_modules/common_modules.py:12-42.
+ * squeeze:   y[b, c*f*f + fh*f + fw, h, w] = x[b, c, h*f+fh, w*f+fw];  x is [B,C,H,W], y is [B,C*f*f,H/f,W/f].
+ * unsqueeze: exact inverse; x is [B,C,H,W] with C % (f*f) == 0, y is [B,C/(f*f),H*f,W*f]. */
+int flowk_squeeze2d(const float* x, float* y, int B, int C, int H, int W, int factor, flowk_stream_t stream);
+int flowk_unsqueeze2d(const float* x, float* y, int B, int C, int H, int W, int factor, flowk_stream_t stream);
+
+/* Actnormlayer data-dependent init, common_modules.py:141-151:
+ * bias[c] = -mean_{b,h,w} x ; logs[c] = log(scale / (sqrt(mean((x+bias)^2)) + eps)). */
+int flowk_actnorm_init(const float* x, float* bias, float* logs, int B, int C, int HW,
+                       float scale, float eps, flowk_stream_t stream);
+
+/* Per-channel affine map  y = (x + pre[c]) * mul[c] + post[c].
+ * Actnormlayer forward (pre=bias, mul=e^{logs}, post=0) and reverse (pre=0, mul=e^{-logs}, post=-bias),
+ * common_modules.py:153-186.  ldj_out[b] = ldj_in[b] + ldj_add[0] (device scalar, may be NULL). */
+int flowk_channel_scale(const float* x, const float* pre, const float* mul, const float* post, float* y,
+                        const float* ldj_in, const float* ldj_add, float* ldj_out,
+                        int B, int C, int HW, flowk_stream_t stream);
+
+/* Per-pixel channel mixing  y[b,o,p] = sum_i Wm[o*C+i] * x[b,i,p] + bias[o]   (bias may be NULL).
+ * InvertibleConv1x1 forward/reverse (common_modules.py:113-127) and, with ActNorm folded into
+ * Wm/bias by the caller, the fused ActNorm->InvConv step of FlowStep (marscf_main.py:64-68,95-97).
+ * ldj_out[b] = ldj_in[b] + ldj_add[0].
+ * in_squeeze != 0: x is the UN-squeezed tensor [B, C/4, 2H', 2W'] (H'*W' = HW, `W` = W') and the
+ * squeeze2d index map is applied on load (SqueezeLayer fused into the first step of a level).
+ * out_unsqueeze != 0: y is written through the unsqueeze2d map (last step of a level, reverse). */
+int flowk_channel_mix(const float* x, const float* Wm, const float* bias, float* y,
+                      const float* ldj_in, const float* ldj_add, float* ldj_out,
+                      int B, int C, int H, int W, int in_squeeze, int out_unsqueeze,
+                      flowk_stream_t stream);
+
+/* AffineCoupling arithmetic, flow_modules/affine_coupling.py:100-124, given the conditioner output
+ * h = NN_net(x[:, :C/2]) of shape [B,C,HW]: shift = h[:,0::2], scale = sigmoid(h[:,1::2] + 2).
+ *   fwd: y = cat(x1, x2*scale + shift),  ldj_out = ldj_in + sum log(scale)
+ *   inv: y = cat(x1, (x2 - shift)/scale), ldj_out = ldj_in - sum log(scale)
+ *   bwd: given gy = dL/dy [B,C,HW] and gldj = dL/dldj_out [B] (may be NULL) of the FORWARD op,
+ *        writes gx (second half only; the caller adds gy's first half) and gh [B,C,HW]. */
+int flowk_affine_coupling_fwd(const float* x, const float* h, float* y, const float* ldj_in, float* ldj_out,
+                              void* ws, int B, int C, int HW, flowk_stream_t stream);
+int flowk_affine_coupling_inv(const float* x, const float* h, float* y, const float* ldj_in, float* ldj_out,
+                              void* ws, int B, int C, int HW, flowk_stream_t stream);
+int flowk_affine_coupling_bwd(const float* x, const float* h, const float* gy, const float* gldj,
+                              float* gx, float* gh, int B, int C, int HW, flowk_stream_t stream);
+
+/* MixLogCDFCoupling arithmetic, flow_modules/mixlogcdf_coupling.py:37-57 + log_dist.py, given the RAW
+ * conditioner output `raw` = out_conv(...) of shape [B, (2+3K)*c, HW], c = C/2 (mixlogcdf_nn.py:69-76):
+ * plane j of channel ch is raw[b, j*c+ch, p]; planes (0, 1, 2.., 2+K.., 2+2K..) = (a_raw, b, pi, mu, s);
+ * a = rescale[ch] * tanh(a_raw), s = max(s, -7).  Only K == 32 is built (marscf_main.py:41).
+ *   fwd: out = (logit(F(x1)) + b) * e^a,  ldj += sum(log f(x1) - log u - log(1-u) + a)
+ *        y = cat(out, x2)           (flip == 0)
+ *        y = cat(x2, out)           (flip != 0: TupleFlip fused, marscf_main.py:72-73)
+ *   inv: input is cat(v, x2) (flip == 0) or cat(x2, v) (flip != 0, marscf_main.py:89-90);
+ *        x1 = F^-1(clamp(sigmoid(v e^-a - b), 1e-5, 1-1e-5)) by bisection (log_dist.py:43-72),
+ *        ldj -= sum(a + softplus(t) + softplus(-t) + log f(x1));  y = cat(x1, x2) always.
+ *   bwd: gradients of the forward op given gy = dL/dy [B,C,HW] and gldj = dL/dldj_out [B] (may be NULL):
+ *        gx [B,C,HW] (x2 half = gy's pass-through half; the conditioner's input gradient is added by
+ *        the caller), graw [B,(2+3K)c,HW], and ga_tanh [B,c,HW] = dL/da * tanh(a_raw), whose sum over
+ *        (B,HW) is the gradient of `rescale`. */
+int flowk_mixlogcdf_fwd(const float* x, const float* raw, const float* rescale, float* y,
+                        const float* ldj_in, float* ldj_out, void* ws,
+                        int B, int C, int HW, int K, int flip, flowk_stream_t stream);
+int flowk_mixlogcdf_inv(const float* x, const float* raw, const float* rescale, float* y,
+                        const float* ldj_in, float* ldj_out, void* ws,
+                        int B, int C, int HW, int K, int flip, flowk_stream_t stream);
+int flowk_mixlogcdf_bwd(const float* x, const float* raw, const float* rescale,
+                        const float* gy, const float* gldj, float* gx, float* graw, float* ga_tanh,
+                        int B, int C, int HW, int K, int flip, flowk_stream_t stream);
+
+/* log_dist.py functions on explicit parameter tensors pi/mu/s of shape [B,K,N] and x,y,out of [B,N]
+ * (N = c*H*W flattened): mixture_log_cdf :34, mixture_log_pdf :25, mixture_inv_cdf :43 (bisection;
+ * the (0,1) domain check of :46-47 is the caller's, it needs a host read). */
+int flowk_mixture_log_cdf(const float* x, const float* pi, const float* mu, const float* s, float* out,
+                          int B, int K, int N, flowk_stream_t stream);
+int flowk_mixture_log_pdf(const float* x, const float* pi, const float* mu, const float* s, float* out,
+                          int B, int K, int N, flowk_stream_t stream);
+int flowk_mixture_inv_cdf(const float* y, const float* pi, const float* mu, const float* s, float* out,
+                          int B, int K, int N, flowk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* FLOWK_H_ */

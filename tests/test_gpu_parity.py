@@ -1,0 +1,472 @@
+"""GPU parity tests: the flowk modules (C ABI -> sm_100a kernels) against the golden fixtures the
+reference produced and against the CPU oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): z and logdet within 1e-4 relative in fp32, bits/dim within
+1e-3, squeeze/split index maps exact.  "Relative" is taken against the tensor's largest magnitude
+(an element-wise rtol is meaningless at zero crossings): |got - ref| <= 1e-4 * max(1, max|ref|).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import flow_oracle as O
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def parity(got, ref, rel=REL, what=""):
+    ref = ref.to(torch.float32)
+    got = got.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    scale = max(1.0, float(ref.abs().max())) if ref.numel() else 1.0
+    err = float((got - ref).abs().max()) if ref.numel() else 0.0
+    assert err <= rel * scale, "%s: max abs err %.3e > %.1e * %.3g" % (what, err, rel, scale)
+
+
+@pytest.fixture(scope="module")
+def F():
+    import flowk  # noqa: F401
+    from flowk import ops
+    from flowk.flow_modules import common_modules, affine_coupling, mixlogcdf_coupling, log_dist
+    from flowk import marscf
+
+    class NS:
+        pass
+    ns = NS()
+    ns.ops, ns.cm, ns.ac, ns.mc, ns.ld, ns.marscf = ops, common_modules, affine_coupling, mixlogcdf_coupling, log_dist, marscf
+    return ns
+
+
+# ---------------------------------------------------------------------------------------------
+# squeeze / unsqueeze: exact
+# ---------------------------------------------------------------------------------------------
+def test_squeeze_exact_golden(F, golden):
+    g = golden("squeeze")
+    y = F.cm.squeeze2d(g["x"].to(dev()), 2)
+    assert torch.equal(y.cpu(), g["y"])
+    assert torch.equal(F.cm.unsqueeze2d(y, 2).cpu(), g["x"])
+    assert torch.equal(F.cm.squeeze2d(g["idx"].to(dev()), 2).cpu(), g["idx_squeezed"])
+
+
+@pytest.mark.parametrize("shape,factor", [((64, 3, 32, 32), 2), ((3, 5, 6, 10), 2), ((2, 2, 9, 6), 3),
+                                          ((1, 1, 2, 2), 2), ((2, 4, 8, 8), 1), ((0, 3, 4, 4), 2)])
+def test_squeeze_exact_oracle(F, shape, factor):
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(1))
+    y = F.cm.squeeze2d(x.to(dev()), factor)
+    assert torch.equal(y.cpu(), O.squeeze2d(x, factor))
+    assert torch.equal(F.cm.unsqueeze2d(y, factor).cpu(), x)
+
+
+def test_squeeze_shape_errors(F):
+    with pytest.raises(AssertionError):
+        F.cm.squeeze2d(torch.zeros(1, 1, 7, 8, device=dev()), 2)
+    with pytest.raises(AssertionError):
+        F.cm.unsqueeze2d(torch.zeros(1, 6, 2, 2, device=dev()), 2)
+
+
+def test_squeeze_layer_and_split_and_flip(F):
+    x = torch.randn(2, 4, 4, 6, device=dev())
+    sq = F.cm.SqueezeLayer(2)
+    y, ld = sq(x, 0.5)
+    assert ld == 0.5 and y.shape == (2, 16, 2, 3)
+    back, _ = sq(y, 0.5, reverse=True)
+    assert torch.equal(back, x)
+    sp = F.cm.Split2dMsC(16, 1)
+    (z1, z2), _ = sp(y)
+    assert torch.equal(z1, y[:, :8]) and torch.equal(z2, y[:, 8:])
+    z, _ = sp((z1, z2), reverse=True)
+    assert torch.equal(z, y)
+    fl = F.cm.TupleFlip()
+    f, _ = fl(y)
+    assert torch.equal(f, torch.cat((y[:, 8:], y[:, :8]), 1))
+    assert torch.equal(fl(f, reverse=True)[0], y)
+
+
+# ---------------------------------------------------------------------------------------------
+# ActNorm / InvConv
+# ---------------------------------------------------------------------------------------------
+def test_actnorm_golden(F, golden):
+    g = golden("actnorm")
+    m = F.cm.Actnormlayer(6, 1.0).to(dev())
+    m.train()
+    y, ldj = m(g["x"].to(dev()), g["ldj0"].to(dev()))
+    parity(m.bias, g["init_bias"], what="init bias")
+    parity(m.logs, g["init_logs"], what="init logs")
+    parity(y, g["y_init"], what="y after init")
+    parity(ldj, g["ldj_init"], what="ldj after init")
+    assert float(m.is_initialized) == 1.0
+    m.load_state_dict({"bias": g["bias"], "logs": g["logs"], "is_initialized": torch.ones(1)})
+    m.eval()
+    with torch.no_grad():
+        y, ldj = m(g["x"].to(dev()), g["ldj0"].to(dev()))
+        parity(y, g["y"], what="y")
+        parity(ldj, g["ldj"], what="ldj")
+        xr, ldjr = m(y, ldj, reverse=True)
+        parity(xr, g["xr"], what="xr")
+        parity(ldjr, g["ldjr"], what="ldjr")
+        y2, none = m(g["x"].to(dev()), None)
+        assert none is None and torch.equal(y2, y)
+
+
+def test_actnorm_eval_never_initialises(F):
+    m = F.cm.Actnormlayer(4).to(dev()).eval()
+    m(torch.randn(3, 4, 2, 2, device=dev()) * 5 + 3, None)
+    assert float(m.is_initialized) == 0.0 and float(m.bias.detach().abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("name", ["invconv_c12", "invconv_c24"])
+def test_invconv_golden(F, golden, name):
+    g = golden(name)
+    m = F.cm.InvertibleConv1x1(g.meta["c"]).to(dev())
+    m.load_state_dict(g.sd)
+    with torch.no_grad():
+        w, _ = m.get_weight(g["x"].to(dev()), False)
+        parity(w.view(g.meta["c"], -1), g["w_fwd"], what="W")
+        z, ldj = m(g["x"].to(dev()), g["ldj0"].to(dev()))
+        parity(z, g["z"], what="z")
+        parity(ldj, g["ldj"], what="ldj")
+        wr, _ = m.get_weight(z, True)
+        parity(wr.view(g.meta["c"], -1), g["w_rev"], what="W^-1")
+        xr, ldjr = m(z, ldj, reverse=True)
+        parity(xr, g["xr"], what="xr")
+        parity(ldjr, g["ldjr"], what="ldjr")
+
+
+@pytest.mark.parametrize("C,H,W,B", [(12, 16, 16, 64), (24, 8, 8, 64), (48, 4, 4, 64), (96, 4, 4, 8), (4, 14, 14, 5),
+                                     (20, 3, 5, 3), (12, 64, 64, 40)])
+def test_fused_actnorm_invconv_vs_oracle(F, C, H, W, B):
+    import numpy as np
+    np.random.seed(C)
+    gen = torch.Generator().manual_seed(C * 7 + H)
+    step = F.marscf.FlowStep(H, W, C, C, C, 8, 1.0, "affine").to(dev()).eval()
+    with torch.no_grad():
+        step.actnormlayer.bias.copy_(torch.randn(1, C, 1, 1, generator=gen) * 0.3)
+        step.actnormlayer.logs.copy_(torch.randn(1, C, 1, 1, generator=gen) * 0.2)
+    sd = {k: v.detach().cpu() for k, v in step.state_dict().items()}
+    x = torch.randn(B, C, H, W, generator=gen)
+    ldj0 = torch.randn(B, generator=gen)
+    ref, ref_l = O.actnorm(x, sd["actnormlayer.bias"], sd["actnormlayer.logs"], ldj0)
+    ic = [sd["invert_1x1_layer." + n] for n in ("p", "l", "u", "sign_s", "log_s")]
+    ref, ref_l = O.invconv(ref, *ic, ref_l)
+    with torch.no_grad():
+        mat, bias, add = step._folded((H, W), False)
+        y, l = F.ops.channel_mix(x.to(dev()), mat, bias, ldj0.to(dev()), add, False, False)
+        parity(y, ref, what="fused fwd")
+        parity(l, ref_l, what="fused fwd ldj")
+        mat, bias, add = step._folded((H, W), True)
+        xr, lr = F.ops.channel_mix(y, mat, bias, l, add, False, False)
+        parity(xr, x, what="fused round trip")
+        parity(lr, ldj0, what="fused round trip ldj")
+        if C % 4 == 0:   # squeeze folded into the load / unsqueeze into the store
+            xu = O.unsqueeze2d(x)
+            mat, bias, add = step._folded((H, W), False)
+            y2, _ = F.ops.channel_mix(xu.to(dev()), mat, bias, ldj0.to(dev()), add, True, False)
+            assert torch.equal(y2, y)
+            mat, bias, add = step._folded((H, W), True)
+            xr2, _ = F.ops.channel_mix(y, mat, bias, l, add, False, True)
+            assert torch.equal(xr2, F.cm.unsqueeze2d(xr, 2))
+
+
+# ---------------------------------------------------------------------------------------------
+# affine coupling
+# ---------------------------------------------------------------------------------------------
+def test_affine_golden(F, golden):
+    g = golden("affine")
+    m = F.ac.AffineCoupling(12, 12, 16).to(dev())
+    m.load_state_dict({k[len("coupling."):]: v for k, v in g.sd.items()})
+    m.eval()
+    with torch.no_grad():
+        parity(m.NN_net(g["x"][:, :6].to(dev())), g["h"], what="conditioner")
+        y, ldj = m(g["x"].to(dev()), g["ldj0"].to(dev()))
+        parity(y, g["y"], what="y")
+        parity(ldj, g["ldj"], what="ldj")
+        xr, ldjr = m(y, ldj, reverse=True)
+        parity(xr, g["xr"], what="xr")
+        parity(ldjr, g["ldjr"], what="ldjr")
+
+
+@pytest.mark.parametrize("B,C,H,W", [(128, 12, 16, 16), (128, 48, 4, 4), (7, 6, 3, 5), (2, 12, 64, 64), (0, 4, 2, 2)])
+def test_affine_elementwise_vs_oracle(F, B, C, H, W):
+    gen = torch.Generator().manual_seed(B + C)
+    x = torch.randn(B, C, H, W, generator=gen)
+    h = torch.randn(B, C, H, W, generator=gen) * 1.5
+    ldj0 = torch.randn(B, generator=gen)
+    ref_y, ref_l = O.affine_elementwise(x, h, ldj0)
+    y, l = F.ops.affine_coupling(x.to(dev()), h.to(dev()), ldj0.to(dev()), False)
+    parity(y, ref_y, what="fwd")
+    parity(l, ref_l, what="fwd ldj")
+    ref_x, ref_lr = O.affine_elementwise(ref_y, h, ref_l, reverse=True)
+    xr, lr = F.ops.affine_coupling(y, h.to(dev()), l, True)
+    parity(xr, ref_x, what="inv")
+    parity(lr, ref_lr, what="inv ldj")
+
+
+# ---------------------------------------------------------------------------------------------
+# logistic mixture / MixLogCDF coupling
+# ---------------------------------------------------------------------------------------------
+def rand_mix(B, c, H, W, gen, K=32):
+    x = torch.randn(B, 2 * c, H, W, generator=gen)
+    raw = torch.randn(B, (2 + 3 * K) * c, H, W, generator=gen)
+    r5 = raw.view(B, 2 + 3 * K, c, H, W)
+    r5[:, 0] *= 0.5
+    r5[:, 1] *= 0.5
+    r5[:, 2 + 2 * K:] = r5[:, 2 + 2 * K:] * 0.7 - 0.5
+    rescale = torch.rand(c, generator=gen) + 0.5
+    return x, raw, rescale
+
+
+def test_mixture_functions_golden(F, golden):
+    g = golden("mixlogcdf_elementwise")
+    c = g["x"].shape[1] // 2
+    xc = g["x"][:, :c].contiguous().to(dev())
+    p = [g[k].to(dev()) for k in ("pi", "mu", "s")]
+    parity(F.ld.mixture_log_cdf(xc, *p), g["log_cdf"], what="log cdf")
+    parity(F.ld.mixture_log_pdf(xc, *p), g["log_pdf"], what="log pdf")
+    xinv = F.ld.mixture_inv_cdf(g["u"].to(dev()), *p)
+    parity(xinv, g["xinv"], what="inverse cdf")
+    bad = g["u"].clone()
+    bad.view(-1)[3] = 0.0
+    with pytest.raises(RuntimeError, match="outside"):
+        F.ld.mixture_inv_cdf(bad.to(dev()), *p)
+
+
+def test_mixlogcdf_elementwise_golden(F, golden):
+    g = golden("mixlogcdf_elementwise")
+    B, C, H, W = g["x"].shape
+    c = C // 2
+    # rebuild the raw conditioner layout from the fixture's (a, b, pi, mu, s): a = 4 * tanh(a_raw)
+    a_raw = torch.atanh(g["a"].double() / 4.0).float()
+    raw = torch.cat([a_raw.unsqueeze(1), g["b"].unsqueeze(1), g["pi"], g["mu"], g["s"]], dim=1).reshape(B, -1, H, W)
+    ones = torch.full((c,), 4.0)
+    for flip in (False, True):
+        y, ldj = F.ops.mixlogcdf_coupling(g["x"].to(dev()), raw.to(dev()), ones.to(dev()), g["ldj0"].to(dev()),
+                                          False, flip, 32)
+        want = O.tuple_flip(g["y"]) if flip else g["y"]
+        parity(y, want, what="fwd flip=%s" % flip)
+        parity(ldj, g["ldj"], what="fwd ldj")
+        xr, ldjr = F.ops.mixlogcdf_coupling(y, raw.to(dev()), ones.to(dev()), ldj, True, flip, 32)
+        parity(xr, g["xr"], what="inv flip=%s" % flip)
+        parity(ldjr, g["ldjr"], what="inv ldj")
+
+
+@pytest.mark.parametrize("B,c,H,W", [(64, 6, 16, 16), (64, 12, 8, 8), (64, 24, 4, 4), (3, 5, 3, 7), (1, 1, 1, 1),
+                                     (0, 2, 2, 2)])
+def test_mixlogcdf_elementwise_vs_oracle(F, B, c, H, W):
+    gen = torch.Generator().manual_seed(100 + B + c)
+    x, raw, rescale = rand_mix(B, c, H, W, gen)
+    ldj0 = torch.randn(B, generator=gen)
+    a, b, pi, mu, s = O.mixlogcdf_split_params(raw, rescale.view(-1, 1, 1))
+    ref_y, ref_l = O.mixlogcdf_elementwise(x, a, b, pi, mu, s, ldj0)
+    y, l = F.ops.mixlogcdf_coupling(x.to(dev()), raw.to(dev()), rescale.to(dev()), ldj0.to(dev()), False, False, 32)
+    parity(y, ref_y, what="fwd")
+    parity(l, ref_l, what="fwd ldj")
+    if B == 0:
+        return
+    xr, lr = F.ops.mixlogcdf_coupling(y, raw.to(dev()), rescale.to(dev()), l, True, False, 32)
+    ref_x, ref_lr = O.mixlogcdf_elementwise(ref_y, a, b, pi, mu, s, ref_l, reverse=True)
+    # the bisection result is conditioned by 1/pdf: compare in CDF space and, where the density is
+    # not tiny, directly
+    cdf_got = O.mix_log_cdf(xr.cpu()[:, :c], pi, mu, s).exp()
+    cdf_ref = O.mix_log_cdf(ref_x[:, :c], pi, mu, s).exp()
+    assert float((cdf_got - cdf_ref).abs().max()) < 5e-6
+    dense = O.mix_log_pdf(ref_x[:, :c], pi, mu, s).exp() > 0.02
+    assert float(((xr.cpu()[:, :c] - ref_x[:, :c]).abs() * dense).max()) < 3e-4
+    parity(xr[:, c:], ref_x[:, c:], what="pass-through")
+    parity(lr, ref_lr, rel=2e-4, what="inv ldj")
+    parity(xr, x, rel=1e-3, what="round trip")
+
+
+def test_mixlogcdf_tail_elements_use_log_domain(F):
+    """x far outside every component: the linear-domain sums underflow and the kernel must fall back
+    to the reference's log-domain formulation (finite log-pdf, not -inf)."""
+    gen = torch.Generator().manual_seed(5)
+    B, c, H, W, K = 2, 2, 2, 2, 32
+    x, raw, rescale = rand_mix(B, c, H, W, gen)
+    r5 = raw.view(B, 2 + 3 * K, c, H, W)
+    r5[:, 2 + 2 * K:] = -6.5            # very sharp components
+    x[:, :c] = 3.0                      # ~ e^{6.5} * 3 = 2000 widths away
+    ldj0 = torch.zeros(B)
+    a, b, pi, mu, s = O.mixlogcdf_split_params(raw, rescale.view(-1, 1, 1))
+    ref_lp = O.mix_log_pdf(x[:, :c], pi, mu, s)
+    assert torch.isfinite(ref_lp).all() and float(ref_lp.max()) < -80
+    got = F.ld.mixture_log_pdf(x[:, :c].contiguous().to(dev()), pi.contiguous().to(dev()), mu.contiguous().to(dev()),
+                               s.contiguous().to(dev()))
+    parity(got, ref_lp, what="tail log pdf")
+    y, l = F.ops.mixlogcdf_coupling(x.to(dev()), raw.to(dev()), rescale.to(dev()), ldj0.to(dev()), False, False, 32)
+    ref_y, ref_l = O.mixlogcdf_elementwise(x, a, b, pi, mu, s, ldj0)
+    parity(l, ref_l, what="tail ldj")
+
+
+def test_mixlogcdf_coupling_with_conditioner_golden(F, golden):
+    g = golden("mixlogcdf_coupling")
+    m = F.mc.MixLogCDFCoupling(12, 16, 2, 32, 0.2).to(dev())
+    m.load_state_dict({k[len("coupling."):]: v for k, v in g.sd.items()})
+    m.eval()
+    with torch.no_grad():
+        a, b, pi, mu, s = m.nn(g["x"][:, 6:].to(dev()))
+        for got, key in ((a, "a"), (b, "b"), (pi, "pi"), (mu, "mu"), (s, "s")):
+            parity(got, g[key], what="conditioner " + key)
+        y, ldj = m(g["x"].to(dev()), g["ldj0"].to(dev()))
+        parity(y, g["y"], what="y")
+        parity(ldj, g["ldj"], what="ldj")
+        xr, ldjr = m(y, ldj, reverse=True)
+        parity(xr, g["xr"], what="xr")
+        parity(ldjr, g["ldjr"], what="ldjr")
+
+
+def test_logdet_bit_reproducible(F):
+    gen = torch.Generator().manual_seed(9)
+    x, raw, rescale = rand_mix(64, 6, 16, 16, gen)
+    args = (x.to(dev()), raw.to(dev()), rescale.to(dev()), torch.zeros(64, device=dev()), False, True, 32)
+    y0, l0 = F.ops.mixlogcdf_coupling(*args)
+    for _ in range(3):
+        y1, l1 = F.ops.mixlogcdf_coupling(*args)
+        assert torch.equal(l0, l1) and torch.equal(y0, y1)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole stack
+# ---------------------------------------------------------------------------------------------
+def build_from_golden(F, g, fuse):
+    m = g.meta
+    model = F.marscf.MarScfFlow(m["B"], tuple(m["image_hwc"]), m["coupling"], m["L"], m["K"], m["hidden"],
+                                num_blocks=max(m["blocks"], 1), fuse_squeeze=fuse)
+    model.load_state_dict(g.sd, strict=True)
+    return model.to(dev()).eval()
+
+
+@pytest.mark.parametrize("name", ["flownet_affine", "flownet_mixlogcdf"])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_flownet_golden(F, golden, name, fuse):
+    g = golden(name)
+    model = build_from_golden(F, g, fuse)
+    x, noise = g["x"].to(dev()), g["noise"].to(dev())
+    with torch.no_grad():
+        z, nll, _ = model(x, noise=noise)
+        parity(z, g["z"], what="z")
+        assert float((nll.cpu() - g["nll"]).abs().max()) < 1e-3          # bits/dim budget
+        d = x[0].numel()
+        z0 = x + noise / 256.0
+        zf, outs, logdet = model.flow.encode_latents(z0, x.new_full((x.shape[0],), -math.log(256.0) * d))
+        parity(logdet, g["logdet"], what="logdet")
+        for i, o in enumerate(outs):
+            parity(o, g["z2_%d" % i], what="z2_%d" % i)
+        z2s = [g["z2_%d" % i].to(dev()) for i in range(len(outs))]
+        xr, ldr = model.flow.decode_latents(g["z"].to(dev()), z2s, with_logdet=True)
+        parity(xr, g["xr"], what="decode")
+        parity(ldr, g["ldr"], what="decode logdet")
+
+
+@pytest.mark.parametrize("coupling,hidden,B,image,L", [("affine", 64, 32, (32, 32, 3), 3),
+                                                       ("mixlogcdf", 32, 16, (32, 32, 3), 3),
+                                                       ("affine", 32, 4, (64, 64, 3), 4)])
+def test_full_size_round_trip_properties(F, coupling, hidden, B, image, L):
+    """Size-independent properties at the BASELINE shapes: decode(encode(x)) = x,
+    logdet_fwd + logdet_rev = 0, fused-squeeze path == explicit squeeze path, batch independence."""
+    import numpy as np
+    torch.manual_seed(3)
+    np.random.seed(3)
+    model = F.marscf.MarScfFlow(B, image, coupling, L, 4, hidden, num_blocks=2).to(dev())
+    x = torch.rand(B, image[2], image[0], image[1], device=dev()) - 0.5
+    model.train()
+    with torch.no_grad():
+        model(x)                                     # ActNorm data-dependent init
+    with torch.no_grad():                            # move the zero-initialised output convs off zero
+        gen = torch.Generator(device="cpu").manual_seed(4)
+        for n, p in model.named_parameters():
+            p.add_((torch.randn(p.shape, generator=gen) * 0.02).to(p.device))
+    model.eval()
+    with torch.no_grad():
+        z, outs, ld = model.flow.encode_latents(x, x.new_zeros(B))
+        xr, ldr = model.flow.decode_latents(z, outs, with_logdet=True)
+        parity(xr, x.cpu(), rel=2e-3, what="round trip")
+        assert float((ld + ldr).abs().max()) < 2e-3 * max(1.0, float(ld.abs().max()))
+        model.flow.fuse_squeeze = False
+        z_b, outs_b, ld_b = model.flow.encode_latents(x, x.new_zeros(B))
+        assert torch.equal(z, z_b) and torch.equal(ld, ld_b)
+        model.flow.fuse_squeeze = True
+        # each sample is processed independently of its batch neighbours
+        z_half, _, ld_half = model.flow.encode_latents(x[: B // 2].contiguous(), x.new_zeros(B // 2))
+        parity(z_half, z[: B // 2].cpu(), rel=1e-5, what="batch independence")
+        parity(ld_half, ld[: B // 2].cpu(), rel=1e-5, what="batch independence ldj")
+
+
+# ---------------------------------------------------------------------------------------------
+# gradients of the forward ops (training) against autograd through the oracle
+# ---------------------------------------------------------------------------------------------
+def test_affine_backward_vs_oracle(F):
+    gen = torch.Generator().manual_seed(31)
+    B, C, H, W = 5, 8, 4, 6
+    x = torch.randn(B, C, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    h = torch.randn(B, C, H, W, generator=gen, dtype=torch.float64, requires_grad=True)
+    l0 = torch.randn(B, generator=gen, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(B, C, H, W, generator=gen, dtype=torch.float64)
+    gl = torch.randn(B, generator=gen, dtype=torch.float64)
+    y, l = O.affine_elementwise(x, h, l0)
+    ((y * gy).sum() + (l * gl).sum()).backward()
+    xd, hd, ld_ = (t.detach().float().to(dev()).requires_grad_() for t in (x, h, l0))
+    yd, lo = F.ops.affine_coupling(xd, hd, ld_, False)
+    ((yd * gy.float().to(dev())).sum() + (lo * gl.float().to(dev())).sum()).backward()
+    parity(xd.grad, x.grad, what="dx")
+    parity(hd.grad, h.grad, what="dh")
+    parity(ld_.grad, l0.grad, what="dldj")
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_mixlogcdf_backward_vs_oracle(F, flip):
+    gen = torch.Generator().manual_seed(32)
+    B, c, H, W = 3, 3, 4, 5
+    x, raw, rescale = rand_mix(B, c, H, W, gen)
+    x64 = x.double().requires_grad_()
+    raw64 = raw.double().requires_grad_()
+    res64 = rescale.double().requires_grad_()
+    l0 = torch.randn(B, generator=gen, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(B, 2 * c, H, W, generator=gen, dtype=torch.float64)
+    gl = torch.randn(B, generator=gen, dtype=torch.float64)
+    a, b, pi, mu, s = O.mixlogcdf_split_params(raw64, res64.view(-1, 1, 1))
+    y, l = O.mixlogcdf_elementwise(x64, a, b, pi, mu, s, l0)
+    if flip:
+        y = O.tuple_flip(y)
+    ((y * gy).sum() + (l * gl).sum()).backward()
+    xd, rd, sd_, ld_ = (t.detach().float().to(dev()).requires_grad_() for t in (x, raw, rescale, l0))
+    yd, lo = F.ops.mixlogcdf_coupling(xd, rd, sd_, ld_, False, flip, 32)
+    ((yd * gy.float().to(dev())).sum() + (lo * gl.float().to(dev())).sum()).backward()
+    parity(xd.grad, x64.grad, rel=2e-4, what="dx")
+    parity(rd.grad, raw64.grad, rel=2e-4, what="draw")
+    parity(sd_.grad, res64.grad, rel=2e-4, what="drescale")
+    parity(ld_.grad, l0.grad, what="dldj")
+
+
+def test_flowstep_backward_vs_oracle(F, golden):
+    """Gradients w.r.t. every parameter of a small affine FlowNet, against autograd through the oracle."""
+    g = golden("flownet_affine")
+    model = build_from_golden(F, g, True)
+    m = g.meta
+    sd64 = {k: v.double().requires_grad_(v.dtype.is_floating_point and "is_initialized" not in k and
+                                         not k.endswith(".p") and not k.endswith("sign_s"))
+            for k, v in g.sd.items()}
+    x = g["x"].double()
+    z, outs, ldj, nll = O.normal_flow(sd64, x, g["noise"].double(), m["L"], m["K"], m["coupling"])
+    nll.mean().backward()
+    for p in model.parameters():
+        p.requires_grad_(True)
+    _, nll_d, _ = model(g["x"].to(dev()), noise=g["noise"].to(dev()))
+    nll_d.mean().backward()
+    checked = 0
+    for name, p in model.named_parameters():
+        ref = sd64[name].grad
+        if ref is None:
+            continue
+        if name.endswith(".l") or name.endswith(".u"):
+            c = ref.shape[0]
+            mask = torch.tril(torch.ones(c, c), -1) if name.endswith(".l") else torch.triu(torch.ones(c, c), 1)
+            ref = ref * mask
+        parity(p.grad, ref, rel=5e-4, what="grad " + name)
+        checked += 1
+    assert checked > 20
