@@ -43,6 +43,17 @@ SIGNATURES = {
 }
 
 
+# where the integer problem dimensions sit in each entry point's argument list (for per-launch accounting)
+DIMS = {
+    "flowk_squeeze2d": slice(2, 6), "flowk_unsqueeze2d": slice(2, 6), "flowk_actnorm_init": slice(3, 6),
+    "flowk_channel_scale": slice(8, 11), "flowk_channel_mix": slice(7, 11),
+    "flowk_affine_coupling_fwd": slice(6, 9), "flowk_affine_coupling_inv": slice(6, 9),
+    "flowk_affine_coupling_bwd": slice(6, 9),
+    "flowk_mixlogcdf_fwd": slice(7, 10), "flowk_mixlogcdf_inv": slice(7, 10), "flowk_mixlogcdf_bwd": slice(8, 11),
+    "flowk_mixture_log_cdf": slice(5, 8), "flowk_mixture_log_pdf": slice(5, 8), "flowk_mixture_inv_cdf": slice(5, 8),
+}
+
+
 def declared_symbols(header_path=HEADER_PATH):
     """Names of every function include/flowk.h declares (used by the ABI test)."""
     with open(header_path) as f:
@@ -66,6 +77,7 @@ def _load():
 
 lib = _load()
 LAUNCHES = 0          # number of kernel-launching C-ABI calls made by this process
+TIMING = None         # set to a dict to record a CUDA-event pair around every call: name -> [(start, end, int args)]
 
 
 def check(status, what=""):
@@ -80,6 +92,16 @@ def check(status, what=""):
 
 
 def call(name, *args):
+    """Enqueue one C-ABI entry point on the stream passed as its last argument."""
     global LAUNCHES
     LAUNCHES += 1
-    check(getattr(lib, name)(*args), name)
+    if TIMING is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    import torch
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()                       # torch's current stream == the stream handed to the kernel (ops._stream)
+    status = getattr(lib, name)(*args)
+    end.record()
+    check(status, name)
+    TIMING.setdefault(name, []).append((start, end, tuple(args[DIMS.get(name, slice(0, 0))])))
