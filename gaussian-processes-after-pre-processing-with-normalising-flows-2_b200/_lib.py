@@ -40,7 +40,22 @@ SIGNATURES = {
     "flowk_mixture_log_cdf": ([_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
     "flowk_mixture_log_pdf": ([_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
     "flowk_mixture_inv_cdf": ([_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _st], _i),
+    "flowk_conv_gemm": ([ctypes.c_void_p, _st], _i),
+    "flowk_nchw_to_nhwc_hilo": ([_fp, ctypes.c_longlong, _i, _i, _i, _i, _fp, _fp, _st], _i),
+    "flowk_split_hilo": ([_fp, _fp, _fp, ctypes.c_longlong, _st], _i),
 }
+
+
+class ConvGemmArgs(ctypes.Structure):
+    """Mirror of `flowk_conv_gemm_args` (include/flowk.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("a_hi", "a_lo", "w_hi", "w_lo", "bias", "res", "gamma", "beta", "pos",
+                 "out_f32", "out_hi", "out_lo", "out_nchw", "status")] + \
+               [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")]
+
+
+PRE_BIAS, PRE_GLU_RES_LN = 0, 1
+OUT_F32, OUT_HILO, OUT_HILO_POS, OUT_HILO_CELU, OUT_NCHW = 1, 2, 4, 8, 16
 
 
 # where the integer problem dimensions sit in each entry point's argument list (for per-launch accounting)
@@ -51,6 +66,7 @@ DIMS = {
     "flowk_affine_coupling_bwd": slice(6, 9),
     "flowk_mixlogcdf_fwd": slice(7, 10), "flowk_mixlogcdf_inv": slice(7, 10), "flowk_mixlogcdf_bwd": slice(8, 11),
     "flowk_mixture_log_cdf": slice(5, 8), "flowk_mixture_log_pdf": slice(5, 8), "flowk_mixture_inv_cdf": slice(5, 8),
+    "flowk_nchw_to_nhwc_hilo": slice(2, 6), "flowk_split_hilo": slice(3, 4),
 }
 
 

@@ -1,0 +1,578 @@
+// Implicit-GEMM convolution / linear layer of the coupling conditioners on the 5th-gen tensor cores.
+//
+//   D[m, n] = sum_{tap, c} A[pos(m) + shift(tap), c] * Wt[n, tap*Cin + c]        (taps = 1 or 3x3, zero "same" padding)
+//
+// * activations NHWC fp32 [B,H,W,Cin]; an M tile = 128 consecutive positions = a (Bt x Ht x W) box, fetched per tap
+//   by ONE 4-D TMA box load whose coordinates carry the tap shift - out-of-bounds rows/columns are zero-filled by
+//   the TMA unit, which is the convolution's padding;
+// * weights [N, taps*Cin] K-major, 2-D TMA;
+// * tcgen05.mma kind::tf32, M=128, accumulators in TMEM.  fp32 accuracy (the 1e-4 parity budget rules out plain
+//   TF32) comes from the 3xTF32 split: every operand is stored as hi = x with the low 13 mantissa bits cleared and
+//   lo = x - hi (exact), and D += A_hi W_hi + A_lo W_hi + A_hi W_lo (dropped term ~2^-22);
+// * warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane), warps 2..5 = epilogue,
+//   each thread owning one accumulator row (TMEM lane) - so row-wise epilogues (GLU, residual, LayerNorm over the
+//   channel dim) are thread-local;
+// * fused epilogues produce exactly what the next layer consumes: fp32 rows, hi/lo operand pairs (optionally after
+//   concat-ELU or after adding the positional encoding), or the NCHW parameter tensor the MixLogCDF kernel reads.
+//
+// Reference semantics: flow_modules/mixlogcdf_nn.py:12-29 (WNConv2d), :81-102 (ConvAttnBlock), :227-260 (GatedConv),
+// :124-152 (GatedAttn projections), flow_modules/affine_coupling.py:27-80 (NN_net).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace flowk {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                 // fp32 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 8;                   // tf32: 32 bytes per MMA along K
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_CHUNKS = 2;
+
+// --------------------------------------------------------------------------------------------------
+// PTX wrappers
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU.  On timeout the CTA-wide `failed` flag is raised, every
+// later wait returns at once, the kernel finishes (with garbage) and the host sees the flag in `status`.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* failed) {
+  if (*failed) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 400000000LL) {      // ~0.2 s
+      *failed = 1;
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+      "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+      "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+      "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle: 8-row groups of 1024 B (SBO), rows of 128 B; LBO unused.  (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                       // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+// --------------------------------------------------------------------------------------------------
+// kernel parameters (device view)
+// --------------------------------------------------------------------------------------------------
+enum { PRE_BIAS = 0, PRE_GLU_RES_LN = 1 };
+enum { OUT_F32 = 1, OUT_HILO = 2, OUT_HILO_POS = 4, OUT_HILO_CELU = 8, OUT_NCHW = 16 };
+
+struct Params {
+  int M, N, HW, W, H;              // M = B*H*W rows, N = total output columns of the GEMM
+  int taps, kblocks_per_tap;       // K loop = taps * kblocks_per_tap blocks of 32 channels
+  int wt, ht, bt;                  // M tile = bt images x ht rows x wt (= W) columns
+  int n_chunk, n_chunks;           // columns per MMA (<=256, %16) and MMAs per k-step; CTA covers n_chunk*n_chunks columns
+  int tmem_cols, stages;
+  int pre, out_mask;
+  const float* bias;               // [N] or null
+  const float* res;                // [M, C] residual (PRE_GLU_RES_LN), C = N/2
+  const float* gamma;              // LayerNorm weight/bias [C]
+  const float* beta;
+  const float* pos;                // positional encoding [HW, C] (OUT_HILO_POS)
+  float* out_f32;                  // [M, Nout]
+  float* out_hi;                   // [M, Nout] or [M, 2*Nout] (CELU)
+  float* out_lo;
+  float* out_nchw;                 // [B, N, HW]
+  int* status;                     // set to 1 if a barrier wait timed out
+};
+
+template <int PRE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A_hi | A_lo | W_hi | W_lo], then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_tile_bytes = p.n_chunk * p.n_chunks * BLOCK_K * 4;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * w_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  volatile int* failed = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  const int n_base = n_tile * p.n_chunk * p.n_chunks;
+  const int num_kb = p.taps * p.kblocks_per_tap;
+
+  if (threadIdx.x == 0) {
+    *failed = 0;
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&map_a_hi);
+    prefetch_tmap(&map_a_lo);
+    prefetch_tmap(&map_w_hi);
+    prefetch_tmap(&map_w_lo);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // position of this M tile in (b, h, w)
+      const int tiles_per_img = (p.H * p.W) / (p.ht * p.wt);        // >= 1 when bt == 1
+      int b0, h0;
+      if (p.bt > 1) { b0 = m_tile * p.bt; h0 = 0; }
+      else { b0 = m_tile / tiles_per_img; h0 = (m_tile % tiles_per_img) * p.ht; }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u, failed);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const int tap = kb / p.kblocks_per_tap, cb = kb % p.kblocks_per_tap;
+        const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+        mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+        tma_load_4d(st, &map_a_hi, &full_bar[s], cb * BLOCK_K, dx, h0 + dy, b0);
+        tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[s], cb * BLOCK_K, dx, h0 + dy, b0);
+        const int kcol = kb * BLOCK_K;                               // weights are [N, taps*Cin], (tap, c) order
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const int chunk_bytes = p.n_chunk * BLOCK_K * 4;
+          tma_load_2d(st + 2 * A_TILE_BYTES + c * chunk_bytes, &map_w_hi, &full_bar[s], kcol, n_base + c * p.n_chunk);
+          tma_load_2d(st + 2 * A_TILE_BYTES + w_tile_bytes + c * chunk_bytes, &map_w_lo, &full_bar[s], kcol,
+                      n_base + c * p.n_chunk);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.n_chunk);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph, failed);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t w_hi = a_hi + 2 * A_TILE_BYTES;
+        const uint32_t w_lo = w_hi + w_tile_bytes;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 4;                      // bytes inside the 128-byte swizzle row
+          const uint64_t da_hi = make_smem_desc(a_hi + koff), da_lo = make_smem_desc(a_lo + koff);
+          for (int c = 0; c < p.n_chunks; ++c) {
+            const uint32_t coff = c * p.n_chunk * BLOCK_K * 4;
+            const uint64_t db_hi = make_smem_desc(w_hi + coff + koff), db_lo = make_smem_desc(w_lo + coff + koff);
+            const uint32_t d = tmem_base + c * p.n_chunk;
+            umma_tf32(d, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
+            umma_tf32(d, da_lo, db_hi, idesc, 1u);
+            umma_tf32(d, da_hi, db_lo, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);                                  // smem slot free once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);                                    // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: thread == accumulator row =====================
+    mbar_wait(tmem_full_bar, 0, failed);
+    tc_fence_after();
+    const int lane_grp = warp & 3;                                   // TMEM lanes this warp may touch
+    const int row = lane_grp * 32 + lane;
+    const int m = m_tile * BLOCK_M + row;
+    const bool valid = m < p.M;
+    const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+    const int ncols_cta = p.n_chunk * p.n_chunks;
+
+    if (PRE == PRE_BIAS) {
+      const int hw = valid ? m % p.HW : 0, img = valid ? m / p.HW : 0;
+      for (int j = 0; j < ncols_cta; j += 16) {
+        float v[16];
+        tmem_ld16(trow + j, v);
+        const int n0 = n_base + j;
+        if (n0 >= p.N) break;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        if (!valid) continue;
+        const int nvalid = p.N - n0 < 16 ? p.N - n0 : 16;
+        if (p.out_mask & OUT_F32) {
+          float* o = p.out_f32 + (size_t)m * p.N + n0;
+          if (nvalid == 16 && (p.N & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            for (int i = 0; i < nvalid; ++i) o[i] = v[i];
+          }
+        }
+        if (p.out_mask & OUT_HILO) {
+          float* oh = p.out_hi + (size_t)m * p.N + n0;
+          float* ol = p.out_lo + (size_t)m * p.N + n0;
+          for (int i = 0; i < nvalid; ++i) split_tf32(v[i], oh[i], ol[i]);
+        }
+        if (p.out_mask & OUT_HILO_CELU) {                            // concat_elu: [elu(y) | elu(-y)], width 2N
+          float* oh = p.out_hi + (size_t)m * 2 * p.N + n0;
+          float* ol = p.out_lo + (size_t)m * 2 * p.N + n0;
+          for (int i = 0; i < nvalid; ++i) {
+            split_tf32(elu1(v[i]), oh[i], ol[i]);
+            split_tf32(elu1(-v[i]), oh[p.N + i], ol[p.N + i]);
+          }
+        }
+        if (p.out_mask & OUT_NCHW) {
+          float* o = p.out_nchw + ((size_t)img * p.N + n0) * p.HW + hw;
+          for (int i = 0; i < nvalid; ++i) o[(size_t)i * p.HW] = v[i];
+        }
+      }
+    } else {
+      // GLU over [a | b] halves, + residual, LayerNorm over C = N/2 (mixlogcdf_nn.py:92-101, :257-258, :149-151)
+      const int C = p.N >> 1;
+      const uint32_t tb = trow + C;                                    // b half: columns C..2C-1 in both chunkings
+      const float* rrow = p.res + (size_t)(valid ? m : 0) * C;
+      float sum = 0.f;
+      for (int j = 0; j < C; j += 16) {
+        float a[16], g[16];
+        tmem_ld16(trow + j, a);
+        tmem_ld16(tb + j, g);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float av = a[i] + __ldg(p.bias + j + i), bv = g[i] + __ldg(p.bias + C + j + i);
+          const float r = av / (1.f + expf(-bv)) + __ldg(rrow + j + i);
+          a[i] = r;
+          sum += r;
+        }
+        tmem_st16(trow + j, a);
+      }
+      const float mean = sum / (float)C;
+      float var = 0.f;
+      for (int j = 0; j < C; j += 16) {
+        float a[16];
+        tmem_ld16(trow + j, a);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) var += (a[i] - mean) * (a[i] - mean);
+      }
+      const float rstd = rsqrtf(var / (float)C + 1e-5f);
+      const int hw = valid ? m % p.HW : 0;
+      for (int j = 0; j < C; j += 16) {
+        float a[16];
+        tmem_ld16(trow + j, a);
+        if (!valid) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = (a[i] - mean) * rstd * __ldg(p.gamma + j + i) + __ldg(p.beta + j + i);
+        if (p.out_mask & OUT_F32) {
+          float* o = p.out_f32 + (size_t)m * C + j;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+        }
+        if (p.out_mask & OUT_HILO) {
+          float* oh = p.out_hi + (size_t)m * C + j;
+          float* ol = p.out_lo + (size_t)m * C + j;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) split_tf32(a[i], oh[i], ol[i]);
+        }
+        if (p.out_mask & OUT_HILO_POS) {
+          float* oh = p.out_hi + (size_t)m * C + j;
+          float* ol = p.out_lo + (size_t)m * C + j;
+          const float* pe = p.pos + (size_t)hw * C + j;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) split_tf32(a[i] + __ldg(pe + i), oh[i], ol[i]);
+        }
+        if (p.out_mask & OUT_HILO_CELU) {
+          float* oh = p.out_hi + (size_t)m * 2 * C + j;
+          float* ol = p.out_lo + (size_t)m * 2 * C + j;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            split_tf32(elu1(a[i]), oh[i], ol[i]);
+            split_tf32(elu1(-a[i]), oh[C + i], ol[C + i]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (threadIdx.x == 0 && *failed && p.status) *p.status = 1;
+}
+
+// --------------------------------------------------------------------------------------------------
+// elementwise helpers around the GEMMs
+// --------------------------------------------------------------------------------------------------
+// NCHW slice -> NHWC hi/lo operand, channel dim zero-padded to c_pad (conditioner input, mixlogcdf_nn.py:66)
+__global__ void nchw_to_nhwc_hilo_kernel(const float* __restrict__ x, long long batch_stride, int c, int hw, int c_pad,
+                                         float* __restrict__ hi, float* __restrict__ lo, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c_pad);
+    const long long m = i / c_pad;
+    const int p = (int)(m % hw);
+    const long long b = m / hw;
+    const float v = ch < c ? x[b * batch_stride + (long long)ch * hw + p] : 0.f;
+    float h, l;
+    split_tf32(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// fp32 rows -> hi/lo operand pair (attention output -> gate GEMM)
+__global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                  long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float h, l;
+    split_tf32(x[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static bool make_map_act(CUtensorMap* map, const float* base, int B, int H, int W, int C, int bt, int ht, int wt) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)wt, (cuuint32_t)ht, (cuuint32_t)bt};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool make_map_w(CUtensorMap* map, const float* base, int N, int Ktot, int rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)rows};
+  cuuint32_t estr[2] = {1, 1};
+  return encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+}  // namespace flowk
+
+using namespace flowk;
+using namespace flowk::tc;
+
+extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t stream) {
+  if (!a) return FLOWK_ERR_ARG;
+  if (!a->a_hi || !a->a_lo || !a->w_hi || !a->w_lo) return FLOWK_ERR_ARG;
+  const int B = a->B, H = a->H, W = a->W, Cin = a->Cin, N = a->N;
+  if (B < 1 || H < 1 || W < 1 || Cin < BLOCK_K || Cin % BLOCK_K || N < 8) return FLOWK_ERR_SHAPE;
+  if (a->taps != 1 && a->taps != 9) return FLOWK_ERR_ARG;
+  if (!encode_fn()) return FLOWK_ERR_ARG;
+  // M tile = bt images x ht rows x W columns = 128 positions
+  int wt = W, ht, bt;
+  if (W > BLOCK_M || BLOCK_M % W) return FLOWK_ERR_SHAPE;
+  if (H * W >= BLOCK_M) {
+    if ((H * W) % BLOCK_M) return FLOWK_ERR_SHAPE;
+    ht = BLOCK_M / W;
+    bt = 1;
+  } else {
+    if (BLOCK_M % (H * W)) return FLOWK_ERR_SHAPE;
+    ht = H;
+    bt = BLOCK_M / (H * W);
+  }
+  Params p{};
+  p.M = B * H * W;
+  p.N = N;
+  p.HW = H * W;
+  p.W = W;
+  p.H = H;
+  p.taps = a->taps;
+  p.kblocks_per_tap = Cin / BLOCK_K;
+  p.wt = wt;
+  p.ht = ht;
+  p.bt = bt;
+  p.pre = a->pre;
+  p.out_mask = a->out_mask;
+  p.bias = a->bias;
+  p.res = a->res;
+  p.gamma = a->gamma;
+  p.beta = a->beta;
+  p.pos = a->pos;
+  p.out_f32 = a->out_f32;
+  p.out_hi = a->out_hi;
+  p.out_lo = a->out_lo;
+  p.out_nchw = a->out_nchw;
+  p.status = a->status;
+  int n_tiles;
+  if (a->pre == PRE_GLU_RES_LN) {
+    const int C = N / 2;
+    if ((N & 1) || C % 16 || C > 256 || !a->res || !a->gamma || !a->beta || !a->bias) return FLOWK_ERR_SHAPE;
+    if (N <= 256) { p.n_chunk = N; p.n_chunks = 1; }
+    else { p.n_chunk = C; p.n_chunks = 2; }
+    n_tiles = 1;
+  } else {
+    // split N into tiles of <= 256 columns, multiple of 16 (rows past N are zero-filled by TMA)
+    const int n16 = (N + 15) / 16 * 16;
+    n_tiles = (n16 + 255) / 256;
+    int per = (n16 / 16 + n_tiles - 1) / n_tiles * 16;
+    p.n_chunk = per;
+    p.n_chunks = 1;
+  }
+  if (p.n_chunk % 16 || p.n_chunk > 256) return FLOWK_ERR_SHAPE;
+  const int cols = p.n_chunk * p.n_chunks;
+  p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * cols * BLOCK_K * 4;
+  int stages = (int)((220 * 1024 - 2048) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 1) return FLOWK_ERR_SHAPE;
+  p.stages = stages;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+
+  alignas(64) CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+  const int Ktot = a->taps * Cin;
+  if (!make_map_act(&ma_hi, a->a_hi, B, H, W, Cin, bt, ht, wt) || !make_map_act(&ma_lo, a->a_lo, B, H, W, Cin, bt, ht, wt) ||
+      !make_map_w(&mw_hi, a->w_hi, N, Ktot, p.n_chunk) || !make_map_w(&mw_lo, a->w_lo, N, Ktot, p.n_chunk))
+    return FLOWK_ERR_ARG;
+
+  dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, n_tiles);
+  if (a->pre == PRE_GLU_RES_LN) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
+    conv_gemm_kernel<PRE_GLU_RES_LN><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+  } else {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
+    conv_gemm_kernel<PRE_BIAS><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+  }
+  return launch_status();
+}
+
+extern "C" int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, int B, int C, int HW, int C_pad,
+                                       float* hi, float* lo, flowk_stream_t stream) {
+  if (B < 0 || C < 1 || HW < 1 || C_pad < C) return FLOWK_ERR_SHAPE;
+  if (B == 0) return FLOWK_OK;
+  if (!x || !hi || !lo) return FLOWK_ERR_ARG;
+  const long long total = (long long)B * HW * C_pad;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  nchw_to_nhwc_hilo_kernel<<<blocks, 256, 0, stream>>>(x, batch_stride, C, HW, C_pad, hi, lo, total);
+  return launch_status();
+}
+
+extern "C" int flowk_split_hilo(const float* x, float* hi, float* lo, long long n, flowk_stream_t stream) {
+  if (n < 0) return FLOWK_ERR_SHAPE;
+  if (n == 0) return FLOWK_OK;
+  if (!x || !hi || !lo) return FLOWK_ERR_ARG;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  split_hilo_kernel<<<blocks, 256, 0, stream>>>(x, hi, lo, n);
+  return launch_status();
+}

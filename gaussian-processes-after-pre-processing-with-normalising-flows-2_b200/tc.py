@@ -1,0 +1,62 @@
+"""Host side of the tensor-core conditioner layers: operand preparation (3xTF32 hi/lo split, NHWC
+weight layout) and the ctypes call into `flowk_conv_gemm` (include/flowk.h)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (OUT_F32, OUT_HILO, OUT_HILO_CELU, OUT_HILO_POS, OUT_NCHW, PRE_BIAS,  # noqa: F401
+                   PRE_GLU_RES_LN)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def split_hilo(t):
+    """hi = t with the 13 low mantissa bits cleared (exactly representable in TF32), lo = t - hi (exact)."""
+    t = t.contiguous().float()
+    hi = (t.view(torch.int32) & -8192).view(torch.float32)
+    return hi, t - hi
+
+
+def conv_weight_operand(w, cin_pad=None):
+    """[N, Cin, kh, kw] conv weight (or [N, Cin] linear weight) -> K-major [N, taps*Cin_pad] in (tap, c) order, hi/lo."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    n, cin, kh, kw = w.shape
+    cin_pad = cin_pad or ((cin + 31) // 32 * 32)
+    wk = w.permute(0, 2, 3, 1)                                   # [N, kh, kw, Cin]
+    if cin_pad != cin:
+        wk = torch.nn.functional.pad(wk, (0, cin_pad - cin))
+    return split_hilo(wk.reshape(n, kh * kw * cin_pad))
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias=None, res=None, gamma=None,
+              beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None):
+    args = _lib.ConvGemmArgs(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(res), _p(gamma), _p(beta), _p(pos),
+                             _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status),
+                             B, H, W, Cin, N, taps, pre, out_mask)
+    _lib.call("flowk_conv_gemm", ctypes.addressof(args), _stream())
+
+
+def nchw_to_nhwc_hilo(x, c_pad):
+    """x: NCHW view whose (C,H,W) block is contiguous (e.g. a channel slice) -> ([B*HW, c_pad] hi, lo)."""
+    b, c, h, w = x.shape
+    assert x.stride(3) == 1 and x.stride(2) == w and x.stride(1) == h * w, "channel slice of a contiguous NCHW tensor"
+    hi = torch.empty(b * h * w, c_pad, device=x.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    _lib.call("flowk_nchw_to_nhwc_hilo", x.data_ptr(), x.stride(0), b, c, h * w, c_pad, hi.data_ptr(), lo.data_ptr(),
+              _stream())
+    return hi, lo
+
+
+def split_rows(x):
+    hi = torch.empty_like(x)
+    lo = torch.empty_like(x)
+    _lib.call("flowk_split_hilo", x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
+    return hi, lo

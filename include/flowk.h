@@ -117,6 +117,53 @@ int flowk_mixture_log_pdf(const float* x, const float* pi, const float* mu, cons
 int flowk_mixture_inv_cdf(const float* y, const float* pi, const float* mu, const float* s, float* out,
                           int B, int K, int N, flowk_stream_t stream);
 
+/* ---- conditioner layers on the tensor cores (tcgen05, 3xTF32 split operands) --------------------------------
+ * Implicit-GEMM convolution / linear layer in NHWC:
+ *     D[m, n] = sum_{tap, c} A[pos(m) + shift(tap), c] * Wt[n, tap*Cin + c]      taps = 1 (1x1 / Linear) or 9 (3x3, "same")
+ * replacing F.conv2d / F.linear of flow_modules/mixlogcdf_nn.py:12-29,121-122,134,149 and affine_coupling.py:27-80.
+ * Every operand is an (hi, lo) pair of fp32 arrays: hi = value with the 13 low mantissa bits cleared, lo = value - hi.
+ * Constraints: Cin % 32 == 0; W divides 128 and H*W divides or is a multiple of 128.
+ *
+ * `pre` selects what happens to an accumulator row before it is written:
+ *   FLOWK_PRE_BIAS        y = D + bias
+ *   FLOWK_PRE_GLU_RES_LN  N = 2C: y = LayerNorm_C((D_a + bias_a) * sigmoid(D_b + bias_b) + res) * gamma + beta
+ *                         (GatedConv / GatedAttn gate + residual + norm, mixlogcdf_nn.py:92-101,149-151,257-258)
+ * `out_mask` selects the forms y is written in (Nout = N, or C after the GLU):
+ *   FLOWK_OUT_F32        out_f32[m, Nout]
+ *   FLOWK_OUT_HILO       out_hi/out_lo[m, Nout]                       operand of the next GEMM
+ *   FLOWK_OUT_HILO_POS   out_hi/out_lo[m, Nout] of y + pos[m % HW]    (GatedAttn input, mixlogcdf_nn.py:130-131)
+ *   FLOWK_OUT_HILO_CELU  out_hi/out_lo[m, 2*Nout] of [elu(y) | elu(-y)]   (concat_elu, mixlogcdf_nn.py:8-10)
+ *   FLOWK_OUT_NCHW       out_nchw[b, n, hw]                            (raw parameter tensor for flowk_mixlogcdf_*)
+ * `status` (device int, may be NULL) is set to 1 if an internal barrier wait timed out (never hangs). */
+enum { FLOWK_PRE_BIAS = 0, FLOWK_PRE_GLU_RES_LN = 1 };
+enum { FLOWK_OUT_F32 = 1, FLOWK_OUT_HILO = 2, FLOWK_OUT_HILO_POS = 4, FLOWK_OUT_HILO_CELU = 8, FLOWK_OUT_NCHW = 16 };
+
+typedef struct flowk_conv_gemm_args {
+  const float* a_hi;      /* activations NHWC [B,H,W,Cin] */
+  const float* a_lo;
+  const float* w_hi;      /* weights [N, taps*Cin], (tap, c) order along K */
+  const float* w_lo;
+  const float* bias;      /* [N] or NULL */
+  const float* res;       /* [B*H*W, C] residual (GLU_RES_LN) */
+  const float* gamma;     /* [C] LayerNorm weight */
+  const float* beta;      /* [C] LayerNorm bias */
+  const float* pos;       /* [H*W, C] positional encoding (OUT_HILO_POS) */
+  float* out_f32;
+  float* out_hi;
+  float* out_lo;
+  float* out_nchw;
+  int* status;
+  int B, H, W, Cin, N, taps, pre, out_mask;
+} flowk_conv_gemm_args;
+
+int flowk_conv_gemm(const flowk_conv_gemm_args* args, flowk_stream_t stream);
+
+/* x[b, ch, p] (NCHW, `batch_stride` floats between samples, ch < C) -> NHWC hi/lo [B*HW, C_pad], zero-padded channels. */
+int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, int B, int C, int HW, int C_pad,
+                            float* hi, float* lo, flowk_stream_t stream);
+/* fp32 array -> (hi, lo) operand pair. */
+int flowk_split_hilo(const float* x, float* hi, float* lo, long long n, flowk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

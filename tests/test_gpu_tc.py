@@ -1,0 +1,92 @@
+"""tcgen05 implicit-GEMM conv kernel against torch float64 convolutions."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tc():
+    import flowk  # noqa: F401
+    from flowk import tc as mod
+    return mod
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def run_conv(tc, x, w, bias, taps, out_mask=None, **kw):
+    """x [B,Cin,H,W] (Cin % 32 == 0), w [N,Cin,k,k]; returns dict of outputs."""
+    B, Cin, H, W = x.shape
+    N = w.shape[0]
+    a_hi, a_lo = tc.split_hilo(nhwc(x).reshape(B * H * W, Cin))
+    w_hi, w_lo = tc.conv_weight_operand(w)
+    status = torch.zeros(1, dtype=torch.int32, device=x.device)
+    outs = {"status": status}
+    mask = out_mask if out_mask is not None else tc.OUT_F32
+    pre = kw.pop("pre", tc.PRE_BIAS)
+    nout = N // 2 if pre == tc.PRE_GLU_RES_LN else N
+    if mask & tc.OUT_F32:
+        outs["out_f32"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
+    if mask & (tc.OUT_HILO | tc.OUT_HILO_POS):
+        outs["out_hi"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
+        outs["out_lo"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
+    if mask & tc.OUT_HILO_CELU:
+        outs["out_hi"] = torch.full((B * H * W, 2 * nout), float("nan"), device=x.device)
+        outs["out_lo"] = torch.full((B * H * W, 2 * nout), float("nan"), device=x.device)
+    if mask & tc.OUT_NCHW:
+        outs["out_nchw"] = torch.full((B, N, H, W), float("nan"), device=x.device)
+    tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, mask, bias=bias, **kw, **outs)
+    torch.cuda.synchronize()
+    assert int(status) == 0, "barrier wait timed out inside the kernel"
+    return outs
+
+
+def rel_err(got, ref):
+    return float((got.double() - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("B,Cin,H,W,N,taps", [(2, 32, 8, 16, 16, 1), (4, 64, 16, 16, 96, 1), (64, 96, 16, 16, 288, 1),
+                                              (3, 32, 16, 16, 96, 9), (64, 192, 16, 16, 96, 9), (64, 96, 8, 8, 1176, 9),
+                                              (19, 96, 4, 4, 2352, 9), (5, 32, 2, 2, 24, 9), (2, 64, 32, 32, 48, 9)])
+def test_conv_gemm_matches_fp64(tc, B, Cin, H, W, N, taps):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + N)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn(N, Cin, k, k, generator=g) / (Cin * taps) ** 0.5).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)
+    outs = run_conv(tc, x, w, bias, taps, out_mask=tc.OUT_F32 | tc.OUT_NCHW | tc.OUT_HILO_CELU)
+    got = outs["out_f32"].view(B, H, W, N).permute(0, 3, 1, 2)
+    torch.backends.cudnn.allow_tf32 = False
+    lib32 = rel_err(F.conv2d(x, w, bias, padding=k // 2), ref)        # what the fp32 library conv achieves
+    print("K=%d  tcgen05 3xTF32 rel err %.2e   cuDNN fp32 rel err %.2e" % (Cin * taps, rel_err(got, ref), lib32))
+    assert rel_err(got, ref) < max(6e-6, 4 * lib32), (rel_err(got, ref), lib32)
+    assert rel_err(outs["out_nchw"], ref) < max(6e-6, 4 * lib32)
+    celu = F.elu(torch.cat((nhwc(ref), -nhwc(ref)), dim=-1)).reshape(B * H * W, 2 * N)
+    assert rel_err(outs["out_hi"] + outs["out_lo"], celu) < max(6e-6, 4 * lib32)
+    assert int((outs["out_hi"].view(torch.int32) & 8191).abs().max()) == 0      # hi is exactly TF32-representable
+
+
+@pytest.mark.parametrize("B,C,H,W", [(64, 96, 16, 16), (8, 96, 4, 4), (3, 32, 8, 8), (2, 160, 16, 16)])
+def test_glu_residual_layernorm_epilogue(tc, B, C, H, W):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(B + C)
+    x = torch.randn(B, C, H, W, generator=g).to(dev)
+    w = (torch.randn(2 * C, C, 1, 1, generator=g) / C ** 0.5).to(dev)
+    bias = torch.randn(2 * C, generator=g).to(dev)
+    res = torch.randn(B * H * W, C, generator=g).to(dev)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(dev)
+    beta = torch.randn(C, generator=g).to(dev)
+    pos = torch.randn(H * W, C, generator=g).to(dev)
+    y = nhwc(F.conv2d(x.double(), w.double(), bias.double())).reshape(B * H * W, 2 * C)
+    glu = y[:, :C] * torch.sigmoid(y[:, C:]) + res.double()
+    ref = F.layer_norm(glu, (C,), gamma.double(), beta.double())
+    outs = run_conv(tc, x, w, bias, 1, out_mask=tc.OUT_F32 | tc.OUT_HILO_POS, pre=tc.PRE_GLU_RES_LN, res=res,
+                    gamma=gamma, beta=beta, pos=pos)
+    assert rel_err(outs["out_f32"], ref) < 1e-5, rel_err(outs["out_f32"], ref)
+    ref_pos = ref + pos.double().repeat(B, 1)
+    assert rel_err(outs["out_hi"] + outs["out_lo"], ref_pos) < 1e-5
