@@ -50,7 +50,7 @@ class ConvGemmArgs(ctypes.Structure):
     """Mirror of `flowk_conv_gemm_args` (include/flowk.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("a_hi", "a_lo", "w_hi", "w_lo", "bias", "res", "gamma", "beta", "pos",
-                 "out_f32", "out_hi", "out_lo", "out_nchw", "status")] + \
+                 "out_f32", "out_hi", "out_lo", "out_nchw", "status", "trace")] + \
                [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")]
 
 

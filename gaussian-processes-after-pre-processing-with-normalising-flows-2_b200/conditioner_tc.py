@@ -1,0 +1,148 @@
+"""Tensor-core (tcgen05) execution of the coupling conditioners, inference / no-grad mode.
+
+`mixlogcdf_nn_raw(nn_module, x_id)` computes what `NN.forward_raw` computes (flow_modules/mixlogcdf_nn.py:64-69:
+in_conv -> 10 x ConvAttnBlock -> out_conv) as a chain of `flowk_conv_gemm` launches over NHWC activations:
+
+    per block   G1 conv3x3  concat_elu(x)      -> concat_elu(conv + bias)                         (hi/lo operand)
+                G2 gate1x1                      -> LayerNorm(GLU + x)          = x1 (+ pos. enc.)   (fp32 + operand)
+                G3 in_proj  x1 + pos            -> (k | v | q)                                      (fp32)
+                   attention  softmax(q k^T / sqrt(d)) v   per image and head
+                G4 gate     attention output    -> LayerNorm(GLU + x1)         = x2, concat_elu(x2) (fp32 + operand)
+
+Every nonlinearity lives in a GEMM epilogue, so a block is 4 GEMM launches + attention.  Weight-normalised,
+re-laid-out, hi/lo-split weights are cached per parameter version.
+"""
+import torch
+
+from . import _lib, tc
+
+ENABLED = True      # set False to force the torch/cuDNN conditioner (used by tests to A/B the two paths)
+
+
+def supported(channels, h, w):
+    """Shapes the tcgen05 path takes: channel counts that are multiples of 32 (K blocks) and 16 (MMA N), spatial
+    tiles that pack into 128-row M tiles."""
+    if channels % 32:
+        return False
+    if w > 128 or 128 % w:
+        return False
+    hw = h * w
+    return (hw % 128 == 0) if hw >= 128 else (128 % hw == 0)
+
+
+class _Cache:
+    """Per-module operand cache keyed on the parameters' (data_ptr, version)."""
+
+    def __init__(self):
+        self.key = None
+        self.value = None
+
+    def get(self, params, build):
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key:
+            with torch.no_grad():
+                self.value = build()
+            self.key = key
+        return self.value
+
+
+def _wn_operand(core):
+    """(w_hi, w_lo, bias) of a weight-normed conv / linear (`_WeightNormed`)."""
+    w_hi, w_lo = tc.conv_weight_operand(core.normed_weight())
+    bias = None if core.bias is None else core.bias.detach().contiguous()
+    return w_hi, w_lo, bias
+
+
+def _nn_operands(nn_module):
+    ops = {"in": _wn_operand(nn_module.in_conv.conv), "out": _wn_operand(nn_module.out_conv.conv), "blocks": []}
+    for blk in nn_module.mid_convs:
+        d = {"conv": _wn_operand(blk.conv.conv.conv), "gate": _wn_operand(blk.conv.gate.conv),
+             "ln1": (blk.norm_1.weight.detach().contiguous(), blk.norm_1.bias.detach().contiguous())}
+        if blk.attn is not None:
+            d["in_proj"] = _wn_operand(blk.attn.in_proj)
+            d["attn_gate"] = _wn_operand(blk.attn.gate)
+            d["ln2"] = (blk.norm_2.weight.detach().contiguous(), blk.norm_2.bias.detach().contiguous())
+            d["heads"] = blk.attn.num_heads
+        ops["blocks"].append(d)
+    return ops
+
+
+def mixlogcdf_nn_raw(nn_module, x_id, status=None):
+    """x_id: [B,c,H,W] channel slice of a contiguous NCHW tensor.  Returns raw [B,(2+3K)c,H,W] fp32."""
+    assert not torch.is_grad_enabled() or not any(p.requires_grad for p in nn_module.parameters()), \
+        "tcgen05 conditioner path is inference-only"
+    B, c, H, W = x_id.shape
+    dev = x_id.device
+    M, HW = B * H * W, H * W
+    C = nn_module.in_conv.conv.weight_v.shape[0]
+    cache = nn_module.__dict__.setdefault("_tc_cache", _Cache())
+    ops = cache.get(list(nn_module.parameters()), lambda: _nn_operands(nn_module))
+
+    def buf(*shape):
+        return torch.empty(*shape, device=dev, dtype=torch.float32)
+
+    cin0 = ops["in"][0].shape[1] // 9
+    a_hi, a_lo = tc.nchw_to_nhwc_hilo(x_id, cin0)
+    x = buf(M, C)
+    nxt_hi, nxt_lo = buf(M, 2 * C), buf(M, 2 * C)
+    w_hi, w_lo, bias = ops["in"]
+    tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, cin0, C, 9, tc.PRE_BIAS, tc.OUT_F32 | tc.OUT_HILO_CELU, bias=bias,
+                 out_f32=x, out_hi=nxt_hi, out_lo=nxt_lo, status=status)
+    nblocks = len(ops["blocks"])
+    for bi, blk in enumerate(ops["blocks"]):
+        last = bi == nblocks - 1
+        # G1: conv3x3 on concat_elu(x) -> concat_elu(. + bias)
+        c1_hi, c1_lo = buf(M, 2 * C), buf(M, 2 * C)
+        w_hi, w_lo, bias = blk["conv"]
+        tc.conv_gemm(nxt_hi, nxt_lo, w_hi, w_lo, B, H, W, 2 * C, C, 9, tc.PRE_BIAS, tc.OUT_HILO_CELU, bias=bias,
+                     out_hi=c1_hi, out_lo=c1_lo, status=status)
+        # G2: gate 1x1 -> GLU + x -> LayerNorm
+        w_hi, w_lo, bias = blk["gate"]
+        x1 = buf(M, C)
+        has_attn = "in_proj" in blk
+        if has_attn:
+            p_hi, p_lo = buf(M, C), buf(M, C)
+            pos = nn_module.mid_convs[bi].attn._pos_enc(HW, C, dev).reshape(HW, C).contiguous()
+            tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN,
+                         tc.OUT_F32 | tc.OUT_HILO_POS, bias=bias, res=x, gamma=blk["ln1"][0], beta=blk["ln1"][1], pos=pos,
+                         out_f32=x1, out_hi=p_hi, out_lo=p_lo, status=status)
+            # G3: in_proj -> (k | v | q)
+            w_hi, w_lo, _ = blk["in_proj"]
+            qkv = buf(M, 3 * C)
+            tc.conv_gemm(p_hi, p_lo, w_hi, w_lo, B, H, W, C, 3 * C, 1, tc.PRE_BIAS, tc.OUT_F32, out_f32=qkv,
+                         status=status)
+            heads = blk["heads"]
+            d = C // heads
+            t = qkv.view(B, HW, 3, heads, d)
+            k, v, q = t[:, :, 0].permute(0, 2, 1, 3), t[:, :, 1].permute(0, 2, 1, 3), t[:, :, 2].permute(0, 2, 1, 3)
+            att = torch.softmax((q * (d ** -0.5)) @ k.transpose(-1, -2), dim=-1) @ v          # [B, heads, HW, d]
+            att = att.permute(0, 2, 1, 3).reshape(M, C).contiguous()
+            t_hi, t_lo = tc.split_rows(att)
+            # G4: attention gate -> GLU + x1 -> LayerNorm
+            w_hi, w_lo, bias = blk["attn_gate"]
+            x2 = buf(M, C)
+            if last:
+                nxt_hi, nxt_lo = buf(M, C), buf(M, C)
+            else:
+                nxt_hi, nxt_lo = buf(M, 2 * C), buf(M, 2 * C)
+            tc.conv_gemm(t_hi, t_lo, w_hi, w_lo, B, H, W, C, 2 * C, 1, tc.PRE_GLU_RES_LN,
+                         tc.OUT_F32 | (tc.OUT_HILO if last else tc.OUT_HILO_CELU), bias=bias, res=x1,
+                         gamma=blk["ln2"][0], beta=blk["ln2"][1], out_f32=x2, out_hi=nxt_hi, out_lo=nxt_lo, status=status)
+            x = x2
+        else:
+            if last:
+                nxt_hi, nxt_lo = buf(M, C), buf(M, C)
+            else:
+                nxt_hi, nxt_lo = buf(M, 2 * C), buf(M, 2 * C)
+            tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN,
+                         tc.OUT_F32 | (tc.OUT_HILO if last else tc.OUT_HILO_CELU), bias=bias, res=x,
+                         gamma=blk["ln1"][0], beta=blk["ln1"][1], out_f32=x1, out_hi=nxt_hi, out_lo=nxt_lo, status=status)
+            x = x1
+    if nblocks == 0:                                   # out_conv takes the plain activation
+        nxt_hi, nxt_lo = tc.split_rows(x)
+    w_hi, w_lo, bias = ops["out"]
+    n_out = w_hi.shape[0]
+    raw = buf(B, n_out, H, W)
+    tc.conv_gemm(nxt_hi, nxt_lo, w_hi, w_lo, B, H, W, C, n_out, 9, tc.PRE_BIAS, tc.OUT_NCHW, bias=bias, out_nchw=raw,
+                 status=status)
+    return raw

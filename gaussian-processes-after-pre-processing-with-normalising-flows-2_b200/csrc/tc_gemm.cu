@@ -27,7 +27,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                 // fp32 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 8;                   // tf32: 32 bytes per MMA along K
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 16;                // 4 per TMEM lane group: they split the column chunks
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_CHUNKS = 2;
 
 // --------------------------------------------------------------------------------------------------
@@ -150,7 +151,9 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
   lo = x - hi;
 }
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// elu(x) = x > 0 ? x : e^x - 1.  The result feeds a GEMM operand, so what matters is ABSOLUTE error (~1e-7 here).
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : ex2_fast(x * kLog2e) - 1.f; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + ex2_fast(-x * kLog2e)); }
 
 // --------------------------------------------------------------------------------------------------
 // kernel parameters (device view)
@@ -164,6 +167,7 @@ struct Params {
   int wt, ht, bt;                  // M tile = bt images x ht rows x wt (= W) columns
   int n_chunk, n_chunks;           // columns per MMA (<=256, %16) and MMAs per k-step; CTA covers n_chunk*n_chunks columns
   int tmem_cols, stages;
+  int bar_offset;                  // byte offset of the mbarriers: past the pipeline stages AND the epilogue staging area
   int pre, out_mask;
   const float* bias;               // [N] or null
   const float* res;                // [M, C] residual (PRE_GLU_RES_LN), C = N/2
@@ -175,6 +179,7 @@ struct Params {
   float* out_lo;
   float* out_nchw;                 // [B, N, HW]
   int* status;                     // set to 1 if a barrier wait timed out
+  long long* trace;                // optional [8] clock64 stamps of CTA (0,0): setup, first full, last mma, epi start, epi end
 };
 
 template <int PRE>
@@ -187,7 +192,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_tile_bytes = p.n_chunk * p.n_chunks * BLOCK_K * 4;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * w_tile_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -216,6 +221,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool tracing = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+  if (tracing && threadIdx.x == 0) p.trace[0] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -253,6 +260,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph, failed);
         tc_fence_after();
+        if (tracing && kb == 0) p.trace[1] = clock64();
+        if (tracing && kb == num_kb - 1) p.trace[2] = clock64();
         const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t a_lo = a_hi + A_TILE_BYTES;
         const uint32_t w_hi = a_hi + 2 * A_TILE_BYTES;
@@ -275,122 +284,170 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       umma_commit(tmem_full_bar);                                    // accumulator complete
     }
   } else {
-    // ===================== epilogue: thread == accumulator row =====================
+    // ===================== epilogue =====================
+    // TMEM hands every thread one accumulator ROW (lane).  Writing rows straight to row-major global memory would
+    // make each warp store touch 32 different sectors, so tiles go through shared memory (the idle pipeline
+    // stages) and are written back with lane == COLUMN: every warp store is one contiguous 128-byte segment, and
+    // the per-column vectors (bias, LayerNorm gamma/beta, positional encoding) become coalesced per-lane loads.
+    // 16 epilogue warps: the 4 warps that share a TMEM lane group (warp id % 4) split the column chunks.
     mbar_wait(tmem_full_bar, 0, failed);
     tc_fence_after();
+    if (tracing && threadIdx.x == 64) p.trace[3] = clock64();
     const int lane_grp = warp & 3;                                   // TMEM lanes this warp may touch
-    const int row = lane_grp * 32 + lane;
-    const int m = m_tile * BLOCK_M + row;
-    const bool valid = m < p.M;
+    const int sub = (warp - 2) >> 2;                                 // 0..3 among the warps of this lane group
+    const int slab_row0 = m_tile * BLOCK_M + lane_grp * 32;          // first global row of the 32-row slab
     const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const int ncols_cta = p.n_chunk * p.n_chunks;
 
     if (PRE == PRE_BIAS) {
-      const int hw = valid ? m % p.HW : 0, img = valid ? m / p.HW : 0;
-      for (int j = 0; j < ncols_cta; j += 16) {
-        float v[16];
-        tmem_ld16(trow + j, v);
-        const int n0 = n_base + j;
-        if (n0 >= p.N) break;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-        if (!valid) continue;
-        const int nvalid = p.N - n0 < 16 ? p.N - n0 : 16;
-        if (p.out_mask & OUT_F32) {
-          float* o = p.out_f32 + (size_t)m * p.N + n0;
-          if (nvalid == 16 && (p.N & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-            for (int i = 0; i < nvalid; ++i) o[i] = v[i];
-          }
-        }
-        if (p.out_mask & OUT_HILO) {
-          float* oh = p.out_hi + (size_t)m * p.N + n0;
-          float* ol = p.out_lo + (size_t)m * p.N + n0;
-          for (int i = 0; i < nvalid; ++i) split_tf32(v[i], oh[i], ol[i]);
-        }
-        if (p.out_mask & OUT_HILO_CELU) {                            // concat_elu: [elu(y) | elu(-y)], width 2N
-          float* oh = p.out_hi + (size_t)m * 2 * p.N + n0;
-          float* ol = p.out_lo + (size_t)m * 2 * p.N + n0;
-          for (int i = 0; i < nvalid; ++i) {
-            split_tf32(elu1(v[i]), oh[i], ol[i]);
-            split_tf32(elu1(-v[i]), oh[p.N + i], ol[p.N + i]);
-          }
-        }
-        if (p.out_mask & OUT_NCHW) {
+      if (p.out_mask & OUT_NCHW) {
+        // [b, n, hw] output: consecutive rows are consecutive hw, so the row-per-thread mapping IS the coalesced one
+        const int m = slab_row0 + lane;
+        const bool valid = m < p.M;
+        const int hw = valid ? m % p.HW : 0, img = valid ? m / p.HW : 0;
+        for (int j = sub * 16; j < ncols_cta; j += 16 * (EPI_WARPS / 4)) {
+          const int n0 = n_base + j;
+          if (n0 >= p.N) break;
+          float v[16];
+          tmem_ld16(trow + j, v);
+          if (!valid) continue;
           float* o = p.out_nchw + ((size_t)img * p.N + n0) * p.HW + hw;
-          for (int i = 0; i < nvalid; ++i) o[(size_t)i * p.HW] = v[i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + i < p.N) o[(size_t)i * p.HW] = v[i] + (p.bias ? __ldg(p.bias + n0 + i) : 0.f);
+        }
+      }
+      if (p.out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_CELU)) {
+        float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);      // [32 rows][33] per warp
+        for (int j = sub * 32; j < ncols_cta; j += 32 * (EPI_WARPS / 4)) {
+          if (n_base + j >= p.N) break;
+          float v[16];
+          tmem_ld16(trow + j, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tile[lane * 33 + i] = v[i];
+          if (j + 16 < ncols_cta) {
+            tmem_ld16(trow + j + 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tile[lane * 33 + 16 + i] = v[i];
+          }
+          __syncwarp();
+          const int n = n_base + j + lane;                           // this lane's output column
+          const bool ncol_ok = n < p.N && (j + lane) < ncols_cta;
+          const float bv = (p.bias && ncol_ok) ? __ldg(p.bias + n) : 0.f;
+          if (ncol_ok) {
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float y[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) y[u] = tile[(r0 + u) * 33 + lane] + bv;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int m = slab_row0 + r0 + u;
+                if (m < p.M) {
+                  const size_t o = (size_t)m * p.N + n;
+                  if (p.out_mask & OUT_F32) p.out_f32[o] = y[u];
+                  if (p.out_mask & OUT_HILO) split_tf32(y[u], p.out_hi[o], p.out_lo[o]);
+                  if (p.out_mask & OUT_HILO_CELU) {                  // concat_elu: [elu(y) | elu(-y)], width 2N
+                    const size_t o2 = (size_t)m * 2 * p.N + n;
+                    split_tf32(elu1(y[u]), p.out_hi[o2], p.out_lo[o2]);
+                    split_tf32(elu1(-y[u]), p.out_hi[o2 + p.N], p.out_lo[o2 + p.N]);
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
         }
       }
     } else {
-      // GLU over [a | b] halves, + residual, LayerNorm over C = N/2 (mixlogcdf_nn.py:92-101, :257-258, :149-151)
+      // GLU over the [a | b] halves, + residual, LayerNorm over C = N/2
+      // (mixlogcdf_nn.py:92-101 ConvAttnBlock, :257-258 GatedConv gate, :149-151 GatedAttn gate)
       const int C = p.N >> 1;
-      const uint32_t tb = trow + C;                                    // b half: columns C..2C-1 in both chunkings
-      const float* rrow = p.res + (size_t)(valid ? m : 0) * C;
-      float sum = 0.f;
-      for (int j = 0; j < C; j += 16) {
-        float a[16], g[16];
+      const int pitch = C + 1;                                       // odd pitch: conflict-free in both mappings
+      float* slab = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch + 64);   // shared by the 4 warps of the group
+      float* stats = slab + 32 * pitch;                              // [32][2] mean, rstd
+      const int bar_id = 1 + lane_grp;                               // named barrier of this lane group (128 threads)
+      // 1. lane == row (straight out of TMEM): g = (a + bias_a) * sigmoid(b + bias_b)  -> slab[row][col]
+      for (int j = sub * 16; j < C; j += 16 * (EPI_WARPS / 4)) {
+        float a[16], b[16];
         tmem_ld16(trow + j, a);
-        tmem_ld16(tb + j, g);
+        tmem_ld16(trow + C + j, b);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float av = a[i] + __ldg(p.bias + j + i), bv = g[i] + __ldg(p.bias + C + j + i);
-          const float r = av / (1.f + expf(-bv)) + __ldg(rrow + j + i);
-          a[i] = r;
-          sum += r;
-        }
-        tmem_st16(trow + j, a);
+        for (int i = 0; i < 16; ++i)
+          slab[lane * pitch + j + i] = (a[i] + __ldg(p.bias + j + i)) * sigmoid_fast(b[i] + __ldg(p.bias + C + j + i));
       }
-      const float mean = sum / (float)C;
-      float var = 0.f;
-      for (int j = 0; j < C; j += 16) {
-        float a[16];
-        tmem_ld16(trow + j, a);
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      // 2. lane == column: add the residual with coalesced loads
+      for (int q = sub; q * 32 < C; q += EPI_WARPS / 4) {
+        const int col = q * 32 + lane;
+        if (col < C) {
+          for (int r0 = 0; r0 < 32; r0 += 8) {
+            float res[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) var += (a[i] - mean) * (a[i] - mean);
+            for (int u = 0; u < 8; ++u) {
+              const int m = slab_row0 + r0 + u;
+              res[u] = m < p.M ? __ldg(p.res + (size_t)m * C + col) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) slab[(r0 + u) * pitch + col] += res[u];
+          }
+        }
       }
-      const float rstd = rsqrtf(var / (float)C + 1e-5f);
-      const int hw = valid ? m % p.HW : 0;
-      for (int j = 0; j < C; j += 16) {
-        float a[16];
-        tmem_ld16(trow + j, a);
-        if (!valid) continue;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = (a[i] - mean) * rstd * __ldg(p.gamma + j + i) + __ldg(p.beta + j + i);
-        if (p.out_mask & OUT_F32) {
-          float* o = p.out_f32 + (size_t)m * C + j;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      // 3. row statistics, two-pass: warp `sub` owns rows sub*8..sub*8+7, four lanes per row
+      {
+        const int r = sub * 8 + (lane >> 2), part = lane & 3;
+        const float* rowp = slab + r * pitch;
+        float sum = 0.f;
+        for (int c = part; c < C; c += 4) sum += rowp[c];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float mean = sum / (float)C;
+        float var = 0.f;
+        for (int c = part; c < C; c += 4) var = fmaf(rowp[c] - mean, rowp[c] - mean, var);
+        var += __shfl_xor_sync(0xffffffffu, var, 1);
+        var += __shfl_xor_sync(0xffffffffu, var, 2);
+        if (part == 0) {
+          stats[r * 2] = mean;
+          stats[r * 2 + 1] = rsqrtf(var / (float)C + 1e-5f);
         }
-        if (p.out_mask & OUT_HILO) {
-          float* oh = p.out_hi + (size_t)m * C + j;
-          float* ol = p.out_lo + (size_t)m * C + j;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      // 4. lane == column: normalise and emit every requested form, coalesced
+      for (int q = sub; q * 32 < C; q += EPI_WARPS / 4) {
+        const int col = q * 32 + lane;
+        if (col >= C) continue;
+        const float ga = __ldg(p.gamma + col), be = __ldg(p.beta + col);
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          float y[8], pe[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_tf32(a[i], oh[i], ol[i]);
-        }
-        if (p.out_mask & OUT_HILO_POS) {
-          float* oh = p.out_hi + (size_t)m * C + j;
-          float* ol = p.out_lo + (size_t)m * C + j;
-          const float* pe = p.pos + (size_t)hw * C + j;
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + u, m = slab_row0 + r;
+            y[u] = (slab[r * pitch + col] - stats[r * 2]) * stats[r * 2 + 1] * ga + be;
+            pe[u] = ((p.out_mask & OUT_HILO_POS) && m < p.M) ? __ldg(p.pos + (size_t)(m % p.HW) * C + col) : 0.f;
+          }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_tf32(a[i] + __ldg(pe + i), oh[i], ol[i]);
-        }
-        if (p.out_mask & OUT_HILO_CELU) {
-          float* oh = p.out_hi + (size_t)m * 2 * C + j;
-          float* ol = p.out_lo + (size_t)m * 2 * C + j;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            split_tf32(elu1(a[i]), oh[i], ol[i]);
-            split_tf32(elu1(-a[i]), oh[C + i], ol[C + i]);
+          for (int u = 0; u < 8; ++u) {
+            const int m = slab_row0 + r0 + u;
+            if (m < p.M) {
+              const size_t o = (size_t)m * C + col;
+              if (p.out_mask & OUT_F32) p.out_f32[o] = y[u];
+              if (p.out_mask & OUT_HILO) split_tf32(y[u], p.out_hi[o], p.out_lo[o]);
+              if (p.out_mask & OUT_HILO_POS) split_tf32(y[u] + pe[u], p.out_hi[o], p.out_lo[o]);
+              if (p.out_mask & OUT_HILO_CELU) {
+                const size_t o2 = (size_t)m * 2 * C + col;
+                split_tf32(elu1(y[u]), p.out_hi[o2], p.out_lo[o2]);
+                split_tf32(elu1(-y[u]), p.out_hi[o2 + C], p.out_lo[o2 + C]);
+              }
+            }
           }
         }
       }
     }
   }
-
+  if (tracing && threadIdx.x == 64) p.trace[4] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (tracing && threadIdx.x == 0) p.trace[5] = clock64();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (threadIdx.x == 0 && *failed && p.status) *p.status = 1;
 }
@@ -513,6 +570,7 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   p.out_lo = a->out_lo;
   p.out_nchw = a->out_nchw;
   p.status = a->status;
+  p.trace = a->trace;
   int n_tiles;
   if (a->pre == PRE_GLU_RES_LN) {
     const int C = N / 2;
@@ -535,8 +593,16 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   int stages = (int)((220 * 1024 - 2048) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 1) return FLOWK_ERR_SHAPE;
+  // epilogue staging (reuses the pipeline stages once the accumulator is complete)
+  size_t epi_bytes = (size_t)EPI_WARPS * 32 * 33 * sizeof(float);
+  if (a->pre == PRE_GLU_RES_LN) epi_bytes = 4 * (32 * (N / 2 + 1) + 64) * sizeof(float);
+  while (stages > 1 && (size_t)stages * stage_bytes + 2048 > 227 * 1024) --stages;
+  size_t region = (size_t)stages * stage_bytes;
+  if (epi_bytes > region) region = (epi_bytes + 1023) / 1024 * 1024;
+  if (region + 2048 > 227 * 1024) return FLOWK_ERR_SHAPE;
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+  p.bar_offset = (int)region;
+  const size_t smem_bytes = region + 1024 + 256;
 
   alignas(64) CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
   const int Ktot = a->taps * Cin;

@@ -199,6 +199,13 @@ class NN(nn.Module):
         self.rescale = _WNRescale(in_channels)
 
     def forward_raw(self, x, aux=None):
+        """Un-split out_conv output [B,(2+3K)c,H,W].  In inference mode (eval, autograd off) on supported shapes
+        the whole stack runs as tcgen05 implicit GEMMs (flowk.conditioner_tc); otherwise (training: dropout and
+        autograd; odd channel counts) through the torch layers below."""
+        from .. import conditioner_tc
+        if (conditioner_tc.ENABLED and aux is None and not self.training and not torch.is_grad_enabled()
+                and x.is_cuda and conditioner_tc.supported(self.in_conv.conv.weight_v.shape[0], x.size(2), x.size(3))):
+            return conditioner_tc.mixlogcdf_nn_raw(self, x)
         x = self.in_conv(x)
         for block in self.mid_convs:
             x = block(x, aux)

@@ -37,9 +37,9 @@ def _p(t):
 
 
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias=None, res=None, gamma=None,
-              beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None):
+              beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None, trace=None):
     args = _lib.ConvGemmArgs(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(res), _p(gamma), _p(beta), _p(pos),
-                             _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status),
+                             _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status), _p(trace),
                              B, H, W, Cin, N, taps, pre, out_mask)
     _lib.call("flowk_conv_gemm", ctypes.addressof(args), _stream())
 

@@ -153,6 +153,7 @@ typedef struct flowk_conv_gemm_args {
   float* out_lo;
   float* out_nchw;
   int* status;
+  long long* trace;       /* optional device [8]: clock64 stamps of CTA (0,0) for profiling; NULL in production */
   int B, H, W, Cin, N, taps, pre, out_mask;
 } flowk_conv_gemm_args;
 

@@ -470,3 +470,30 @@ def test_flowstep_backward_vs_oracle(F, golden):
         parity(p.grad, ref, rel=5e-4, what="grad " + name)
         checked += 1
     assert checked > 20
+
+
+def test_cfg2_architecture_vs_oracle(F):
+    """The BASELINE cfg2 architecture (MixLogCDF, L=3, K=4, C=96, 10 blocks) at a small batch: the whole GPU stack
+    (tcgen05 conditioners + fused flow kernels) against the CPU oracle with the same weights."""
+    import numpy as np
+    torch.manual_seed(0)
+    np.random.seed(0)
+    B = 4
+    model = F.marscf.MarScfFlow(B, (32, 32, 3), "mixlogcdf", 3, 4, 96).to(dev())
+    gen = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 3, 32, 32, generator=gen) - 0.5
+    noise = torch.rand(B, 3, 32, 32, generator=gen)
+    model.train()
+    with torch.no_grad():
+        model(x.to(dev()), noise=noise.to(dev()))
+    model.eval()
+    with torch.no_grad():
+        z, nll, _ = model(x.to(dev()), noise=noise.to(dev()))
+        zf, outs, ld = model.flow.encode_latents((x + noise / 256.0).to(dev()), torch.zeros(B, device=dev()))
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    z_ref, outs_ref, ld_ref, nll_ref = O.normal_flow(sd, x, noise, 3, 4, "mixlogcdf")
+    parity(z, z_ref, what="z")
+    for a, b in zip(outs, outs_ref):
+        parity(a, b, what="z2")
+    parity(ld, ld_ref - float(-math.log(256.0) * 3072), what="logdet")
+    assert float((nll.cpu() - nll_ref).abs().max()) < 1e-3

@@ -90,3 +90,32 @@ def test_glu_residual_layernorm_epilogue(tc, B, C, H, W):
     assert rel_err(outs["out_f32"], ref) < 1e-5, rel_err(outs["out_f32"], ref)
     ref_pos = ref + pos.double().repeat(B, 1)
     assert rel_err(outs["out_hi"] + outs["out_lo"], ref_pos) < 1e-5
+
+
+@pytest.mark.parametrize("c,C,H,W,B,blocks", [(6, 96, 16, 16, 64, 2), (12, 96, 8, 8, 64, 2), (24, 96, 4, 4, 64, 2),
+                                              (6, 32, 16, 16, 3, 1), (6, 64, 32, 32, 2, 1)])
+def test_conditioner_tc_matches_torch_path(tc, c, C, H, W, B, blocks):
+    """NN.forward_raw through the tcgen05 chain vs the torch/cuDNN fp32 layers (same module, same weights)."""
+    from flowk import conditioner_tc
+    from flowk.flow_modules.mixlogcdf_nn import NN
+    torch.manual_seed(c + C)
+    dev = torch.device("cuda:0")
+    net = NN(c, C, blocks, 32, 0.2).to(dev).eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.02)
+        x = torch.randn(B, 2 * c, H, W, device=dev)
+        x_id = x[:, c:]
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        got = conditioner_tc.mixlogcdf_nn_raw(net, x_id, status=status)
+        conditioner_tc.ENABLED = False
+        try:
+            ref = net.forward_raw(x_id)
+            ref64 = net.double().forward_raw(x_id.double())
+        finally:
+            conditioner_tc.ENABLED = True
+            net.float()
+    assert int(status) == 0
+    e_tc, e_lib = rel_err(got, ref64), rel_err(ref, ref64)
+    print("conditioner c=%d C=%d %dx%d: tcgen05 rel err %.2e, torch fp32 rel err %.2e" % (c, C, H, W, e_tc, e_lib))
+    assert e_tc < max(2e-5, 4 * e_lib)
