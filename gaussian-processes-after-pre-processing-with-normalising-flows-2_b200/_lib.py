@@ -43,6 +43,7 @@ SIGNATURES = {
     "flowk_conv_gemm": ([ctypes.c_void_p, _st], _i),
     "flowk_nchw_to_nhwc_hilo": ([_fp, ctypes.c_longlong, _i, _i, _i, _i, _fp, _fp, _st], _i),
     "flowk_split_hilo": ([_fp, _fp, _fp, ctypes.c_longlong, _st], _i),
+    "flowk_attention": ([_fp, _fp, _fp, _i, _i, _i, _i, _st], _i),
 }
 
 
@@ -66,7 +67,7 @@ DIMS = {
     "flowk_affine_coupling_bwd": slice(6, 9),
     "flowk_mixlogcdf_fwd": slice(7, 10), "flowk_mixlogcdf_inv": slice(7, 10), "flowk_mixlogcdf_bwd": slice(8, 11),
     "flowk_mixture_log_cdf": slice(5, 8), "flowk_mixture_log_pdf": slice(5, 8), "flowk_mixture_inv_cdf": slice(5, 8),
-    "flowk_nchw_to_nhwc_hilo": slice(2, 6), "flowk_split_hilo": slice(3, 4),
+    "flowk_nchw_to_nhwc_hilo": slice(2, 6), "flowk_split_hilo": slice(3, 4), "flowk_attention": slice(3, 7),
 }
 
 

@@ -112,12 +112,14 @@ def mixlogcdf_nn_raw(nn_module, x_id, status=None):
             tc.conv_gemm(p_hi, p_lo, w_hi, w_lo, B, H, W, C, 3 * C, 1, tc.PRE_BIAS, tc.OUT_F32, out_f32=qkv,
                          status=status)
             heads = blk["heads"]
-            d = C // heads
-            t = qkv.view(B, HW, 3, heads, d)
-            k, v, q = t[:, :, 0].permute(0, 2, 1, 3), t[:, :, 1].permute(0, 2, 1, 3), t[:, :, 2].permute(0, 2, 1, 3)
-            att = torch.softmax((q * (d ** -0.5)) @ k.transpose(-1, -2), dim=-1) @ v          # [B, heads, HW, d]
-            att = att.permute(0, 2, 1, 3).reshape(M, C).contiguous()
-            t_hi, t_lo = tc.split_rows(att)
+            if tc.attention_supported(HW, C, heads):
+                t_hi, t_lo = tc.attention(qkv, B, HW, C, heads)
+            else:                                                     # odd head sizes: library matmuls
+                d = C // heads
+                t = qkv.view(B, HW, 3, heads, d)
+                k, v, q = (t[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+                att = torch.softmax((q * (d ** -0.5)) @ k.transpose(-1, -2), dim=-1) @ v      # [B, heads, HW, d]
+                t_hi, t_lo = tc.split_rows(att.permute(0, 2, 1, 3).reshape(M, C).contiguous())
             # G4: attention gate -> GLU + x1 -> LayerNorm
             w_hi, w_lo, bias = blk["attn_gate"]
             x2 = buf(M, C)

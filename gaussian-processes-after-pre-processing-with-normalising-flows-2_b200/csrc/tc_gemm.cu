@@ -168,6 +168,7 @@ struct Params {
   int n_chunk, n_chunks;           // columns per MMA (<=256, %16) and MMAs per k-step; CTA covers n_chunk*n_chunks columns
   int tmem_cols, stages;
   int bar_offset;                  // byte offset of the mbarriers: past the pipeline stages AND the epilogue staging area
+  int dxsplit, a_slots, w_slots;   // 3x3 "dx-split" mode: one accumulator per column shift, activation tile reused by 3 taps
   int pre, out_mask;
   const float* bias;               // [N] or null
   const float* res;                // [M, C] residual (PRE_GLU_RES_LN), C = N/2
@@ -179,7 +180,7 @@ struct Params {
   float* out_lo;
   float* out_nchw;                 // [B, N, HW]
   int* status;                     // set to 1 if a barrier wait timed out
-  long long* trace;                // optional [8] clock64 stamps of CTA (0,0): setup, first full, last mma, epi start, epi end
+  long long* trace;                // optional [16] clock64 stamps of CTA (0,0): setup, first full, last mma, epi start, epi end
 };
 
 template <int PRE>
@@ -192,9 +193,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_tile_bytes = p.n_chunk * p.n_chunks * BLOCK_K * 4;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * w_tile_bytes;
+  // normal mode:   full[stages], empty[stages], tmem_full
+  // dx-split mode:  a_full[a_slots], a_empty[a_slots], w_full[w_slots], w_empty[w_slots], tmem_full
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
-  uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint64_t* empty_bar = full_bar + (p.dxsplit ? p.a_slots : p.stages);
+  uint64_t* wfull_bar = empty_bar + p.a_slots;
+  uint64_t* wempty_bar = wfull_bar + p.w_slots;
+  uint64_t* tmem_full_bar = p.dxsplit ? wempty_bar + p.w_slots : empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   volatile int* failed = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
@@ -205,9 +210,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
   if (threadIdx.x == 0) {
     *failed = 0;
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    if (p.dxsplit) {
+      for (int s = 0; s < p.a_slots; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < p.w_slots; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
+    } else {
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -232,6 +239,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       int b0, h0;
       if (p.bt > 1) { b0 = m_tile * p.bt; h0 = 0; }
       else { b0 = m_tile / tiles_per_img; h0 = (m_tile % tiles_per_img) * p.ht; }
+      if (p.dxsplit) {
+        // group g = (dy, channel block): ONE activation tile (rows shifted by dy, columns unshifted) feeds the three
+        // taps (dy, dx = -1, 0, +1); each tap streams its own weight tile.  Activation traffic / 3.
+        uint8_t* w_ring = smem + (size_t)p.a_slots * 2 * A_TILE_BYTES;
+        const int groups = 3 * p.kblocks_per_tap;
+        int wi = 0;
+        for (int g = 0; g < groups; ++g) {
+          const int dyi = g / p.kblocks_per_tap, cb = g % p.kblocks_per_tap;
+          const int sa = g % p.a_slots;
+          mbar_wait(&empty_bar[sa], (((uint32_t)(g / p.a_slots)) & 1u) ^ 1u, failed);
+          uint8_t* at = smem + (size_t)sa * 2 * A_TILE_BYTES;
+          mbar_expect_tx(&full_bar[sa], 2u * A_TILE_BYTES);
+          tma_load_4d(at, &map_a_hi, &full_bar[sa], cb * BLOCK_K, 0, h0 + dyi - 1, b0);
+          tma_load_4d(at + A_TILE_BYTES, &map_a_lo, &full_bar[sa], cb * BLOCK_K, 0, h0 + dyi - 1, b0);
+          for (int dxi = 0; dxi < 3; ++dxi, ++wi) {
+            const int sw = wi % p.w_slots;
+            mbar_wait(&wempty_bar[sw], (((uint32_t)(wi / p.w_slots)) & 1u) ^ 1u, failed);
+            uint8_t* wt = w_ring + (size_t)sw * 2 * w_tile_bytes;
+            mbar_expect_tx(&wfull_bar[sw], 2u * (uint32_t)w_tile_bytes);
+            const int kcol = ((dyi * 3 + dxi) * p.kblocks_per_tap + cb) * BLOCK_K;
+            tma_load_2d(wt, &map_w_hi, &wfull_bar[sw], kcol, n_base);
+            tma_load_2d(wt + w_tile_bytes, &map_w_lo, &wfull_bar[sw], kcol, n_base);
+          }
+        }
+      } else
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
@@ -255,6 +287,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.n_chunk);
+      if (p.dxsplit) {
+        const uint32_t w_ring = smem_u32(smem + (size_t)p.a_slots * 2 * A_TILE_BYTES);
+        const int groups = 3 * p.kblocks_per_tap;
+        int wi = 0;
+        for (int g = 0; g < groups; ++g) {
+          const int sa = g % p.a_slots;
+          mbar_wait(&full_bar[sa], ((uint32_t)(g / p.a_slots)) & 1u, failed);
+          if (tracing && g == 0) p.trace[1] = clock64();
+          if (tracing && g == groups - 1) p.trace[2] = clock64();
+          const uint32_t a_hi = smem_u32(smem + (size_t)sa * 2 * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+          for (int dxi = 0; dxi < 3; ++dxi, ++wi) {
+            const int sw = wi % p.w_slots;
+            mbar_wait(&wfull_bar[sw], ((uint32_t)(wi / p.w_slots)) & 1u, failed);
+            tc_fence_after();
+            const uint32_t w_hi = w_ring + (uint32_t)sw * 2u * (uint32_t)w_tile_bytes, w_lo = w_hi + w_tile_bytes;
+            const uint32_t d = tmem_base + dxi * p.n_chunk;          // accumulator of this column shift
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint32_t koff = k * UMMA_K * 4;
+              const uint64_t da_hi = make_smem_desc(a_hi + koff), da_lo = make_smem_desc(a_lo + koff);
+              const uint64_t db_hi = make_smem_desc(w_hi + koff), db_lo = make_smem_desc(w_lo + koff);
+              umma_tf32(d, da_hi, db_hi, idesc, (g | k) ? 1u : 0u);
+              umma_tf32(d, da_lo, db_hi, idesc, 1u);
+              umma_tf32(d, da_hi, db_lo, idesc, 1u);
+            }
+            umma_commit(&wempty_bar[sw]);
+          }
+          umma_commit(&empty_bar[sa]);
+        }
+        umma_commit(tmem_full_bar);
+      } else {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
@@ -282,6 +345,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         umma_commit(&empty_bar[s]);                                  // smem slot free once these MMAs retire
       }
       umma_commit(tmem_full_bar);                                    // accumulator complete
+      }
     }
   } else {
     // ===================== epilogue =====================
@@ -290,14 +354,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     // stages) and are written back with lane == COLUMN: every warp store is one contiguous 128-byte segment, and
     // the per-column vectors (bias, LayerNorm gamma/beta, positional encoding) become coalesced per-lane loads.
     // 16 epilogue warps: the 4 warps that share a TMEM lane group (warp id % 4) split the column chunks.
-    mbar_wait(tmem_full_bar, 0, failed);
-    tc_fence_after();
-    if (tracing && threadIdx.x == 64) p.trace[3] = clock64();
     const int lane_grp = warp & 3;                                   // TMEM lanes this warp may touch
     const int sub = (warp - 2) >> 2;                                 // 0..3 among the warps of this lane group
     const int slab_row0 = m_tile * BLOCK_M + lane_grp * 32;          // first global row of the 32-row slab
     const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const int ncols_cta = p.n_chunk * p.n_chunks;
+    mbar_wait(tmem_full_bar, 0, failed);
+    tc_fence_after();
+    if (tracing && threadIdx.x == 64) p.trace[3] = clock64();
 
     if (PRE == PRE_BIAS) {
       if (p.out_mask & OUT_NCHW) {
@@ -322,13 +386,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int j = sub * 32; j < ncols_cta; j += 32 * (EPI_WARPS / 4)) {
           if (n_base + j >= p.N) break;
           float v[16];
-          tmem_ld16(trow + j, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) tile[lane * 33 + i] = v[i];
-          if (j + 16 < ncols_cta) {
-            tmem_ld16(trow + j + 16, v);
+          for (int half = 0; half < 2; ++half) {
+            if (half && !(j + 16 < ncols_cta)) break;
+            if (p.dxsplit) {
+              // out[r] = P0[r] + P-1[r-1] (unless w == 0) + P+1[r+1] (unless w == W-1): neighbours are the adjacent
+              // TMEM lanes = adjacent threads; slab edges coincide with image-row edges (32 % W == 0), where the term is 0
+              float vm[16], vp[16];
+              tmem_ld16(trow + j + half * 16, vm);
+              tmem_ld16(trow + p.n_chunk + j + half * 16, v);
+              tmem_ld16(trow + 2 * p.n_chunk + j + half * 16, vp);
+              const int wcol = (slab_row0 + lane) % p.W;
+              const bool has_l = wcol > 0, has_r = wcol < p.W - 1;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) tile[lane * 33 + 16 + i] = v[i];
+              for (int i = 0; i < 16; ++i) {
+                const float l = __shfl_up_sync(0xffffffffu, vm[i], 1), r = __shfl_down_sync(0xffffffffu, vp[i], 1);
+                v[i] += (has_l ? l : 0.f) + (has_r ? r : 0.f);
+              }
+            } else {
+              tmem_ld16(trow + j + half * 16, v);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tile[lane * 33 + half * 16 + i] = v[i];
           }
           __syncwarp();
           const int n = n_base + j + lane;                           // this lane's output column
@@ -376,6 +455,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           slab[lane * pitch + j + i] = (a[i] + __ldg(p.bias + j + i)) * sigmoid_fast(b[i] + __ldg(p.bias + C + j + i));
       }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (tracing && threadIdx.x == 64) p.trace[6] = clock64();
       // 2. lane == column: add the residual with coalesced loads
       for (int q = sub; q * 32 < C; q += EPI_WARPS / 4) {
         const int col = q * 32 + lane;
@@ -393,6 +473,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (tracing && threadIdx.x == 64) p.trace[7] = clock64();
       // 3. row statistics, two-pass: warp `sub` owns rows sub*8..sub*8+7, four lanes per row
       {
         const int r = sub * 8 + (lane >> 2), part = lane & 3;
@@ -412,6 +493,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (tracing && threadIdx.x == 64) p.trace[8] = clock64();
       // 4. lane == column: normalise and emit every requested form, coalesced
       for (int q = sub; q * 32 < C; q += EPI_WARPS / 4) {
         const int col = q * 32 + lane;
@@ -593,11 +675,24 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   int stages = (int)((220 * 1024 - 2048) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 1) return FLOWK_ERR_SHAPE;
+  // 3x3 dx-split mode: three accumulators (one per column shift) so that an activation tile serves three taps
+  p.dxsplit = (a->taps == 9 && a->pre == PRE_BIAS && !(a->out_mask & OUT_NCHW) && W <= 32 && 32 % W == 0 &&
+               n_tiles == 1 && p.n_chunks == 1 && 3 * p.n_chunk <= 512) ? 1 : 0;
+  if (p.dxsplit) {
+    p.tmem_cols = 3 * p.n_chunk <= 256 ? 256 : 512;
+    if (3 * p.n_chunk <= 128) p.tmem_cols = 128;
+    p.a_slots = 2;
+    const int w_slot_bytes = 2 * cols * BLOCK_K * 4;
+    int ws = (int)((220 * 1024 - 2048 - p.a_slots * 2 * A_TILE_BYTES) / w_slot_bytes);
+    p.w_slots = ws > 8 ? 8 : ws;
+    if (p.w_slots < 2) p.dxsplit = 0;
+  }
   // epilogue staging (reuses the pipeline stages once the accumulator is complete)
   size_t epi_bytes = (size_t)EPI_WARPS * 32 * 33 * sizeof(float);
   if (a->pre == PRE_GLU_RES_LN) epi_bytes = 4 * (32 * (N / 2 + 1) + 64) * sizeof(float);
   while (stages > 1 && (size_t)stages * stage_bytes + 2048 > 227 * 1024) --stages;
   size_t region = (size_t)stages * stage_bytes;
+  if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 2 * cols * BLOCK_K * 4;
   if (epi_bytes > region) region = (epi_bytes + 1023) / 1024 * 1024;
   if (region + 2048 > 227 * 1024) return FLOWK_ERR_SHAPE;
   p.stages = stages;

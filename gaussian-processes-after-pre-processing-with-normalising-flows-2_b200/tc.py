@@ -60,3 +60,16 @@ def split_rows(x):
     lo = torch.empty_like(x)
     _lib.call("flowk_split_hilo", x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
     return hi, lo
+
+
+def attention(qkv, B, HW, C, heads):
+    """qkv [B*HW, 3C] (k | v | q) -> (hi, lo) [B*HW, C] of softmax(q k^T / sqrt(d)) v."""
+    hi = torch.empty(B * HW, C, device=qkv.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    _lib.call("flowk_attention", qkv.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, HW, C, heads, _stream())
+    return hi, lo
+
+
+def attention_supported(HW, C, heads):
+    return C % heads == 0 and (C // heads) in (8, 16, 24, 32, 40, 64) and (HW <= 256 or HW % 256 == 0) and HW % 4 == 0 \
+        and 2 * min(HW, 1 << 30) * (C // heads) * 4 * max(1, 256 // max(HW, 1)) <= 220 * 1024

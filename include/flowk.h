@@ -153,7 +153,7 @@ typedef struct flowk_conv_gemm_args {
   float* out_lo;
   float* out_nchw;
   int* status;
-  long long* trace;       /* optional device [8]: clock64 stamps of CTA (0,0) for profiling; NULL in production */
+  long long* trace;       /* optional device [16]: clock64 stamps of CTA (0,0) for profiling; NULL in production */
   int B, H, W, Cin, N, taps, pre, out_mask;
 } flowk_conv_gemm_args;
 
@@ -164,6 +164,12 @@ int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, int B, int C
                             float* hi, float* lo, flowk_stream_t stream);
 /* fp32 array -> (hi, lo) operand pair. */
 int flowk_split_hilo(const float* x, float* hi, float* lo, long long n, flowk_stream_t stream);
+
+/* Self-attention core of GatedAttn (mixlogcdf_nn.py:134-147,154-173), inference: qkv = in_proj rows [B*HW, 3C] in the
+ * reference's (k | v | q) column order; out_hi/out_lo [B*HW, C] = softmax(q k^T / sqrt(C/heads)) v as an operand pair.
+ * C/heads in {8,16,24,32,40,64}; HW <= 256 or a multiple of 256. */
+int flowk_attention(const float* qkv, float* out_hi, float* out_lo, int B, int HW, int C, int heads,
+                    flowk_stream_t stream);
 
 #ifdef __cplusplus
 }

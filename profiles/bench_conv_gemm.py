@@ -44,12 +44,14 @@ for name, H, W, Cin, N, taps, pre in shapes:
     e.record()
     torch.cuda.synchronize()
     us = s.elapsed_time(e) * 1e3 / reps
-    trace = torch.zeros(8, dtype=torch.int64, device=dev)
+    trace = torch.zeros(16, dtype=torch.int64, device=dev)
     tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, mask, trace=trace, **kw)
     torch.cuda.synchronize()
     t = trace.cpu().tolist()
     tr = "first_full %5d  mma_loop %6d  epi_wait %6d  epilogue %6d  exit %5d" % (
         t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4])
+    if pre == tc.PRE_GLU_RES_LN:
+        tr += "  | glu %d res %d stats %d emit %d" % (t[6] - t[3], t[7] - t[6], t[8] - t[7], t[4] - t[8])
     flops = 2.0 * M * N * taps * Cin
     ntile = min(N, 256) if pre == tc.PRE_BIAS else N
     n16 = (N + 15) // 16 * 16

@@ -119,3 +119,18 @@ def test_conditioner_tc_matches_torch_path(tc, c, C, H, W, B, blocks):
     e_tc, e_lib = rel_err(got, ref64), rel_err(ref, ref64)
     print("conditioner c=%d C=%d %dx%d: tcgen05 rel err %.2e, torch fp32 rel err %.2e" % (c, C, H, W, e_tc, e_lib))
     assert e_tc < max(2e-5, 4 * e_lib)
+
+
+@pytest.mark.parametrize("B,HW,C,heads", [(64, 256, 96, 4), (64, 64, 96, 4), (64, 16, 96, 4), (3, 1024, 64, 4),
+                                          (5, 4, 32, 4), (2, 256, 160, 4)])
+def test_attention_matches_fp64(tc, B, HW, C, heads):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(B + HW)
+    qkv = torch.randn(B * HW, 3 * C, generator=g).to(dev)
+    hi, lo = tc.attention(qkv, B, HW, C, heads)
+    d = C // heads
+    t = qkv.double().view(B, HW, 3, heads, d)
+    k, v, q = (t[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ref = (torch.softmax((q * d ** -0.5) @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * HW, C)
+    assert rel_err(hi + lo, ref) < 2e-6
+    assert int((hi.view(torch.int32) & 8191).abs().max()) == 0
