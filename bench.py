@@ -394,6 +394,11 @@ def run_flowk(args):
         cpu_baseline = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                         "sample": "%d images per step, 2 timed steps after 1 warm-up (%.2f s/step)" % (sample, sec)}
 
+    # ---- training step (fwd + bwd + Adamax + gradient all-reduce), the metric's second half ---------------------------
+    train = None
+    if not args.no_train:
+        train = train_leg(args, device, rank, world, dist)
+
     if rank == 0:
         ew_bytes = elementwise_bytes_per_image(coupling, image, L, K)
         line = {
@@ -413,12 +418,55 @@ def run_flowk(args):
             "roofline": roofline,
             "roofline_large": roofline_large,
             "cpu_baseline": cpu_baseline,
+            "train": train,
             "elementwise_bytes_per_image": ew_bytes,
             "kernels": kernels,
         }
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def train_leg(args, device, rank, world, dist):
+    """Training images/s on the same workload: the reference's step (marscf_main.py:331-347) with the batch sharded
+    over ranks (64 images per GPU, weak scaling) and the gradients all-reduced over NCCL in flat buckets."""
+    import flowk  # noqa: F401
+    from flowk import sharding
+    from flowk.marscf import MarScfFlow
+    coupling, image, L, K, hidden, batch = WORKLOADS[args.workload]
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = MarScfFlow(batch, image, coupling, L, K, hidden).to(device)
+    model.train()
+    xs = [t.to(device) for t in synthetic_batches(4, batch, image, seed=200 + rank)]
+    with torch.no_grad():
+        model(xs[0])                                    # ActNorm data-dependent init on the first batch
+    sharding.broadcast_module(model)
+    trainer = sharding.ShardedTrainer(model, lr=1e-4, warm_up=10000, global_batch=batch * world)
+    steps = max(2, min(args.steps, args.train_steps))
+    for i in range(2):
+        trainer.step(xs[i % len(xs)])
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(steps):
+        loss = trainer.step(xs[i % len(xs)])
+    e.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    if dist is not None:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return {"value": batch * world * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
+            "warmup": 2, "global_batch": batch * world, "grad_allreduce_mb": trainer.buckets.nbytes() / 1e6,
+            "loss_bits_per_dim": float(loss),
+            "note": "fwd+bwd+Adamax(+NCCL all-reduce); conditioner forward/backward through torch autograd (cuDNN fp32), "
+                    "flow ops through the flowk forward/backward kernels"}
 
 
 def main():
@@ -431,6 +479,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-oracle step (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "flowk" else args.warmup
     if args.impl == "reference":

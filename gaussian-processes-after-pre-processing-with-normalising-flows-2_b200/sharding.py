@@ -1,0 +1,141 @@
+"""Batch-sharded training / evaluation: one process per GPU, full parameter replica per rank, NCCL over
+NVLink for the only two exchanges the path has: the gradient all-reduce and the bits/dim
+sum.  Replaces the reference's single-process nn.DataParallel (marscf_main.py:326,379).
+
+Works with any backend torch.distributed offers (tests run it on CPU with gloo, world_size 2)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None):
+    """Process-group set-up from the torchrun environment.  Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kwargs["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kwargs)
+    return rank, world, local
+
+
+def shard_batch(x, rank, world):
+    """Rank r takes samples [r*B/G, (r+1)*B/G) (the reference scatters on dim 0 the same way)."""
+    per = x.shape[0] // world
+    return x[rank * per:(rank + 1) * per]
+
+
+def broadcast_module(module, src=0):
+    """Make every replica identical to rank `src` (after ActNorm's data-dependent init: the reference's
+    DataParallel keeps replica 0's statistics, marscf_main.py:326 / SURVEY.md section 7)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src)
+
+
+class GradientBuckets:
+    """Flat fp32 gradient buckets, all-reduced asynchronously as soon as every gradient of a bucket has been
+    accumulated (overlaps the exchange with the rest of backward).  Gradients are views into the flat buffers,
+    so there is no packing copy."""
+
+    def __init__(self, params, bucket_bytes=32 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.buckets = []            # (flat tensor, [params])
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):          # backward produces gradients roughly in reverse order
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self._seal(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self._seal(cur)
+        self._pending = []
+        self._ready = [0] * len(self.buckets)
+        self._bucket_of = {}
+        for bi, (_, ps) in enumerate(self.buckets):
+            for p in ps:
+                self._bucket_of[p] = bi
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def _seal(self, ps):
+        flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+        off = 0
+        for p in ps:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.buckets.append((flat, list(ps)))
+
+    def _hook(self, p):
+        bi = self._bucket_of[p]
+        self._ready[bi] += 1
+        if self._ready[bi] == len(self.buckets[bi][1]):
+            self._launch(bi)
+
+    def _launch(self, bi):
+        if self.world > 1:
+            self._pending.append(dist.all_reduce(self.buckets[bi][0], async_op=True))
+
+    def zero(self):
+        for flat, _ in self.buckets:
+            flat.zero_()
+        self._ready = [0] * len(self.buckets)
+
+    def finish(self):
+        """Wait for the outstanding all-reduces and turn sums into means."""
+        for bi, n in enumerate(self._ready):       # parameters that got no gradient this step
+            if n != len(self.buckets[bi][1]) and self.world > 1:
+                self._pending.append(dist.all_reduce(self.buckets[bi][0], async_op=True))
+        for h in self._pending:
+            h.wait()
+        self._pending = []
+        if self.world > 1:
+            for flat, _ in self.buckets:
+                flat.div_(self.world)
+
+    def nbytes(self):
+        return sum(f.numel() * 4 for f, _ in self.buckets)
+
+
+class ShardedTrainer:
+    """The reference's training step (marscf_main.py:302-303,331-347): Adamax(lr=1e-4), LambdaLR warm-up on the
+    number of samples seen, loss = mean bits/dim - with the batch sharded over ranks."""
+
+    def __init__(self, model, lr=1e-4, warm_up=10000, global_batch=None, bucket_bytes=32 << 20):
+        self.model = model
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.buckets = GradientBuckets(model.parameters(), bucket_bytes)
+        self.opt = torch.optim.Adamax(model.parameters(), lr=lr)
+        self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s: min(1., s / warm_up))
+        self.global_step = 0
+        self.global_batch = global_batch
+
+    def step(self, x_local):
+        self.buckets.zero()
+        _, nll, _ = self.model(x_local)
+        loss = nll.mean()
+        loss.backward()
+        self.buckets.finish()
+        self.opt.step()
+        self.global_step += self.global_batch or x_local.shape[0] * self.world
+        self.sched.last_epoch = self.global_step - 1
+        self.sched.step()
+        return loss.detach()
+
+
+def mean_bits_per_dim(nll_local):
+    """Global mean of per-sample bits/dim: one 2-element all-reduce (sum, count)."""
+    acc = torch.stack([nll_local.sum(), torch.tensor(float(nll_local.numel()), device=nll_local.device)])
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(acc)
+    return acc[0] / acc[1]

@@ -290,7 +290,9 @@ def test_mixlogcdf_tail_elements_use_log_domain(F):
     x, raw, rescale = rand_mix(B, c, H, W, gen)
     r5 = raw.view(B, 2 + 3 * K, c, H, W)
     r5[:, 2 + 2 * K:] = -6.5            # very sharp components
-    x[:, :c] = 3.0                      # ~ e^{6.5} * 3 = 2000 widths away
+    x[:, :c] = -4.5                     # thousands of widths BELOW every component: u underflows to exactly 0 on
+                                        # both sides (above them u rounds to 1 or 1-ulp, where the reference's
+                                        # 1e-22 log floor makes the log-det jump by ~34 on a 1-ulp difference)
     ldj0 = torch.zeros(B)
     a, b, pi, mu, s = O.mixlogcdf_split_params(raw, rescale.view(-1, 1, 1))
     ref_lp = O.mix_log_pdf(x[:, :c], pi, mu, s)
