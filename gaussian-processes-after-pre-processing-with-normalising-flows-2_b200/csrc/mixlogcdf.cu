@@ -10,6 +10,8 @@
 // log domain exactly as the reference does (three max-shifted log-sum-exps).  Per-element transcendentals
 // (tanh, exp(a), the logit and its log-derivative) use the precise libdevice functions.
 #include "common.cuh"
+#include "tma.cuh"
+#include <stdlib.h>
 
 namespace flowk {
 
@@ -128,6 +130,82 @@ mixlogcdf_fwd_kernel(const float* __restrict__ x, const float* __restrict__ raw,
     local += log_pdf + scale_ldj + a;                                     // mixlogcdf_coupling.py:53
   }
   if (ldj_out) finish_sample_ldj<kThreads>(local, ldj_in, ldj_out, 1.f, ws);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward, TMA-staged: one 2-D bulk tensor load brings a [98 planes x 128 elements] tile (50 KB) of the raw
+// parameter tensor into shared memory; threads then read their column conflict-free.  No registers are tied up
+// by loads in flight, and 4 resident CTAs per SM keep ~200 KB per SM on the wire - that is what saturates HBM.
+// Same arithmetic as mixlogcdf_fwd_kernel (shared mixture_eval body via the smem view).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmaTile = 128;
+
+__device__ __forceinline__ void mixture_eval_smem(float x, const float* sm, int t, float& u, float& log_pdf) {
+  const float* spi = sm + 2 * kTmaTile + t;
+  const float* smu = sm + (2 + K) * kTmaTile + t;
+  const float* ss = sm + (2 + 2 * K) * kTmaTile + t;
+  float m = spi[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) m = fmaxf(m, spi[k * kTmaTile]);
+  const float m2 = m * kLog2e;
+  float W = 0.f, cdf = 0.f, pdf = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float mu = smu[k * kTmaTile];
+    const float s = fmaxf(ss[k * kTmaTile], kSFloor);
+    const float w = ex2_fast(fmaf(spi[k * kTmaTile], kLog2e, -m2));
+    const float inv = ex2_fast(-s * kLog2e);
+    const float z = (x - mu) * inv;
+    const float e = ex2_fast(-fabsf(z) * kLog2e);
+    const float r = rcp_fast(1.f + e);
+    const float er = e * r;
+    W += w;
+    cdf = fmaf(w, z >= 0.f ? r : er, cdf);
+    pdf = fmaf(w * inv, er * r, pdf);
+  }
+  if (pdf > kUnderflow && cdf > kUnderflow) {
+    u = cdf / W;
+    log_pdf = logf(pdf / W);
+  } else if (pdf != pdf || cdf != cdf) {
+    u = cdf + pdf;
+    log_pdf = u;
+  } else {
+    float lc, lp;
+    MixView v{spi, smu, ss, (size_t)kTmaTile};
+    mixture_logdomain<true>(x, v, &lc, &lp);
+    u = expf(lc);
+    log_pdf = lp;
+  }
+}
+
+__global__ void __launch_bounds__(kTmaTile, 4)
+mixlogcdf_fwd_tma_kernel(const __grid_constant__ CUtensorMap raw_map, const float* __restrict__ x,
+                         const float* __restrict__ rescale, float* __restrict__ y, const float* __restrict__ ldj_in,
+                         float* __restrict__ ldj_out, LdjWs ws, int C, int HW, int flip, int* __restrict__ status) {
+  extern __shared__ __align__(128) float tile[];                // [PLANES][kTmaTile]
+  __shared__ __align__(8) uint64_t bar;
+  const int c = C >> 1, E = c * HW, b = blockIdx.y;
+  const int e0 = blockIdx.x * kTmaTile, t = threadIdx.x, e = e0 + t;
+  if (t == 0) {
+    tma::mbar_init(&bar, 1);
+    tma::mbar_expect_tx(&bar, PLANES * kTmaTile * 4);
+    tma::load_2d(tile, &raw_map, &bar, e0, b * PLANES);          // coords: (column = element, row = b*98 + plane)
+  }
+  const float* xc = x + (size_t)b * C * HW;
+  float* yb = y + (size_t)b * C * HW;
+  const float xv = ld_stream(xc + e);
+  (flip ? yb : yb + E)[e] = ld_stream(xc + E + e);               // pass-through half (TupleFlip fused)
+  const float rs = rescale[e / HW];
+  __syncthreads();                                              // barrier init visible to the waiters
+  const bool ok = tma::mbar_wait(&bar, 0);
+  if (!ok && t == 0 && status) *status = 1;
+  float u, log_pdf;
+  mixture_eval_smem(xv, tile, t, u, log_pdf);
+  const float a = rs * tanhf(tile[t]);
+  const float logit = -logf(fmaxf(1.0f / u - 1.0f, kLogFloor));
+  const float scale_ldj = -logf(fmaxf(u, kLogFloor)) - logf(fmaxf(1.0f - u, kLogFloor));
+  (flip ? yb + E : yb)[e] = (logit + tile[kTmaTile + t]) * expf(a);
+  if (ldj_out) finish_sample_ldj<kTmaTile>(log_pdf + scale_ldj + a, ldj_in, ldj_out, 1.f, ws);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -370,6 +448,27 @@ extern "C" int flowk_mixlogcdf_fwd(const float* x, const float* raw, const float
   if (st) return st;
   if (B == 0) return FLOWK_OK;
   if (ldj_out && !ws) return FLOWK_ERR_ARG;
+  {
+    // TMA-staged path: whole 128-element tiles, rows of the [B*98, E] view 16-byte aligned, <= 64 tiles per sample
+    const long long E = (long long)(C / 2) * HW;
+    static int use_tma = -1;
+    if (use_tma < 0) { const char* env = getenv("FLOWK_MIXLOGCDF_TMA"); use_tma = (env && env[0] == '0') ? 0 : 1; }
+    if (use_tma && E % kTmaTile == 0 && E / kTmaTile <= kMaxParts && aligned16(raw) && tma::encode_fn()) {
+      alignas(64) CUtensorMap map;
+      if (tma::make_map_2d(&map, raw, (long long)B * PLANES, E, PLANES, kTmaTile)) {
+        const int smem = PLANES * kTmaTile * 4;
+        static bool attr_set = false;
+        if (!attr_set) {
+          FLOWK_CUDA_OK(cudaFuncSetAttribute(mixlogcdf_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          attr_set = true;
+        }
+        dim3 grid((unsigned)(E / kTmaTile), B);
+        mixlogcdf_fwd_tma_kernel<<<grid, kTmaTile, smem, stream>>>(map, x, rescale, y, ldj_in, ldj_out, carve_ws(ws, B),
+                                                                  C, HW, flip, nullptr);
+        return launch_status();
+      }
+    }
+  }
   dim3 grid(parts_for((long long)(C / 2) * HW, kThreads), B);
   mixlogcdf_fwd_kernel<<<grid, kThreads, 0, stream>>>(x, raw, rescale, y, ldj_in, ldj_out, carve_ws(ws, B), C, HW,
                                                       flip);
