@@ -183,7 +183,7 @@ struct Params {
   long long* trace;                // optional [16] clock64 stamps of CTA (0,0): setup, first full, last mma, epi start, epi end
 };
 
-template <int PRE>
+template <int PRE, int NV>      // NV: 128-column groups per lane in the LayerNorm epilogue (1: C <= 128, 2: C <= 256)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -382,68 +382,81 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
       }
       if (p.out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_CELU)) {
-        float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);      // [32 rows][33] per warp
-        for (int j = sub * 32; j < ncols_cta; j += 32 * (EPI_WARPS / 4)) {
-          if (n_base + j >= p.N) break;
+        // A. lane == row: accumulator (+ the two shifted neighbours in dx-split mode) + bias -> slab[row][col]
+        const int pitch = ncols_cta + 4;                             // float4-aligned, conflict-free for 128-bit access
+        float* slab = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch);
+        const int bar_id = 1 + lane_grp;
+        for (int j = sub * 16; j < ncols_cta; j += 16 * (EPI_WARPS / 4)) {
           float v[16];
+          if (p.dxsplit) {
+            // out[r] = P0[r] + P-1[r-1] (unless w == 0) + P+1[r+1] (unless w == W-1): neighbours are the adjacent
+            // TMEM lanes = adjacent threads; slab edges coincide with image-row edges (32 % W == 0), where the term is 0
+            float vm[16], vp[16];
+            tmem_ld16(trow + j, vm);
+            tmem_ld16(trow + p.n_chunk + j, v);
+            tmem_ld16(trow + 2 * p.n_chunk + j, vp);
+            const int wcol = (slab_row0 + lane) % p.W;
+            const bool has_l = wcol > 0, has_r = wcol < p.W - 1;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half && !(j + 16 < ncols_cta)) break;
-            if (p.dxsplit) {
-              // out[r] = P0[r] + P-1[r-1] (unless w == 0) + P+1[r+1] (unless w == W-1): neighbours are the adjacent
-              // TMEM lanes = adjacent threads; slab edges coincide with image-row edges (32 % W == 0), where the term is 0
-              float vm[16], vp[16];
-              tmem_ld16(trow + j + half * 16, vm);
-              tmem_ld16(trow + p.n_chunk + j + half * 16, v);
-              tmem_ld16(trow + 2 * p.n_chunk + j + half * 16, vp);
-              const int wcol = (slab_row0 + lane) % p.W;
-              const bool has_l = wcol > 0, has_r = wcol < p.W - 1;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float l = __shfl_up_sync(0xffffffffu, vm[i], 1), r = __shfl_down_sync(0xffffffffu, vp[i], 1);
-                v[i] += (has_l ? l : 0.f) + (has_r ? r : 0.f);
-              }
-            } else {
-              tmem_ld16(trow + j + half * 16, v);
+            for (int i = 0; i < 16; ++i) {
+              const float l = __shfl_up_sync(0xffffffffu, vm[i], 1), r = __shfl_down_sync(0xffffffffu, vp[i], 1);
+              v[i] += (has_l ? l : 0.f) + (has_r ? r : 0.f);
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) tile[lane * 33 + half * 16 + i] = v[i];
+          } else {
+            tmem_ld16(trow + j, v);
           }
-          __syncwarp();
-          const int n = n_base + j + lane;                           // this lane's output column
-          const bool ncol_ok = n < p.N && (j + lane) < ncols_cta;
-          const float bv = (p.bias && ncol_ok) ? __ldg(p.bias + n) : 0.f;
-          if (ncol_ok) {
-            for (int r0 = 0; r0 < 32; r0 += 8) {
-              float y[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) y[u] = tile[(r0 + u) * 33 + lane] + bv;
+          for (int i = 0; i < 16; i += 4) {
+            const int n = n_base + j + i;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && n < p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            *reinterpret_cast<float4*>(slab + lane * pitch + j + i) =
+                make_float4(v[i] + bv.x, v[i + 1] + bv.y, v[i + 2] + bv.z, v[i + 3] + bv.w);
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        // B. warp `sub` owns rows sub*8..sub*8+7; a lane owns 4 consecutive columns: 128-bit smem reads, 128-bit
+        //    fully coalesced global stores
+        for (int c4 = lane * 4; c4 < ncols_cta; c4 += 128) {
+          const int n = n_base + c4;
+          if (n >= p.N) break;
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int m = slab_row0 + r0 + u;
-                if (m < p.M) {
-                  const size_t o = (size_t)m * p.N + n;
-                  if (p.out_mask & OUT_F32) p.out_f32[o] = y[u];
-                  if (p.out_mask & OUT_HILO) split_tf32(y[u], p.out_hi[o], p.out_lo[o]);
-                  if (p.out_mask & OUT_HILO_CELU) {                  // concat_elu: [elu(y) | elu(-y)], width 2N
-                    const size_t o2 = (size_t)m * 2 * p.N + n;
-                    split_tf32(elu1(y[u]), p.out_hi[o2], p.out_lo[o2]);
-                    split_tf32(elu1(-y[u]), p.out_hi[o2 + p.N], p.out_lo[o2 + p.N]);
-                  }
-                }
+          for (int rr = 0; rr < 8; ++rr) {
+            const int r = sub * 8 + rr, m = slab_row0 + r;
+            if (m >= p.M) break;
+            const float4 y = *reinterpret_cast<const float4*>(slab + r * pitch + c4);
+            const float ys[4] = {y.x, y.y, y.z, y.w};
+            const size_t o = (size_t)m * p.N + n;
+            if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(p.out_f32 + o) = y;
+            if (p.out_mask & OUT_HILO) {
+              float h[4], l[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) split_tf32(ys[i], h[i], l[i]);
+              *reinterpret_cast<float4*>(p.out_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(p.out_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+            if (p.out_mask & OUT_HILO_CELU) {                        // concat_elu: [elu(y) | elu(-y)], width 2N
+              const size_t o2 = (size_t)m * 2 * p.N + n;
+              float h[4], l[4], h2[4], l2[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                split_tf32(elu1(ys[i]), h[i], l[i]);
+                split_tf32(elu1(-ys[i]), h2[i], l2[i]);
               }
+              *reinterpret_cast<float4*>(p.out_hi + o2) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(p.out_lo + o2) = make_float4(l[0], l[1], l[2], l[3]);
+              *reinterpret_cast<float4*>(p.out_hi + o2 + p.N) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+              *reinterpret_cast<float4*>(p.out_lo + o2 + p.N) = make_float4(l2[0], l2[1], l2[2], l2[3]);
             }
           }
-          __syncwarp();
         }
       }
     } else {
       // GLU over the [a | b] halves, + residual, LayerNorm over C = N/2
       // (mixlogcdf_nn.py:92-101 ConvAttnBlock, :257-258 GatedConv gate, :149-151 GatedAttn gate)
       const int C = p.N >> 1;
-      const int pitch = C + 1;                                       // odd pitch: conflict-free in both mappings
-      float* slab = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch + 64);   // shared by the 4 warps of the group
-      float* stats = slab + 32 * pitch;                              // [32][2] mean, rstd
+      const int pitch = C + 4;
+      float* slab = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch);      // shared by the 4 warps of the group
       const int bar_id = 1 + lane_grp;                               // named barrier of this lane group (128 threads)
       // 1. lane == row (straight out of TMEM): g = (a + bias_a) * sigmoid(b + bias_b)  -> slab[row][col]
       for (int j = sub * 16; j < C; j += 16 * (EPI_WARPS / 4)) {
@@ -451,76 +464,99 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         tmem_ld16(trow + j, a);
         tmem_ld16(trow + C + j, b);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          slab[lane * pitch + j + i] = (a[i] + __ldg(p.bias + j + i)) * sigmoid_fast(b[i] + __ldg(p.bias + C + j + i));
+        for (int i = 0; i < 16; i += 4) {
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + j + i));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + C + j + i));
+          *reinterpret_cast<float4*>(slab + lane * pitch + j + i) =
+              make_float4((a[i] + ba.x) * sigmoid_fast(b[i] + bb.x), (a[i + 1] + ba.y) * sigmoid_fast(b[i + 1] + bb.y),
+                          (a[i + 2] + ba.z) * sigmoid_fast(b[i + 2] + bb.z), (a[i + 3] + ba.w) * sigmoid_fast(b[i + 3] + bb.w));
+        }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       if (tracing && threadIdx.x == 64) p.trace[6] = clock64();
-      // 2. lane == column: add the residual with coalesced loads
-      for (int q = sub; q * 32 < C; q += EPI_WARPS / 4) {
-        const int col = q * 32 + lane;
-        if (col < C) {
-          for (int r0 = 0; r0 < 32; r0 += 8) {
-            float res[8];
+      // 2. warp `sub` owns rows sub*8..+7; a lane owns 4 consecutive columns (x2 when C > 128).  Residual add,
+      //    two-pass row statistics (warp-shuffle reductions), normalisation and every output form, all in registers.
+      const int nv = (C + 127) / 128;
+      float g[8][NV][4], pe[8][NV][4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int m = slab_row0 + r0 + u;
-              res[u] = m < p.M ? __ldg(p.res + (size_t)m * C + col) : 0.f;
-            }
+      for (int rr = 0; rr < 8; ++rr) {
+        const int r = sub * 8 + rr, m = slab_row0 + r;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) slab[(r0 + u) * pitch + col] += res[u];
-          }
-        }
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (tracing && threadIdx.x == 64) p.trace[7] = clock64();
-      // 3. row statistics, two-pass: warp `sub` owns rows sub*8..sub*8+7, four lanes per row
-      {
-        const int r = sub * 8 + (lane >> 2), part = lane & 3;
-        const float* rowp = slab + r * pitch;
-        float sum = 0.f;
-        for (int c = part; c < C; c += 4) sum += rowp[c];
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        const float mean = sum / (float)C;
-        float var = 0.f;
-        for (int c = part; c < C; c += 4) var = fmaf(rowp[c] - mean, rowp[c] - mean, var);
-        var += __shfl_xor_sync(0xffffffffu, var, 1);
-        var += __shfl_xor_sync(0xffffffffu, var, 2);
-        if (part == 0) {
-          stats[r * 2] = mean;
-          stats[r * 2 + 1] = rsqrtf(var / (float)C + 1e-5f);
-        }
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (tracing && threadIdx.x == 64) p.trace[8] = clock64();
-      // 4. lane == column: normalise and emit every requested form, coalesced
-      for (int q = sub; q * 32 < C; q += EPI_WARPS / 4) {
-        const int col = q * 32 + lane;
-        if (col >= C) continue;
-        const float ga = __ldg(p.gamma + col), be = __ldg(p.beta + col);
-        for (int r0 = 0; r0 < 32; r0 += 8) {
-          float y[8], pe[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int r = r0 + u, m = slab_row0 + r;
-            y[u] = (slab[r * pitch + col] - stats[r * 2]) * stats[r * 2 + 1] * ga + be;
-            pe[u] = ((p.out_mask & OUT_HILO_POS) && m < p.M) ? __ldg(p.pos + (size_t)(m % p.HW) * C + col) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int m = slab_row0 + r0 + u;
+        for (int v = 0; v < NV; ++v) {
+          const int c4 = v * 128 + lane * 4;
+          float4 res = make_float4(0.f, 0.f, 0.f, 0.f), ps = res, gv = res;
+          if (v < nv && c4 < C) {
+            gv = *reinterpret_cast<const float4*>(slab + r * pitch + c4);
             if (m < p.M) {
-              const size_t o = (size_t)m * C + col;
-              if (p.out_mask & OUT_F32) p.out_f32[o] = y[u];
-              if (p.out_mask & OUT_HILO) split_tf32(y[u], p.out_hi[o], p.out_lo[o]);
-              if (p.out_mask & OUT_HILO_POS) split_tf32(y[u] + pe[u], p.out_hi[o], p.out_lo[o]);
-              if (p.out_mask & OUT_HILO_CELU) {
-                const size_t o2 = (size_t)m * 2 * C + col;
-                split_tf32(elu1(y[u]), p.out_hi[o2], p.out_lo[o2]);
-                split_tf32(elu1(-y[u]), p.out_hi[o2 + C], p.out_lo[o2 + C]);
-              }
+              res = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m * C + c4));
+              if (p.out_mask & OUT_HILO_POS) ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(m % p.HW) * C + c4));
             }
+          }
+          g[rr][v][0] = gv.x + res.x; g[rr][v][1] = gv.y + res.y; g[rr][v][2] = gv.z + res.z; g[rr][v][3] = gv.w + res.w;
+          pe[rr][v][0] = ps.x; pe[rr][v][1] = ps.y; pe[rr][v][2] = ps.z; pe[rr][v][3] = ps.w;
+        }
+      }
+      if (tracing && threadIdx.x == 64) p.trace[7] = clock64();
+      float mean[8], rstd[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) sacc += (g[rr][v][0] + g[rr][v][1]) + (g[rr][v][2] + g[rr][v][3]);   // zeros past C
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        mean[rr] = sacc / (float)C;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        float vacc = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (v < nv && v * 128 + lane * 4 < C) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) vacc = fmaf(g[rr][v][i] - mean[rr], g[rr][v][i] - mean[rr], vacc);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vacc += __shfl_xor_sync(0xffffffffu, vacc, o);
+        rstd[rr] = rsqrtf(vacc / (float)C + 1e-5f);
+      }
+      if (tracing && threadIdx.x == 64) p.trace[8] = clock64();
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c4 = v * 128 + lane * 4;
+        if (v >= nv || c4 >= C) continue;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + c4));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c4));
+        const float gs[4] = {ga.x, ga.y, ga.z, ga.w}, bs[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int m = slab_row0 + sub * 8 + rr;
+          if (m >= p.M) continue;
+          float y[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = (g[rr][v][i] - mean[rr]) * rstd[rr] * gs[i] + bs[i];
+          const size_t o = (size_t)m * C + c4;
+          if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+          if (p.out_mask & (OUT_HILO | OUT_HILO_POS)) {
+            float h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(y[i] + pe[rr][v][i], h[i], l[i]);     // pe == 0 unless OUT_HILO_POS
+            *reinterpret_cast<float4*>(p.out_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(p.out_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+          }
+          if (p.out_mask & OUT_HILO_CELU) {
+            const size_t o2 = (size_t)m * 2 * C + c4;
+            float h[4], l[4], h2[4], l2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              split_tf32(elu1(y[i]), h[i], l[i]);
+              split_tf32(elu1(-y[i]), h2[i], l2[i]);
+            }
+            *reinterpret_cast<float4*>(p.out_hi + o2) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(p.out_lo + o2) = make_float4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<float4*>(p.out_hi + o2 + C) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+            *reinterpret_cast<float4*>(p.out_lo + o2 + C) = make_float4(l2[0], l2[1], l2[2], l2[3]);
           }
         }
       }
@@ -667,6 +703,10 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     int per = (n16 / 16 + n_tiles - 1) / n_tiles * 16;
     p.n_chunk = per;
     p.n_chunks = 1;
+    if (n_tiles == 2 && !(a->out_mask & OUT_NCHW)) {     // 256 < N <= 512: one CTA, two accumulator chunks, one wave
+      n_tiles = 1;
+      p.n_chunks = 2;
+    }
   }
   if (p.n_chunk % 16 || p.n_chunk > 256) return FLOWK_ERR_SHAPE;
   const int cols = p.n_chunk * p.n_chunks;
@@ -688,8 +728,9 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     if (p.w_slots < 2) p.dxsplit = 0;
   }
   // epilogue staging (reuses the pipeline stages once the accumulator is complete)
-  size_t epi_bytes = (size_t)EPI_WARPS * 32 * 33 * sizeof(float);
-  if (a->pre == PRE_GLU_RES_LN) epi_bytes = 4 * (32 * (N / 2 + 1) + 64) * sizeof(float);
+  size_t epi_bytes = (size_t)4 * 32 * (cols + 4) * sizeof(float);
+  if (a->pre == PRE_GLU_RES_LN) epi_bytes = (size_t)4 * 32 * (N / 2 + 4) * sizeof(float);
+  if ((a->out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_POS | OUT_HILO_CELU)) && (N & 3)) return FLOWK_ERR_SHAPE;
   while (stages > 1 && (size_t)stages * stage_bytes + 2048 > 227 * 1024) --stages;
   size_t region = (size_t)stages * stage_bytes;
   if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 2 * cols * BLOCK_K * 4;
@@ -706,14 +747,18 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     return FLOWK_ERR_ARG;
 
   dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, n_tiles);
-  if (a->pre == PRE_GLU_RES_LN) {
-    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (a->pre == PRE_GLU_RES_LN && N / 2 > 128) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    conv_gemm_kernel<PRE_GLU_RES_LN><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    conv_gemm_kernel<PRE_GLU_RES_LN, 2><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+  } else if (a->pre == PRE_GLU_RES_LN) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
+    conv_gemm_kernel<PRE_GLU_RES_LN, 1><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
   } else {
-    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_BIAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    conv_gemm_kernel<PRE_BIAS><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    conv_gemm_kernel<PRE_BIAS, 1><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
   }
   return launch_status();
 }
