@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const float* __restri
                                                         int pairs_total, int pairs_per_block, int q_per_block,
                                                         float scale) {
   extern __shared__ __align__(16) float sm[];                  // [pairs_per_block][2][HW][D]
+  griddep_launch();
+  griddep_wait();                                              // PDL: qkv is the previous kernel's output
   const int row_stride = 3 * C;
   const int pair0 = blockIdx.x * pairs_per_block;
   // cooperative load of K and V of every pair of this block (rows of D contiguous floats, 16-byte vectors)
@@ -120,9 +122,8 @@ static int launch_attention(const float* qkv, float* out_hi, float* out_lo, int 
   if (smem > 48 * 1024)
     FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((pairs + pairs_per_block - 1) / pairs_per_block, (HW + q_per_block - 1) / q_per_block);
-  attention_kernel<D><<<grid, q_per_block * pairs_per_block, smem, st>>>(qkv, out_hi, out_lo, HW, C, heads, pairs,
-                                                                        pairs_per_block, q_per_block,
-                                                                        1.0f / sqrtf((float)D));
+  FLOWK_CUDA_OK(launch_pdl(attention_kernel<D>, grid, dim3(q_per_block * pairs_per_block), smem, st, qkv, out_hi, out_lo,
+                           HW, C, heads, pairs, pairs_per_block, q_per_block, 1.0f / sqrtf((float)D)));
   return launch_status();
 }
 

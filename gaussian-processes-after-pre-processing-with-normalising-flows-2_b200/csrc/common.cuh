@@ -101,6 +101,28 @@ __device__ __forceinline__ void finish_sample_ldj(float local, const float* __re
   }
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with `launch_pdl` may start while its predecessor in the
+// stream is still running; it must call griddep_wait() before its first read of the predecessor's output and before
+// its first global write.  griddep_launch() lets the NEXT kernel in the stream begin its own prologue early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int parts_for(long long work_items, int per_cta) {
   long long p = (work_items + per_cta - 1) / per_cta;
   if (p < 1) p = 1;

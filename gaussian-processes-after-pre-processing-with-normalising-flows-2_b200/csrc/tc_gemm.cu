@@ -18,6 +18,7 @@
 // Reference semantics: flow_modules/mixlogcdf_nn.py:12-29 (WNConv2d), :81-102 (ConvAttnBlock), :227-260 (GatedConv),
 // :124-152 (GatedAttn projections), flow_modules/affine_coupling.py:27-80 (NN_net).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace flowk {
@@ -102,6 +103,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -230,6 +239,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const bool tracing = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
   if (tracing && threadIdx.x == 0) p.trace[0] = clock64();
+  griddep_launch();                 // PDL: the next kernel may start its prologue; it waits on our completion itself
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -239,12 +249,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       int b0, h0;
       if (p.bt > 1) { b0 = m_tile * p.bt; h0 = 0; }
       else { b0 = m_tile / tiles_per_img; h0 = (m_tile % tiles_per_img) * p.ht; }
+      griddep_wait();               // PDL: everything before this overlapped the previous kernel's tail; its output is
+                                    // complete and visible from here on (all our global writes come after these loads)
       if (p.dxsplit) {
         // group g = (dy, channel block): ONE activation tile (rows shifted by dy, columns unshifted) feeds the three
         // taps (dy, dx = -1, 0, +1); each tap streams its own weight tile.  Activation traffic / 3.
         uint8_t* w_ring = smem + (size_t)p.a_slots * 2 * A_TILE_BYTES;
         const int groups = 3 * p.kblocks_per_tap;
-        int wi = 0;
         for (int g = 0; g < groups; ++g) {
           const int dyi = g / p.kblocks_per_tap, cb = g % p.kblocks_per_tap;
           const int sa = g % p.a_slots;
@@ -253,14 +264,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           mbar_expect_tx(&full_bar[sa], 2u * A_TILE_BYTES);
           tma_load_4d(at, &map_a_hi, &full_bar[sa], cb * BLOCK_K, 0, h0 + dyi - 1, b0);
           tma_load_4d(at + A_TILE_BYTES, &map_a_lo, &full_bar[sa], cb * BLOCK_K, 0, h0 + dyi - 1, b0);
-          for (int dxi = 0; dxi < 3; ++dxi, ++wi) {
-            const int sw = wi % p.w_slots;
-            mbar_wait(&wempty_bar[sw], (((uint32_t)(wi / p.w_slots)) & 1u) ^ 1u, failed);
-            uint8_t* wt = w_ring + (size_t)sw * 2 * w_tile_bytes;
-            mbar_expect_tx(&wfull_bar[sw], 2u * (uint32_t)w_tile_bytes);
+          // the three taps (dy, dx=-1,0,+1) of this group: weight tiles back to back in ONE slot, so that the three
+          // per-shift accumulators (adjacent TMEM column ranges) can be fed by wide MMAs
+          const int sw = g % p.w_slots;
+          mbar_wait(&wempty_bar[sw], (((uint32_t)(g / p.w_slots)) & 1u) ^ 1u, failed);
+          uint8_t* wt = w_ring + (size_t)sw * 6 * w_tile_bytes;
+          mbar_expect_tx(&wfull_bar[sw], 6u * (uint32_t)w_tile_bytes);
+          for (int dxi = 0; dxi < 3; ++dxi) {
             const int kcol = ((dyi * 3 + dxi) * p.kblocks_per_tap + cb) * BLOCK_K;
-            tma_load_2d(wt, &map_w_hi, &wfull_bar[sw], kcol, n_base);
-            tma_load_2d(wt + w_tile_bytes, &map_w_lo, &wfull_bar[sw], kcol, n_base);
+            tma_load_2d(wt + dxi * w_tile_bytes, &map_w_hi, &wfull_bar[sw], kcol, n_base);
+            tma_load_2d(wt + (3 + dxi) * w_tile_bytes, &map_w_lo, &wfull_bar[sw], kcol, n_base);
           }
         }
       } else
@@ -290,30 +303,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       if (p.dxsplit) {
         const uint32_t w_ring = smem_u32(smem + (size_t)p.a_slots * 2 * A_TILE_BYTES);
         const int groups = 3 * p.kblocks_per_tap;
-        int wi = 0;
+        // the three accumulators are the TMEM columns [0, 3*n_chunk): cover them with as few MMAs as possible
+        // (a K=8 TF32 MMA costs ~100 cycles whatever its N, measured)
+        const int n_total = 3 * p.n_chunk;
+        int n_mma = (n_total + 255) / 256;
+        if ((n_total / n_mma) % 16 || n_total % n_mma) n_mma = 3;
+        const int n_per = n_total / n_mma;
+        const uint32_t idesc_w = make_idesc(n_per);
+        const uint64_t per_units = (uint64_t)((uint32_t)(n_per * BLOCK_K * 4) >> 4);
         for (int g = 0; g < groups; ++g) {
-          const int sa = g % p.a_slots;
+          const int sa = g % p.a_slots, sw = g % p.w_slots;
           mbar_wait(&full_bar[sa], ((uint32_t)(g / p.a_slots)) & 1u, failed);
+          mbar_wait(&wfull_bar[sw], ((uint32_t)(g / p.w_slots)) & 1u, failed);
+          tc_fence_after();
           if (tracing && g == 0) p.trace[1] = clock64();
           if (tracing && g == groups - 1) p.trace[2] = clock64();
-          const uint32_t a_hi = smem_u32(smem + (size_t)sa * 2 * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
-          for (int dxi = 0; dxi < 3; ++dxi, ++wi) {
-            const int sw = wi % p.w_slots;
-            mbar_wait(&wfull_bar[sw], ((uint32_t)(wi / p.w_slots)) & 1u, failed);
-            tc_fence_after();
-            const uint32_t w_hi = w_ring + (uint32_t)sw * 2u * (uint32_t)w_tile_bytes, w_lo = w_hi + w_tile_bytes;
-            const uint32_t d = tmem_base + dxi * p.n_chunk;          // accumulator of this column shift
+          const uint32_t a_hi = smem_u32(smem + (size_t)sa * 2 * A_TILE_BYTES);
+          const uint32_t w_hi = w_ring + (uint32_t)sw * 6u * (uint32_t)w_tile_bytes;
+          const uint64_t da_hi = make_smem_desc(a_hi), da_lo = da_hi + (A_TILE_BYTES >> 4);
+          const uint64_t db_hi = make_smem_desc(w_hi), db_lo = db_hi + ((3u * (uint32_t)w_tile_bytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint32_t koff = k * UMMA_K * 4;
-              const uint64_t da_hi = make_smem_desc(a_hi + koff), da_lo = make_smem_desc(a_lo + koff);
-              const uint64_t db_hi = make_smem_desc(w_hi + koff), db_lo = make_smem_desc(w_lo + koff);
-              umma_tf32(d, da_hi, db_hi, idesc, (g | k) ? 1u : 0u);
-              umma_tf32(d, da_lo, db_hi, idesc, 1u);
-              umma_tf32(d, da_hi, db_lo, idesc, 1u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
+            for (int q = 0; q < n_mma; ++q) {
+              const uint64_t bo = ko + q * per_units;
+              const uint32_t d = tmem_base + q * n_per;
+              if ((g | k) == 0) umma_tf32(d, da_hi + ko, db_hi + bo, idesc_w, 0u);
+              else umma_tf32_acc(d, da_hi + ko, db_hi + bo, idesc_w);
+              umma_tf32_acc(d, da_lo + ko, db_hi + bo, idesc_w);
+              umma_tf32_acc(d, da_hi + ko, db_lo + bo, idesc_w);
             }
-            umma_commit(&wempty_bar[sw]);
           }
+          umma_commit(&wempty_bar[sw]);
           umma_commit(&empty_bar[sa]);
         }
         umma_commit(tmem_full_bar);
@@ -326,20 +347,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (tracing && kb == 0) p.trace[1] = clock64();
         if (tracing && kb == num_kb - 1) p.trace[2] = clock64();
         const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t a_lo = a_hi + A_TILE_BYTES;
-        const uint32_t w_hi = a_hi + 2 * A_TILE_BYTES;
-        const uint32_t w_lo = w_hi + w_tile_bytes;
+        const uint64_t da_hi0 = make_smem_desc(a_hi), da_lo0 = da_hi0 + (A_TILE_BYTES >> 4);
+        const uint64_t db_hi0 = da_hi0 + (2 * A_TILE_BYTES >> 4), db_lo0 = db_hi0 + ((uint32_t)w_tile_bytes >> 4);
+        const uint64_t chunk_units = (uint64_t)((uint32_t)(p.n_chunk * BLOCK_K * 4) >> 4);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint32_t koff = k * UMMA_K * 4;                      // bytes inside the 128-byte swizzle row
-          const uint64_t da_hi = make_smem_desc(a_hi + koff), da_lo = make_smem_desc(a_lo + koff);
+          const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);       // 16-byte units inside the 128-byte swizzle row
           for (int c = 0; c < p.n_chunks; ++c) {
-            const uint32_t coff = c * p.n_chunk * BLOCK_K * 4;
-            const uint64_t db_hi = make_smem_desc(w_hi + coff + koff), db_lo = make_smem_desc(w_lo + coff + koff);
+            const uint64_t co = ko + c * chunk_units;
             const uint32_t d = tmem_base + c * p.n_chunk;
-            umma_tf32(d, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
-            umma_tf32(d, da_lo, db_hi, idesc, 1u);
-            umma_tf32(d, da_hi, db_lo, idesc, 1u);
+            if ((kb | k) == 0) umma_tf32(d, da_hi0 + ko, db_hi0 + co, idesc, 0u);
+            else umma_tf32_acc(d, da_hi0 + ko, db_hi0 + co, idesc);
+            umma_tf32_acc(d, da_lo0 + ko, db_hi0 + co, idesc);
+            umma_tf32_acc(d, da_hi0 + ko, db_lo0 + co, idesc);
           }
         }
         umma_commit(&empty_bar[s]);                                  // smem slot free once these MMAs retire
@@ -576,6 +596,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 // NCHW slice -> NHWC hi/lo operand, channel dim zero-padded to c_pad (conditioner input, mixlogcdf_nn.py:66)
 __global__ void nchw_to_nhwc_hilo_kernel(const float* __restrict__ x, long long batch_stride, int c, int hw, int c_pad,
                                          float* __restrict__ hi, float* __restrict__ lo, long long total) {
+  griddep_launch();
+  griddep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(i % c_pad);
@@ -593,6 +615,8 @@ __global__ void nchw_to_nhwc_hilo_kernel(const float* __restrict__ x, long long 
 // fp32 rows -> hi/lo operand pair (attention output -> gate GEMM)
 __global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
                                   long long total) {
+  griddep_launch();
+  griddep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float h, l;
@@ -703,9 +727,16 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     int per = (n16 / 16 + n_tiles - 1) / n_tiles * 16;
     p.n_chunk = per;
     p.n_chunks = 1;
-    if (n_tiles == 2 && !(a->out_mask & OUT_NCHW)) {     // 256 < N <= 512: one CTA, two accumulator chunks, one wave
-      n_tiles = 1;
-      p.n_chunks = 2;
+    const int m_tiles = (B * H * W + BLOCK_M - 1) / BLOCK_M;
+    if (n_tiles == 2 && !(a->out_mask & OUT_NCHW) && m_tiles * 2 > 148) {
+      n_tiles = 1;                                       // 256 < N <= 512 on a full machine: one CTA, two accumulator
+      p.n_chunks = 2;                                    // chunks -> one wave instead of two
+    }
+    // Few M tiles (deep levels, small batches): per-CTA time is bound by the ~32 B/clk an SM can pull from / push to
+    // L2, so spread the output columns over the idle SMs - narrower weight tiles and narrower epilogues per CTA.
+    while (p.n_chunks == 1 && p.n_chunk % 32 == 0 && p.n_chunk >= 64 && m_tiles * n_tiles * 2 <= 148) {
+      p.n_chunk /= 2;
+      n_tiles *= 2;
     }
   }
   if (p.n_chunk % 16 || p.n_chunk > 256) return FLOWK_ERR_SHAPE;
@@ -717,14 +748,15 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   if (stages < 1) return FLOWK_ERR_SHAPE;
   // 3x3 dx-split mode: three accumulators (one per column shift) so that an activation tile serves three taps
   p.dxsplit = (a->taps == 9 && a->pre == PRE_BIAS && !(a->out_mask & OUT_NCHW) && W <= 32 && 32 % W == 0 &&
-               n_tiles == 1 && p.n_chunks == 1 && 3 * p.n_chunk <= 512) ? 1 : 0;
+               p.n_chunks == 1 && 3 * p.n_chunk <= 512) ? 1 : 0;
   if (p.dxsplit) {
     p.tmem_cols = 3 * p.n_chunk <= 256 ? 256 : 512;
     if (3 * p.n_chunk <= 128) p.tmem_cols = 128;
     p.a_slots = 2;
-    const int w_slot_bytes = 2 * cols * BLOCK_K * 4;
+    if (const char* e = getenv("FLOWK_A_SLOTS")) p.a_slots = atoi(e);   // tuning knob
+    const int w_slot_bytes = 6 * cols * BLOCK_K * 4;            // 3 column shifts x (hi, lo)
     int ws = (int)((220 * 1024 - 2048 - p.a_slots * 2 * A_TILE_BYTES) / w_slot_bytes);
-    p.w_slots = ws > 8 ? 8 : ws;
+    p.w_slots = ws > 4 ? 4 : ws;
     if (p.w_slots < 2) p.dxsplit = 0;
   }
   // epilogue staging (reuses the pipeline stages once the accumulator is complete)
@@ -733,7 +765,7 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   if ((a->out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_POS | OUT_HILO_CELU)) && (N & 3)) return FLOWK_ERR_SHAPE;
   while (stages > 1 && (size_t)stages * stage_bytes + 2048 > 227 * 1024) --stages;
   size_t region = (size_t)stages * stage_bytes;
-  if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 2 * cols * BLOCK_K * 4;
+  if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 6 * cols * BLOCK_K * 4;
   if (epi_bytes > region) region = (epi_bytes + 1023) / 1024 * 1024;
   if (region + 2048 > 227 * 1024) return FLOWK_ERR_SHAPE;
   p.stages = stages;
@@ -750,15 +782,15 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   if (a->pre == PRE_GLU_RES_LN && N / 2 > 128) {
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    conv_gemm_kernel<PRE_GLU_RES_LN, 2><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));
   } else if (a->pre == PRE_GLU_RES_LN) {
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    conv_gemm_kernel<PRE_GLU_RES_LN, 1><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));
   } else {
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_BIAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    conv_gemm_kernel<PRE_BIAS, 1><<<grid, NUM_THREADS, smem_bytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_BIAS, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));
   }
   return launch_status();
 }
@@ -770,7 +802,7 @@ extern "C" int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, i
   if (!x || !hi || !lo) return FLOWK_ERR_ARG;
   const long long total = (long long)B * HW * C_pad;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  nchw_to_nhwc_hilo_kernel<<<blocks, 256, 0, stream>>>(x, batch_stride, C, HW, C_pad, hi, lo, total);
+  FLOWK_CUDA_OK(launch_pdl(nchw_to_nhwc_hilo_kernel, dim3(blocks), dim3(256), 0, stream, x, batch_stride, C, HW, C_pad, hi, lo, total));
   return launch_status();
 }
 
@@ -779,6 +811,6 @@ extern "C" int flowk_split_hilo(const float* x, float* hi, float* lo, long long 
   if (n == 0) return FLOWK_OK;
   if (!x || !hi || !lo) return FLOWK_ERR_ARG;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  split_hilo_kernel<<<blocks, 256, 0, stream>>>(x, hi, lo, n);
+  FLOWK_CUDA_OK(launch_pdl(split_hilo_kernel, dim3(blocks), dim3(256), 0, stream, x, hi, lo, (long long)n));
   return launch_status();
 }
