@@ -7,6 +7,7 @@
 // seq <= 1024 and d <= 64 here (seq = 256/64/16, d = 24 at the BASELINE shapes), so the problem per (image, head) is
 // tiny: K and V of a pair live in shared memory, one thread owns one query and streams the keys with an online
 // softmax in registers (fp32 throughout; every lane reads the same key at the same time -> broadcast LDS.128).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace flowk {
@@ -102,12 +103,195 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const float* __restri
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float y = acc[4 * i + u] * inv;
-      hi[u] = __uint_as_float(__float_as_uint(y) & 0xffffe000u);
-      lo[u] = y - hi[u];
+      hi[u] = __uint_as_float((__float_as_uint(y) + 0x1000u) & 0xffffe000u);
+      lo[u] = __uint_as_float((__float_as_uint(y - hi[u]) + 0x1000u) & 0xffffe000u);
     }
     oh[i] = make_float4(hi[0], hi[1], hi[2], hi[3]);
     ol[i] = make_float4(lo[0], lo[1], lo[2], lo[3]);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-level tensor-core version (mma.sync m16n8k8 TF32, 3xTF32 split for fp32 accuracy).  The problem per
+// (image, head) - seq <= 1024, d <= 64 - is far too small for a 128-row tcgen05 tile pipeline, so this is a
+// flash-attention style kernel: a warp owns 16 queries, keys stream through in blocks of 8, online softmax in the
+// accumulator fragments, P is re-used as the A operand of P*V by permuting the key order inside a block
+// (accumulator columns (2t, 2t+1) == operand columns (t, t+4) of the permuted keys).  ~4x fewer issue slots per
+// query-key pair than the scalar kernel above.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_bits(float x, uint32_t& hi, uint32_t& lo) {   // round-to-nearest TF32 split
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+}
+
+template <int D, int NKB>      // NKB key blocks (of 8 keys) per softmax update
+__global__ void __launch_bounds__(512) attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out_hi,
+                                                            float* __restrict__ out_lo, int HW, int C, int heads,
+                                                            int pairs_total, int pairs_per_block, int warps_per_pair,
+                                                            int key_tile, float scale) {
+  extern __shared__ __align__(16) float sm[];                  // [pairs_per_block][2][key_tile][D + 4]
+  constexpr int P = D + 4;                                     // row pitch: conflict-free fragment loads
+  constexpr int KS = D / 8;                                    // k-steps of QK^T == n-blocks of PV
+  griddep_launch();
+  griddep_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int pl = warp / warps_per_pair;                        // pair handled by this warp
+  const int pair = blockIdx.x * pairs_per_block + pl;
+  const bool pair_ok = pl < pairs_per_block && pair < pairs_total;
+  const int b = pair_ok ? pair / heads : 0, h = pair_ok ? pair - b * heads : 0;
+  const int q0 = (blockIdx.y * warps_per_pair + (warp - pl * warps_per_pair)) * 16;    // first query of this warp
+  const int row_stride = 3 * C;
+  const bool q_lo_ok = pair_ok && q0 + g < HW, q_hi_ok = pair_ok && q0 + g + 8 < HW;
+
+  // Q fragments (scaled), split once
+  uint32_t qh[KS][4], ql[KS][4];
+  {
+    const float* q_lo_p = qkv + (size_t)(b * HW + (q_lo_ok ? q0 + g : 0)) * row_stride + 2 * C + h * D;
+    const float* q_hi_p = qkv + (size_t)(b * HW + (q_hi_ok ? q0 + g + 8 : 0)) * row_stride + 2 * C + h * D;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float v0 = q_lo_ok ? __ldg(q_lo_p + ks * 8 + t) * scale : 0.f, v1 = q_hi_ok ? __ldg(q_hi_p + ks * 8 + t) * scale : 0.f;
+      const float v2 = q_lo_ok ? __ldg(q_lo_p + ks * 8 + t + 4) * scale : 0.f, v3 = q_hi_ok ? __ldg(q_hi_p + ks * 8 + t + 4) * scale : 0.f;
+      split_bits(v0, qh[ks][0], ql[ks][0]); split_bits(v1, qh[ks][1], ql[ks][1]);
+      split_bits(v2, qh[ks][2], ql[ks][2]); split_bits(v3, qh[ks][3], ql[ks][3]);
+    }
+  }
+  float o[KS][4];
+#pragma unroll
+  for (int nb = 0; nb < KS; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+  float mx_lo = -INFINITY, mx_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+  float* Ks = sm + (size_t)(pl < pairs_per_block ? pl : 0) * 2 * key_tile * P;
+  float* Vs = Ks + (size_t)key_tile * P;
+  constexpr int V4 = D / 4;
+  for (int kt0 = 0; kt0 < HW; kt0 += key_tile) {
+    __syncthreads();                                           // previous tile fully consumed
+    {                                                          // cooperative K/V tile load, all pairs of the block
+      const int vec_per_pair = 2 * key_tile * V4;
+      for (int i = threadIdx.x; i < pairs_per_block * vec_per_pair; i += blockDim.x) {
+        const int pp = i / vec_per_pair, r = i - pp * vec_per_pair;
+        const int which = r / (key_tile * V4), rr = r - which * (key_tile * V4);
+        const int j = rr / V4, v4 = rr - j * V4;
+        const int pr = blockIdx.x * pairs_per_block + pp;
+        if (pr < pairs_total && kt0 + j < HW) {
+          const int bb = pr / heads, hh = pr - bb * heads;
+          const float4 val = __ldg(reinterpret_cast<const float4*>(qkv + (size_t)(bb * HW + kt0 + j) * row_stride + which * C + hh * D) + v4);
+          *reinterpret_cast<float4*>(sm + ((size_t)(pp * 2 + which) * key_tile + j) * P + v4 * 4) = val;
+        }
+      }
+    }
+    __syncthreads();
+    const int keys_here = HW - kt0 < key_tile ? HW - kt0 : key_tile;
+    for (int k0 = 0; k0 < keys_here; k0 += 8 * NKB) {
+      // ---- S = Q K^T for NKB blocks of 8 keys
+      float sc[NKB][4];
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        sc[kb][0] = sc[kb][1] = sc[kb][2] = sc[kb][3] = 0.f;
+        const float* kr = Ks + (size_t)(k0 + kb * 8 + g) * P + t;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t bh0, bl0, bh1, bl1;
+          split_bits(kr[ks * 8], bh0, bl0);
+          split_bits(kr[ks * 8 + 4], bh1, bl1);
+          mma_tf32(sc[kb], qh[ks], bh0, bh1);
+          mma_tf32(sc[kb], ql[ks], bh0, bh1);
+          mma_tf32(sc[kb], qh[ks], bl0, bl1);
+        }
+      }
+      // ---- online softmax: rows g (c0,c1) and g+8 (c2,c3); a row lives in the 4 lanes of a quad
+      float m_lo = sc[0][0], m_hi = sc[0][2];
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        m_lo = fmaxf(m_lo, fmaxf(sc[kb][0], sc[kb][1]));
+        m_hi = fmaxf(m_hi, fmaxf(sc[kb][2], sc[kb][3]));
+      }
+      m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1)); m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+      m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1)); m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+      const float nm_lo = fmaxf(mx_lo, m_lo), nm_hi = fmaxf(mx_hi, m_hi);
+      const float c_lo = __expf(mx_lo - nm_lo), c_hi = __expf(mx_hi - nm_hi);
+      mx_lo = nm_lo; mx_hi = nm_hi;
+      l_lo *= c_lo; l_hi *= c_hi;
+#pragma unroll
+      for (int nb = 0; nb < KS; ++nb) { o[nb][0] *= c_lo; o[nb][1] *= c_lo; o[nb][2] *= c_hi; o[nb][3] *= c_hi; }
+      // ---- O += P V, P re-used straight from the accumulator fragment (keys permuted inside the block)
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        const float p0 = __expf(sc[kb][0] - mx_lo), p1 = __expf(sc[kb][1] - mx_lo);
+        const float p2 = __expf(sc[kb][2] - mx_hi), p3 = __expf(sc[kb][3] - mx_hi);
+        l_lo += p0 + p1;
+        l_hi += p2 + p3;
+        uint32_t ph[4], plo[4];
+        split_bits(p0, ph[0], plo[0]);      // a0 = (row g,   k = t)   <- key 2t
+        split_bits(p2, ph[1], plo[1]);      // a1 = (row g+8, k = t)   <- key 2t
+        split_bits(p1, ph[2], plo[2]);      // a2 = (row g,   k = t+4) <- key 2t+1
+        split_bits(p3, ph[3], plo[3]);      // a3 = (row g+8, k = t+4) <- key 2t+1
+        const float* vr = Vs + (size_t)(k0 + kb * 8 + 2 * t) * P + g;
+#pragma unroll
+        for (int nb = 0; nb < KS; ++nb) {
+          uint32_t bh0, bl0, bh1, bl1;
+          split_bits(vr[nb * 8], bh0, bl0);            // b0 = (k = t,   n = g) <- V[key 2t  ][dim nb*8+g]
+          split_bits(vr[P + nb * 8], bh1, bl1);        // b1 = (k = t+4, n = g) <- V[key 2t+1][dim nb*8+g]
+          mma_tf32(o[nb], ph, bh0, bh1);
+          mma_tf32(o[nb], plo, bh0, bh1);
+          mma_tf32(o[nb], ph, bl0, bl1);
+        }
+      }
+    }
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+#pragma unroll
+  for (int nb = 0; nb < KS; ++nb) {
+    const int col = h * D + nb * 8 + 2 * t;
+    if (q_lo_ok) {
+      const size_t off = (size_t)(b * HW + q0 + g) * C + col;
+      uint32_t h0, l0, h1, l1;
+      split_bits(o[nb][0] * i_lo, h0, l0); split_bits(o[nb][1] * i_lo, h1, l1);
+      *reinterpret_cast<float2*>(out_hi + off) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
+      *reinterpret_cast<float2*>(out_lo + off) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
+    }
+    if (q_hi_ok) {
+      const size_t off = (size_t)(b * HW + q0 + g + 8) * C + col;
+      uint32_t h0, l0, h1, l1;
+      split_bits(o[nb][2] * i_hi, h0, l0); split_bits(o[nb][3] * i_hi, h1, l1);
+      *reinterpret_cast<float2*>(out_hi + off) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
+      *reinterpret_cast<float2*>(out_lo + off) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
+    }
+  }
+}
+
+template <int D>
+static int launch_attention_mma(const float* qkv, float* out_hi, float* out_lo, int B, int HW, int C, int heads,
+                                cudaStream_t st) {
+  const int pairs = B * heads;
+  int warps_per_pair = (HW + 15) / 16;
+  if (warps_per_pair > 16) warps_per_pair = 16;                 // 256 queries of a pair per block
+  int pairs_per_block = 16 / warps_per_pair;
+  if (pairs_per_block < 1) pairs_per_block = 1;
+  const int key_tile = HW < 256 ? HW : 256;
+  const size_t smem = (size_t)pairs_per_block * 2 * key_tile * (D + 4) * sizeof(float);
+  dim3 grid((pairs + pairs_per_block - 1) / pairs_per_block, (HW + warps_per_pair * 16 - 1) / (warps_per_pair * 16));
+  const int threads = 32 * warps_per_pair * pairs_per_block;
+  const float scale = 1.0f / sqrtf((float)D);
+  if (HW % 32 == 0) {
+    if (smem > 48 * 1024)
+      FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FLOWK_CUDA_OK(launch_pdl(attention_mma_kernel<D, 4>, grid, dim3(threads), smem, st, qkv, out_hi, out_lo, HW, C, heads,
+                             pairs, pairs_per_block, warps_per_pair, key_tile, scale));
+  } else {
+    if (smem > 48 * 1024)
+      FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FLOWK_CUDA_OK(launch_pdl(attention_mma_kernel<D, 1>, grid, dim3(threads), smem, st, qkv, out_hi, out_lo, HW, C, heads,
+                             pairs, pairs_per_block, warps_per_pair, key_tile, scale));
+  }
+  return launch_status();
 }
 
 template <int D>
@@ -137,6 +321,19 @@ extern "C" int flowk_attention(const float* qkv, float* out_hi, float* out_lo, i
   if (B == 0) return FLOWK_OK;
   if (!qkv || !out_hi || !out_lo) return FLOWK_ERR_ARG;
   if ((HW > 256 && HW % 256) || HW % 4) return FLOWK_ERR_SHAPE;
+  static int use_mma = -1;
+  if (use_mma < 0) { const char* e = getenv("FLOWK_ATTENTION_MMA"); use_mma = (e && e[0] == '0') ? 0 : 1; }
+  if (use_mma && HW % 8 == 0) {
+    switch (C / heads) {
+      case 8: return launch_attention_mma<8>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
+      case 16: return launch_attention_mma<16>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
+      case 24: return launch_attention_mma<24>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
+      case 32: return launch_attention_mma<32>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
+      case 40: return launch_attention_mma<40>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
+      case 64: return launch_attention_mma<64>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
+      default: return FLOWK_ERR_SHAPE;
+    }
+  }
   switch (C / heads) {
     case 8: return launch_attention<8>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
     case 16: return launch_attention<16>(qkv, out_hi, out_lo, B, HW, C, heads, stream);

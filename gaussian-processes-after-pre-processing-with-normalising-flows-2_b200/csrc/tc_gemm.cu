@@ -156,9 +156,14 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+// x = hi + lo with BOTH parts exactly representable in TF32 (round-to-nearest): the tensor core merely truncates
+// its fp32 containers, which would otherwise bias every product by up to 2^-10 of the lo term.
+__device__ __forceinline__ float rna_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = x - hi;
+  hi = rna_tf32(x);
+  lo = rna_tf32(x - hi);
 }
 // elu(x) = x > 0 ? x : e^x - 1.  The result feeds a GEMM operand, so what matters is ABSOLUTE error (~1e-7 here).
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : ex2_fast(x * kLog2e) - 1.f; }

@@ -14,10 +14,13 @@ def _stream():
 
 
 def split_hilo(t):
-    """hi = t with the 13 low mantissa bits cleared (exactly representable in TF32), lo = t - hi (exact)."""
+    """t = hi + lo with both parts rounded to nearest TF32 (13 low mantissa bits zero), like the device-side split."""
     t = t.contiguous().float()
-    hi = (t.view(torch.int32) & -8192).view(torch.float32)
-    return hi, t - hi
+
+    def rna(v):
+        return ((v.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    hi = rna(t)
+    return hi, rna(t - hi)
 
 
 def conv_weight_operand(w, cin_pad=None):
