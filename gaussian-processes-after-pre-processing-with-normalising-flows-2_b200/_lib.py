@@ -56,7 +56,7 @@ class ConvGemmArgs(ctypes.Structure):
 
 
 PRE_BIAS, PRE_GLU_RES_LN = 0, 1
-OUT_F32, OUT_HILO, OUT_HILO_POS, OUT_HILO_CELU, OUT_NCHW = 1, 2, 4, 8, 16
+OUT_F32, OUT_HILO, OUT_HILO_POS, OUT_HILO_CELU, OUT_NCHW, OUT_HILO_RELU = 1, 2, 4, 8, 16, 32
 
 
 # where the integer problem dimensions sit in each entry point's argument list (for per-launch accounting)

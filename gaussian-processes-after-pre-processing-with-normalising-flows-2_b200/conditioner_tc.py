@@ -148,3 +148,50 @@ def mixlogcdf_nn_raw(nn_module, x_id, status=None):
     tc.conv_gemm(nxt_hi, nxt_lo, w_hi, w_lo, B, H, W, C, n_out, 9, tc.PRE_BIAS, tc.OUT_NCHW, bias=bias, out_nchw=raw,
                  status=status)
     return raw
+
+
+def _affine_operands(net):
+    """NN_net (flow_modules/affine_coupling.py:68-80) with both ActNorms folded into the conv weights:
+    (conv(x) + b) e^{logs} = conv(x; w e^{logs}) + b e^{logs};  Conv2dZeros: (conv + bias) e^{3 logs}."""
+    ops = []
+    for conv in (net.conv1, net.conv2):
+        gain = torch.exp(conv.actnorm.logs.detach().reshape(-1))
+        w_hi, w_lo = tc.conv_weight_operand(conv.weight.detach() * gain.view(-1, 1, 1, 1))
+        ops.append((w_hi, w_lo, (conv.actnorm.bias.detach().reshape(-1) * gain).contiguous()))
+    gain = torch.exp(net.conv3.logs.detach().reshape(-1) * net.conv3.logscale_factor)
+    w_hi, w_lo = tc.conv_weight_operand(net.conv3.weight.detach() * gain.view(-1, 1, 1, 1))
+    ops.append((w_hi, w_lo, (net.conv3.bias.detach() * gain).contiguous()))
+    return ops
+
+
+def affine_supported(net, h, w):
+    hidden = net.conv1.weight.shape[0]
+    return (tuple(net.conv1.weight.shape[2:]) == (3, 3) and tuple(net.conv2.weight.shape[2:]) == (1, 1)
+            and net.conv3.weight.shape[0] % 4 == 0 and supported(hidden, h, w))
+
+
+def affine_nn_net(net, z1, status=None):
+    """h = NN_net(z1) as three tcgen05 implicit GEMMs (3x3 -> ReLU -> 1x1 -> ReLU -> 3x3), NCHW output [B,C,H,W]."""
+    B, c, H, W = z1.shape
+    dev = z1.device
+    M = B * H * W
+    hidden = net.conv1.weight.shape[0]
+    n_out = net.conv3.weight.shape[0]
+    cache = net.__dict__.setdefault("_tc_cache", _Cache())
+    ops = cache.get(list(net.parameters()), lambda: _affine_operands(net))
+
+    def buf(*shape):
+        return torch.empty(*shape, device=dev, dtype=torch.float32)
+
+    cin0 = ops[0][0].shape[1] // 9
+    a_hi, a_lo = tc.nchw_to_nhwc_hilo(z1, cin0)
+    h1_hi, h1_lo = buf(M, hidden), buf(M, hidden)
+    tc.conv_gemm(a_hi, a_lo, ops[0][0], ops[0][1], B, H, W, cin0, hidden, 9, tc.PRE_BIAS, tc.OUT_HILO_RELU, bias=ops[0][2],
+                 out_hi=h1_hi, out_lo=h1_lo, status=status)
+    h2_hi, h2_lo = buf(M, hidden), buf(M, hidden)
+    tc.conv_gemm(h1_hi, h1_lo, ops[1][0], ops[1][1], B, H, W, hidden, hidden, 1, tc.PRE_BIAS, tc.OUT_HILO_RELU,
+                 bias=ops[1][2], out_hi=h2_hi, out_lo=h2_lo, status=status)
+    out = buf(B, n_out, H, W)
+    tc.conv_gemm(h2_hi, h2_lo, ops[2][0], ops[2][1], B, H, W, hidden, n_out, 9, tc.PRE_BIAS, tc.OUT_NCHW, bias=ops[2][2],
+                 out_nchw=out, status=status)
+    return out

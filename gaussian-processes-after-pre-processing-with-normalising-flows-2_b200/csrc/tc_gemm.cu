@@ -173,7 +173,7 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 
 // kernel parameters (device view)
 // --------------------------------------------------------------------------------------------------
 enum { PRE_BIAS = 0, PRE_GLU_RES_LN = 1 };
-enum { OUT_F32 = 1, OUT_HILO = 2, OUT_HILO_POS = 4, OUT_HILO_CELU = 8, OUT_NCHW = 16 };
+enum { OUT_F32 = 1, OUT_HILO = 2, OUT_HILO_POS = 4, OUT_HILO_CELU = 8, OUT_NCHW = 16, OUT_HILO_RELU = 32 };
 
 struct Params {
   int M, N, HW, W, H;              // M = B*H*W rows, N = total output columns of the GEMM
@@ -406,7 +406,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             if (n0 + i < p.N) o[(size_t)i * p.HW] = v[i] + (p.bias ? __ldg(p.bias + n0 + i) : 0.f);
         }
       }
-      if (p.out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_CELU)) {
+      if (p.out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_CELU | OUT_HILO_RELU)) {
         // A. lane == row: accumulator (+ the two shifted neighbours in dx-split mode) + bias -> slab[row][col]
         const int pitch = ncols_cta + 4;                             // float4-aligned, conflict-free for 128-bit access
         float* slab = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch);
@@ -453,10 +453,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const float ys[4] = {y.x, y.y, y.z, y.w};
             const size_t o = (size_t)m * p.N + n;
             if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(p.out_f32 + o) = y;
-            if (p.out_mask & OUT_HILO) {
+            if (p.out_mask & (OUT_HILO | OUT_HILO_RELU)) {             // RELU: NN_net's activations (affine_coupling.py:77-78)
               float h[4], l[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) split_tf32(ys[i], h[i], l[i]);
+              for (int i = 0; i < 4; ++i) split_tf32((p.out_mask & OUT_HILO_RELU) ? fmaxf(ys[i], 0.f) : ys[i], h[i], l[i]);
               *reinterpret_cast<float4*>(p.out_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
               *reinterpret_cast<float4*>(p.out_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
             }
@@ -737,6 +737,8 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
       n_tiles = 1;                                       // 256 < N <= 512 on a full machine: one CTA, two accumulator
       p.n_chunks = 2;                                    // chunks -> one wave instead of two
     }
+    if (a->taps == 9 && !(a->out_mask & OUT_NCHW) && W <= 32 && 32 % W == 0 && p.n_chunks == 1)
+      while (3 * p.n_chunk > 512 && p.n_chunk % 32 == 0) { p.n_chunk /= 2; n_tiles *= 2; }
     // Few M tiles (deep levels, small batches): per-CTA time is bound by the ~32 B/clk an SM can pull from / push to
     // L2, so spread the output columns over the idle SMs - narrower weight tiles and narrower epilogues per CTA.
     while (p.n_chunks == 1 && p.n_chunk % 32 == 0 && p.n_chunk >= 64 && m_tiles * n_tiles * 2 <= 148) {
@@ -767,7 +769,7 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   // epilogue staging (reuses the pipeline stages once the accumulator is complete)
   size_t epi_bytes = (size_t)4 * 32 * (cols + 4) * sizeof(float);
   if (a->pre == PRE_GLU_RES_LN) epi_bytes = (size_t)4 * 32 * (N / 2 + 4) * sizeof(float);
-  if ((a->out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_POS | OUT_HILO_CELU)) && (N & 3)) return FLOWK_ERR_SHAPE;
+  if ((a->out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_POS | OUT_HILO_CELU | OUT_HILO_RELU)) && (N & 3)) return FLOWK_ERR_SHAPE;
   while (stages > 1 && (size_t)stages * stage_bytes + 2048 > 227 * 1024) --stages;
   size_t region = (size_t)stages * stage_bytes;
   if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 6 * cols * BLOCK_K * 4;

@@ -5,7 +5,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (OUT_F32, OUT_HILO, OUT_HILO_CELU, OUT_HILO_POS, OUT_NCHW, PRE_BIAS,  # noqa: F401
+from ._lib import (OUT_F32, OUT_HILO, OUT_HILO_CELU, OUT_HILO_POS, OUT_HILO_RELU, OUT_NCHW, PRE_BIAS,  # noqa: F401
                    PRE_GLU_RES_LN)
 
 

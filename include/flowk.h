@@ -134,9 +134,11 @@ int flowk_mixture_inv_cdf(const float* y, const float* pi, const float* mu, cons
  *   FLOWK_OUT_HILO_POS   out_hi/out_lo[m, Nout] of y + pos[m % HW]    (GatedAttn input, mixlogcdf_nn.py:130-131)
  *   FLOWK_OUT_HILO_CELU  out_hi/out_lo[m, 2*Nout] of [elu(y) | elu(-y)]   (concat_elu, mixlogcdf_nn.py:8-10)
  *   FLOWK_OUT_NCHW       out_nchw[b, n, hw]                            (raw parameter tensor for flowk_mixlogcdf_*)
+ *   FLOWK_OUT_HILO_RELU  out_hi/out_lo[m, Nout] of max(y, 0)            (NN_net activations, affine_coupling.py:77-78)
  * `status` (device int, may be NULL) is set to 1 if an internal barrier wait timed out (never hangs). */
 enum { FLOWK_PRE_BIAS = 0, FLOWK_PRE_GLU_RES_LN = 1 };
-enum { FLOWK_OUT_F32 = 1, FLOWK_OUT_HILO = 2, FLOWK_OUT_HILO_POS = 4, FLOWK_OUT_HILO_CELU = 8, FLOWK_OUT_NCHW = 16 };
+enum { FLOWK_OUT_F32 = 1, FLOWK_OUT_HILO = 2, FLOWK_OUT_HILO_POS = 4, FLOWK_OUT_HILO_CELU = 8, FLOWK_OUT_NCHW = 16,
+       FLOWK_OUT_HILO_RELU = 32 };
 
 typedef struct flowk_conv_gemm_args {
   const float* a_hi;      /* activations NHWC [B,H,W,Cin] */

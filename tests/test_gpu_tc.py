@@ -134,3 +134,31 @@ def test_attention_matches_fp64(tc, B, HW, C, heads):
     ref = (torch.softmax((q * d ** -0.5) @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * HW, C)
     assert rel_err(hi + lo, ref) < 2e-5      # fp32-accumulate order over up to 1024 keys; the conditioner budget is 1e-4
     assert int((hi.view(torch.int32) & 8191).abs().max()) == 0
+
+
+@pytest.mark.parametrize("c,hidden,H,W,B", [(6, 64, 16, 16, 32), (12, 256, 8, 8, 128), (24, 256, 4, 4, 128),
+                                            (6, 256, 32, 32, 4), (48, 256, 4, 4, 16)])
+def test_affine_conditioner_tc_matches_torch_path(tc, c, hidden, H, W, B):
+    from flowk import conditioner_tc
+    from flowk.flow_modules.affine_coupling import NN_net
+    torch.manual_seed(c + hidden)
+    dev = torch.device("cuda:0")
+    net = NN_net(c, 2 * c, hidden).to(dev).eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+        x = torch.randn(B, 2 * c, H, W, device=dev)
+        z1 = x[:, :c]
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        got = conditioner_tc.affine_nn_net(net, z1, status=status)
+        conditioner_tc.ENABLED = False
+        try:
+            ref = net(z1)
+            ref64 = net.double()(z1.double())
+        finally:
+            conditioner_tc.ENABLED = True
+            net.float()
+    assert int(status) == 0
+    e_tc, e_lib = rel_err(got, ref64), rel_err(ref, ref64)
+    print("NN_net c=%d hidden=%d %dx%d: tcgen05 rel err %.2e, torch fp32 rel err %.2e" % (c, hidden, H, W, e_tc, e_lib))
+    assert e_tc < max(3e-5, 4 * e_lib)       # K = 9*256: tensor-core fp32 accumulation order
