@@ -108,8 +108,9 @@ def check(status, what=""):
     raise RuntimeError(msg)
 
 
-def call(name, *args):
-    """Enqueue one C-ABI entry point on the stream passed as its last argument."""
+def call(name, *args, meta=None):
+    """Enqueue one C-ABI entry point on the stream passed as its last argument.  `meta` (problem dimensions) is only
+    used by the optional per-launch timing table when the dimensions travel inside a struct."""
     global LAUNCHES
     LAUNCHES += 1
     if TIMING is None:
@@ -121,4 +122,4 @@ def call(name, *args):
     status = getattr(lib, name)(*args)
     end.record()
     check(status, name)
-    TIMING.setdefault(name, []).append((start, end, tuple(args[DIMS.get(name, slice(0, 0))])))
+    TIMING.setdefault(name, []).append((start, end, meta if meta is not None else tuple(args[DIMS.get(name, slice(0, 0))])))

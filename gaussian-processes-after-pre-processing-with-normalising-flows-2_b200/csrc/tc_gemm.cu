@@ -483,6 +483,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int pitch = C + 4;
       float* slab = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch);      // shared by the 4 warps of the group
       const int bar_id = 1 + lane_grp;                               // named barrier of this lane group (128 threads)
+      // 0. residual rows of this warp's 8 rows x 4 columns per lane: issue the loads now, they land during step 1
+      const int nv = (C + 127) / 128;
+      float4 resv[8][NV];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        const int m = slab_row0 + sub * 8 + rr;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c4 = v * 128 + lane * 4;
+          resv[rr][v] = (v < nv && c4 < C && m < p.M) ? __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m * C + c4))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       // 1. lane == row (straight out of TMEM): g = (a + bias_a) * sigmoid(b + bias_b)  -> slab[row][col]
       for (int j = sub * 16; j < C; j += 16 * (EPI_WARPS / 4)) {
         float a[16], b[16];
@@ -501,7 +514,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       if (tracing && threadIdx.x == 64) p.trace[6] = clock64();
       // 2. warp `sub` owns rows sub*8..+7; a lane owns 4 consecutive columns (x2 when C > 128).  Residual add,
       //    two-pass row statistics (warp-shuffle reductions), normalisation and every output form, all in registers.
-      const int nv = (C + 127) / 128;
       float g[8][NV][4], pe[8][NV][4];
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
@@ -509,13 +521,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int c4 = v * 128 + lane * 4;
-          float4 res = make_float4(0.f, 0.f, 0.f, 0.f), ps = res, gv = res;
+          float4 ps = make_float4(0.f, 0.f, 0.f, 0.f), gv = ps;
+          const float4 res = resv[rr][v];
           if (v < nv && c4 < C) {
             gv = *reinterpret_cast<const float4*>(slab + r * pitch + c4);
-            if (m < p.M) {
-              res = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m * C + c4));
-              if (p.out_mask & OUT_HILO_POS) ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(m % p.HW) * C + c4));
-            }
+            if ((p.out_mask & OUT_HILO_POS) && m < p.M)         // needed only at the very end: overlaps the statistics
+              ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(m % p.HW) * C + c4));
           }
           g[rr][v][0] = gv.x + res.x; g[rr][v][1] = gv.y + res.y; g[rr][v][2] = gv.z + res.z; g[rr][v][3] = gv.w + res.w;
           pe[rr][v][0] = ps.x; pe[rr][v][1] = ps.y; pe[rr][v][2] = ps.z; pe[rr][v][3] = ps.w;
@@ -786,15 +797,22 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     return FLOWK_ERR_ARG;
 
   dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, n_tiles);
+  static size_t smem_set[3] = {0, 0, 0};               // largest dynamic-smem opt-in requested so far, per variant
+  const int variant = a->pre == PRE_GLU_RES_LN ? (N / 2 > 128 ? 2 : 1) : 0;
+  const bool need_attr = smem_bytes > smem_set[variant];
+  if (need_attr) smem_set[variant] = smem_bytes;
   if (a->pre == PRE_GLU_RES_LN && N / 2 > 128) {
+    if (need_attr)
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
     FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));
   } else if (a->pre == PRE_GLU_RES_LN) {
+    if (need_attr)
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
     FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));
   } else {
+    if (need_attr)
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_BIAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
     FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_BIAS, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));

@@ -44,7 +44,7 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias
     args = _lib.ConvGemmArgs(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(res), _p(gamma), _p(beta), _p(pos),
                              _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status), _p(trace),
                              B, H, W, Cin, N, taps, pre, out_mask)
-    _lib.call("flowk_conv_gemm", ctypes.addressof(args), _stream())
+    _lib.call("flowk_conv_gemm", ctypes.addressof(args), _stream(), meta=(B, H, W, Cin, N, taps, pre))
 
 
 def nchw_to_nhwc_hilo(x, c_pad):
