@@ -52,7 +52,8 @@ class ConvGemmArgs(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("a_hi", "a_lo", "w_hi", "w_lo", "bias", "res", "gamma", "beta", "pos",
                  "out_f32", "out_hi", "out_lo", "out_nchw", "status", "trace")] + \
-               [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")]
+               [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")] + \
+               [(n, ctypes.c_void_p) for n in ("w2_hi", "w2_lo", "out2_f32")] + [("N2", ctypes.c_int)]
 
 
 PRE_BIAS, PRE_GLU_RES_LN = 0, 1

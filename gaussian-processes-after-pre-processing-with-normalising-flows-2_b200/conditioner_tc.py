@@ -17,6 +17,7 @@ import torch
 from . import _lib, tc
 
 ENABLED = True      # set False to force the torch/cuDNN conditioner (used by tests to A/B the two paths)
+CHAIN = True        # gate -> in_proj fused into one launch where it fits
 
 
 def supported(channels, h, w):
@@ -101,16 +102,24 @@ def mixlogcdf_nn_raw(nn_module, x_id, status=None):
         x1 = buf(M, C)
         has_attn = "in_proj" in blk
         if has_attn:
-            p_hi, p_lo = buf(M, C), buf(M, C)
             pos = nn_module.mid_convs[bi].attn._pos_enc(HW, C, dev).reshape(HW, C).contiguous()
-            tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN,
-                         tc.OUT_F32 | tc.OUT_HILO_POS, bias=bias, res=x, gamma=blk["ln1"][0], beta=blk["ln1"][1], pos=pos,
-                         out_f32=x1, out_hi=p_hi, out_lo=p_lo, status=status)
-            # G3: in_proj -> (k | v | q)
-            w_hi, w_lo, _ = blk["in_proj"]
             qkv = buf(M, 3 * C)
-            tc.conv_gemm(p_hi, p_lo, w_hi, w_lo, B, H, W, C, 3 * C, 1, tc.PRE_BIAS, tc.OUT_F32, out_f32=qkv,
-                         status=status)
+            if CHAIN and tc.chain_supported(C, 3 * C):
+                # G2 + G3 in one launch: the normalised rows (+ positional encoding) go from the epilogue into swizzled
+                # shared-memory operand tiles and are multiplied by in_proj's weight in the same CTA
+                w3_hi, w3_lo, _ = blk["in_proj"]
+                tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN, tc.OUT_F32, bias=bias,
+                             res=x, gamma=blk["ln1"][0], beta=blk["ln1"][1], pos=pos, out_f32=x1, status=status,
+                             w2_hi=w3_hi, w2_lo=w3_lo, out2_f32=qkv, n2=3 * C)
+            else:
+                p_hi, p_lo = buf(M, C), buf(M, C)
+                tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN,
+                             tc.OUT_F32 | tc.OUT_HILO_POS, bias=bias, res=x, gamma=blk["ln1"][0], beta=blk["ln1"][1],
+                             pos=pos, out_f32=x1, out_hi=p_hi, out_lo=p_lo, status=status)
+                # G3: in_proj -> (k | v | q)
+                w_hi, w_lo, _ = blk["in_proj"]
+                tc.conv_gemm(p_hi, p_lo, w_hi, w_lo, B, H, W, C, 3 * C, 1, tc.PRE_BIAS, tc.OUT_F32, out_f32=qkv,
+                             status=status)
             heads = blk["heads"]
             if tc.attention_supported(HW, C, heads):
                 t_hi, t_lo = tc.attention(qkv, B, HW, C, heads)

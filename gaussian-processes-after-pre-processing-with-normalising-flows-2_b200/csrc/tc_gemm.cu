@@ -193,6 +193,10 @@ struct Params {
   float* out_hi;                   // [M, Nout] or [M, 2*Nout] (CELU)
   float* out_lo;
   float* out_nchw;                 // [B, N, HW]
+  // chained second GEMM (GLU kernels only): rows (y [+ pos]) go from the epilogue straight into swizzled shared-memory
+  // operand tiles and are multiplied by a second weight matrix [n2, C] in the same CTA (gate -> in_proj fusion)
+  int chain, n2, n2_chunk, n2_chunks, a3_offset, w2_offset;
+  float* out2_f32;                 // [M, n2]
   int* status;                     // set to 1 if a barrier wait timed out
   long long* trace;                // optional [16] clock64 stamps of CTA (0,0): setup, first full, last mma, epi start, epi end
 };
@@ -201,6 +205,7 @@ template <int PRE, int NV>      // NV: 128-column groups per lane in the LayerNo
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                  const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A_hi | A_lo | W_hi | W_lo], then barriers
@@ -214,7 +219,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   uint64_t* wfull_bar = empty_bar + p.a_slots;
   uint64_t* wempty_bar = wfull_bar + p.w_slots;
   uint64_t* tmem_full_bar = p.dxsplit ? wempty_bar + p.w_slots : empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* a3_full_bar = tmem_full_bar + 1;      // chain: operand tiles written by the epilogue warps
+  uint64_t* w2_full_bar = tmem_full_bar + 2;
+  uint64_t* w2_empty_bar = tmem_full_bar + 3;
+  uint64_t* acc2_full_bar = tmem_full_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 5);
   volatile int* failed = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,6 +240,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(a3_full_bar, EPI_WARPS);
+    mbar_init(w2_full_bar, 1);
+    mbar_init(w2_empty_bar, 1);
+    mbar_init(acc2_full_bar, 1);
     fence_barrier_init();
     prefetch_tmap(&map_a_hi);
     prefetch_tmap(&map_a_lo);
@@ -298,6 +311,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           tma_load_2d(st + 2 * A_TILE_BYTES + c * chunk_bytes, &map_w_hi, &full_bar[s], kcol, n_base + c * p.n_chunk);
           tma_load_2d(st + 2 * A_TILE_BYTES + w_tile_bytes + c * chunk_bytes, &map_w_lo, &full_bar[s], kcol,
                       n_base + c * p.n_chunk);
+        }
+      }
+      if (p.chain) {
+        // second GEMM's weights [n2, C]: their slot lies over the (now idle) pipeline stages, so wait for the first
+        // GEMM to retire; the load then hides behind the GLU/LayerNorm epilogue
+        mbar_wait(tmem_full_bar, 0, failed);
+        const int w2_chunk_bytes = p.n2_chunk * BLOCK_K * 4, w2_half = w2_chunk_bytes * p.n2_chunks;
+        const int kb2 = (p.N >> 1) / BLOCK_K;
+        for (int kb = 0; kb < kb2; ++kb) {
+          mbar_wait(w2_empty_bar, ((uint32_t)kb & 1u) ^ 1u, failed);
+          mbar_expect_tx(w2_full_bar, 2u * (uint32_t)w2_half);
+          for (int c = 0; c < p.n2_chunks; ++c) {
+            tma_load_2d(smem + p.w2_offset + c * w2_chunk_bytes, &map_w2_hi, w2_full_bar, kb * BLOCK_K, c * p.n2_chunk);
+            tma_load_2d(smem + p.w2_offset + w2_half + c * w2_chunk_bytes, &map_w2_lo, w2_full_bar, kb * BLOCK_K,
+                        c * p.n2_chunk);
+          }
         }
       }
     }
@@ -370,6 +399,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         umma_commit(&empty_bar[s]);                                  // smem slot free once these MMAs retire
       }
       umma_commit(tmem_full_bar);                                    // accumulator complete
+      }
+      if (p.chain) {
+        mbar_wait(a3_full_bar, 0, failed);                           // epilogue warps have written the operand tiles
+        tc_fence_after();
+        const uint32_t idesc2 = make_idesc(p.n2_chunk);
+        const int kb2 = (p.N >> 1) / BLOCK_K;
+        const uint32_t w2_half = (uint32_t)(p.n2_chunk * BLOCK_K * 4 * p.n2_chunks);
+        const uint64_t chunk2_units = (uint64_t)((uint32_t)(p.n2_chunk * BLOCK_K * 4) >> 4);
+        for (int kb = 0; kb < kb2; ++kb) {
+          mbar_wait(w2_full_bar, (uint32_t)kb & 1u, failed);
+          tc_fence_after();
+          const uint64_t da_hi = make_smem_desc(smem_u32(smem + p.a3_offset + (size_t)kb * 2 * A_TILE_BYTES));
+          const uint64_t da_lo = da_hi + (A_TILE_BYTES >> 4);
+          const uint64_t db_hi = make_smem_desc(smem_u32(smem + p.w2_offset)), db_lo = db_hi + (w2_half >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
+            for (int c = 0; c < p.n2_chunks; ++c) {
+              const uint64_t co = ko + c * chunk2_units;
+              const uint32_t d = tmem_base + p.N + c * p.n2_chunk;   // second accumulator: columns after the first
+              if ((kb | k) == 0) umma_tf32(d, da_hi + ko, db_hi + co, idesc2, 0u);
+              else umma_tf32_acc(d, da_hi + ko, db_hi + co, idesc2);
+              umma_tf32_acc(d, da_lo + ko, db_hi + co, idesc2);
+              umma_tf32_acc(d, da_hi + ko, db_lo + co, idesc2);
+            }
+          }
+          umma_commit(w2_empty_bar);
+        }
+        umma_commit(acc2_full_bar);
       }
     }
   } else {
@@ -525,7 +583,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const float4 res = resv[rr][v];
           if (v < nv && c4 < C) {
             gv = *reinterpret_cast<const float4*>(slab + r * pitch + c4);
-            if ((p.out_mask & OUT_HILO_POS) && m < p.M)         // needed only at the very end: overlaps the statistics
+            if (((p.out_mask & OUT_HILO_POS) || (p.chain && p.pos)) && m < p.M)   // needed only at the end
               ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(m % p.HW) * C + c4));
           }
           g[rr][v][0] = gv.x + res.x; g[rr][v][1] = gv.y + res.y; g[rr][v][2] = gv.z + res.z; g[rr][v][3] = gv.w + res.w;
@@ -568,7 +626,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
           const int m = slab_row0 + sub * 8 + rr;
-          if (m >= p.M) continue;
+          if (m >= p.M) {
+            if (p.chain) {
+              const int R = lane_grp * 32 + sub * 8 + rr, kb = c4 >> 5, chunk = (c4 & 31) >> 2;
+              uint8_t* t = smem + p.a3_offset + (size_t)kb * 2 * A_TILE_BYTES + R * 128 + ((chunk ^ (R & 7)) << 4);
+              *reinterpret_cast<float4*>(t) = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(t + A_TILE_BYTES) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            continue;
+          }
           float y[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) y[i] = (g[rr][v][i] - mean[rr]) * rstd[rr] * gs[i] + bs[i];
@@ -593,6 +659,44 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             *reinterpret_cast<float4*>(p.out_lo + o2) = make_float4(l[0], l[1], l[2], l[3]);
             *reinterpret_cast<float4*>(p.out_hi + o2 + C) = make_float4(h2[0], h2[1], h2[2], h2[3]);
             *reinterpret_cast<float4*>(p.out_lo + o2 + C) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+          }
+          if (p.chain) {
+            // operand of the chained GEMM, written where the tensor core will read it: K-major tile of 128 rows x 128 B
+            // per 32-column block, 16-byte chunks XOR-swizzled with (row % 8) - the layout a SWIZZLE_128B TMA load
+            // would have produced
+            const int R = lane_grp * 32 + sub * 8 + rr, kb = c4 >> 5, chunk = (c4 & 31) >> 2;
+            float h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(y[i] + pe[rr][v][i], h[i], l[i]);
+            uint8_t* t = smem + p.a3_offset + (size_t)kb * 2 * A_TILE_BYTES + R * 128 + ((chunk ^ (R & 7)) << 4);
+            *reinterpret_cast<float4*>(t) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(t + A_TILE_BYTES) = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        }
+      }
+      if (p.chain) {
+        fence_proxy_async();                                         // generic-proxy smem writes -> visible to the MMA unit
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a3_full_bar)) : "memory");
+        // ---- second epilogue: rows of the chained GEMM, fp32 [M, n2]
+        mbar_wait(acc2_full_bar, 0, failed);
+        tc_fence_after();
+        const int n2 = p.n2, pitch2 = n2 + 4;
+        float* slab2 = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch2);   // all smem is idle again
+        for (int j = sub * 16; j < n2; j += 16 * (EPI_WARPS / 4)) {
+          float v16[16];
+          tmem_ld16(trow + p.N + j, v16);
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(slab2 + lane * pitch2 + j + i) = make_float4(v16[i], v16[i + 1], v16[i + 2], v16[i + 3]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        for (int c4 = lane * 4; c4 < n2; c4 += 128) {
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int r = sub * 8 + rr, m = slab_row0 + r;
+            if (m >= p.M) break;
+            *reinterpret_cast<float4*>(p.out2_f32 + (size_t)m * n2 + c4) = *reinterpret_cast<const float4*>(slab2 + r * pitch2 + c4);
           }
         }
       }
@@ -729,6 +833,7 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   p.out_nchw = a->out_nchw;
   p.status = a->status;
   p.trace = a->trace;
+  p.out2_f32 = a->out2_f32;
   int n_tiles;
   if (a->pre == PRE_GLU_RES_LN) {
     const int C = N / 2;
@@ -786,15 +891,42 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 6 * cols * BLOCK_K * 4;
   if (epi_bytes > region) region = (epi_bytes + 1023) / 1024 * 1024;
   if (region + 2048 > 227 * 1024) return FLOWK_ERR_SHAPE;
+  // chained second GEMM (gate -> in_proj): needs both accumulators in TMEM and the operand / weight tiles in smem
+  p.chain = 0;
+  if (a->w2_hi && a->w2_lo && a->out2_f32 && a->N2 > 0) {
+    const int C = N / 2, n2 = a->N2;
+    if (a->pre != PRE_GLU_RES_LN || p.n_chunks != 1 || C % BLOCK_K || n2 % 16 || N + n2 > 512) return FLOWK_ERR_SHAPE;
+    p.n2 = n2;
+    p.n2_chunks = n2 <= 256 ? 1 : 2;
+    p.n2_chunk = n2 / p.n2_chunks;
+    if (p.n2_chunk % 16 || p.n2_chunk > 256) return FLOWK_ERR_SHAPE;
+    const size_t slab = (size_t)4 * 32 * (C + 4) * sizeof(float);
+    p.a3_offset = (int)((slab + 1023) / 1024 * 1024);
+    p.w2_offset = p.a3_offset + (C / BLOCK_K) * 2 * A_TILE_BYTES;
+    const size_t chain_end = (size_t)p.w2_offset + (size_t)2 * n2 * BLOCK_K * 4;
+    const size_t slab2 = (size_t)4 * 32 * (n2 + 4) * sizeof(float);
+    if (chain_end > region) region = (chain_end + 1023) / 1024 * 1024;
+    if (slab2 > region) region = (slab2 + 1023) / 1024 * 1024;
+    if (region + 2048 > 227 * 1024) return FLOWK_ERR_SHAPE;
+    p.tmem_cols = 512;
+    p.chain = 1;
+  }
   p.stages = stages;
   p.bar_offset = (int)region;
   const size_t smem_bytes = region + 1024 + 256;
 
-  alignas(64) CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+  alignas(64) CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo;
   const int Ktot = a->taps * Cin;
   if (!make_map_act(&ma_hi, a->a_hi, B, H, W, Cin, bt, ht, wt) || !make_map_act(&ma_lo, a->a_lo, B, H, W, Cin, bt, ht, wt) ||
       !make_map_w(&mw_hi, a->w_hi, N, Ktot, p.n_chunk) || !make_map_w(&mw_lo, a->w_lo, N, Ktot, p.n_chunk))
     return FLOWK_ERR_ARG;
+  if (p.chain) {
+    if (!make_map_w(&mw2_hi, a->w2_hi, p.n2, N / 2, p.n2_chunk) || !make_map_w(&mw2_lo, a->w2_lo, p.n2, N / 2, p.n2_chunk))
+      return FLOWK_ERR_ARG;
+  } else {
+    mw2_hi = mw_hi;
+    mw2_lo = mw_lo;
+  }
 
   dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, n_tiles);
   static size_t smem_set[3] = {0, 0, 0};               // largest dynamic-smem opt-in requested so far, per variant
@@ -805,17 +937,17 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     if (need_attr)
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));
+    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));
   } else if (a->pre == PRE_GLU_RES_LN) {
     if (need_attr)
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));
+    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));
   } else {
     if (need_attr)
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_BIAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_BIAS, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, p));
+    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_BIAS, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));
   }
   return launch_status();
 }

@@ -40,10 +40,11 @@ def _p(t):
 
 
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias=None, res=None, gamma=None,
-              beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None, trace=None):
+              beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None, trace=None,
+              w2_hi=None, w2_lo=None, out2_f32=None, n2=0):
     args = _lib.ConvGemmArgs(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(res), _p(gamma), _p(beta), _p(pos),
                              _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status), _p(trace),
-                             B, H, W, Cin, N, taps, pre, out_mask)
+                             B, H, W, Cin, N, taps, pre, out_mask, _p(w2_hi), _p(w2_lo), _p(out2_f32), n2)
     _lib.call("flowk_conv_gemm", ctypes.addressof(args), _stream(), meta=(B, H, W, Cin, N, taps, pre))
 
 
@@ -76,3 +77,11 @@ def attention(qkv, B, HW, C, heads):
 def attention_supported(HW, C, heads):
     return C % heads == 0 and (C // heads) in (8, 16, 24, 32, 40, 64) and (HW <= 256 or HW % 256 == 0) and HW % 4 == 0 \
         and 2 * min(HW, 1 << 30) * (C // heads) * 4 * max(1, 256 // max(HW, 1)) <= 220 * 1024
+
+
+def chain_supported(C, n2):
+    """gate -> in_proj fusion: both accumulators in TMEM (2C + n2 <= 512 columns) and the operand tiles in smem."""
+    if C % 32 or n2 % 16 or 2 * C > 256 or 2 * C + n2 > 512:
+        return False
+    slab = ((4 * 32 * (C + 4) * 4 + 1023) // 1024) * 1024
+    return slab + (C // 32) * 32768 + 2 * n2 * 128 + 2048 <= 227 * 1024

@@ -157,6 +157,13 @@ typedef struct flowk_conv_gemm_args {
   int* status;
   long long* trace;       /* optional device [16]: clock64 stamps of CTA (0,0) for profiling; NULL in production */
   int B, H, W, Cin, N, taps, pre, out_mask;
+  /* optional chained GEMM (FLOWK_PRE_GLU_RES_LN only, N + N2 <= 512): out2_f32[m, N2] = (y [+ pos]) . W2^T with
+   * W2 = [N2, N/2] as an (hi, lo) pair - GatedAttn's in_proj applied to the normalised rows inside the same CTA
+   * (mixlogcdf_nn.py:130-136).  NULL / 0 disables it. */
+  const float* w2_hi;
+  const float* w2_lo;
+  float* out2_f32;
+  int N2;
 } flowk_conv_gemm_args;
 
 int flowk_conv_gemm(const flowk_conv_gemm_args* args, flowk_stream_t stream);

@@ -162,3 +162,34 @@ def test_affine_conditioner_tc_matches_torch_path(tc, c, hidden, H, W, B):
     e_tc, e_lib = rel_err(got, ref64), rel_err(ref, ref64)
     print("NN_net c=%d hidden=%d %dx%d: tcgen05 rel err %.2e, torch fp32 rel err %.2e" % (c, hidden, H, W, e_tc, e_lib))
     assert e_tc < max(3e-5, 4 * e_lib)       # K = 9*256: tensor-core fp32 accumulation order
+
+
+@pytest.mark.parametrize("B,C,H,W", [(64, 96, 16, 16), (64, 96, 4, 4), (3, 32, 8, 8), (5, 64, 4, 4)])
+def test_chained_gate_in_proj(tc, B, C, H, W):
+    """GLU+residual+LayerNorm GEMM with the in_proj GEMM chained inside the same CTA == the two separate launches."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(B * 7 + C)
+    M = B * H * W
+    a = torch.randn(M, 2 * C, generator=g).to(dev)
+    a_hi, a_lo = tc.split_hilo(a)
+    w_hi, w_lo = tc.split_hilo((torch.randn(2 * C, 2 * C, generator=g) / (2 * C) ** 0.5).to(dev))
+    w2 = (torch.randn(3 * C, C, generator=g) / C ** 0.5).to(dev)
+    w2_hi, w2_lo = tc.split_hilo(w2)
+    bias = torch.randn(2 * C, generator=g).to(dev)
+    res = torch.randn(M, C, generator=g).to(dev)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(dev)
+    beta = torch.randn(C, generator=g).to(dev)
+    pos = torch.randn(H * W, C, generator=g).to(dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    assert tc.chain_supported(C, 3 * C)
+    x1 = torch.empty(M, C, device=dev)
+    qkv = torch.full((M, 3 * C), float("nan"), device=dev)
+    tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN, tc.OUT_F32, bias=bias, res=res,
+                 gamma=gamma, beta=beta, pos=pos, out_f32=x1, status=status, w2_hi=w2_hi, w2_lo=w2_lo, out2_f32=qkv, n2=3 * C)
+    torch.cuda.synchronize()
+    assert int(status) == 0
+    y = a.double() @ (w_hi + w_lo).double().t() + bias.double()
+    ln = F.layer_norm(y[:, :C] * torch.sigmoid(y[:, C:]) + res.double(), (C,), gamma.double(), beta.double())
+    ref = (ln + pos.double().repeat(B, 1)) @ w2.double().t()
+    assert rel_err(x1, ln) < 1e-5
+    assert rel_err(qkv, ref) < 1e-5, rel_err(qkv, ref)
