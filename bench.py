@@ -280,13 +280,14 @@ def run_flowk(args):
 
     import flowk  # noqa: F401
     from flowk import _lib
-    from flowk.graphs import GraphedDensity
+    from flowk.graphs import DensityPipeline, GraphedDensity
 
     coupling, image, L, K, hidden, batch = WORKLOADS[args.workload]
     model = build_model(args.workload, device)
     host = [t.pin_memory() for t in synthetic_batches(8, batch, image, seed=100 + rank)]
     pool = [t.to(device) for t in host]
-    graphed = GraphedDensity(model, pool[0])
+    graphed = DensityPipeline(model, pool[0], depth=args.depth) if args.depth > 1 else GraphedDensity(model, pool[0])
+    single = graphed.lanes[0] if args.depth > 1 else graphed
     nll_sum = torch.zeros(1, device=device)
     host_out = [torch.empty(batch, pin_memory=True) for _ in range(8)]
 
@@ -295,22 +296,40 @@ def run_flowk(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def resident_step(i):
-        _, nll = graphed.run(pool[i % len(pool)])
+    def reduce_bits(nll):
         if dist is not None:                      # the path's only exchange in evaluation: the bits/dim sum
             nll_sum.copy_(nll.sum().reshape(1))
             dist.all_reduce(nll_sum)
 
+    def resident_step(i):
+        if args.depth > 1:
+            graphed.submit(pool[i % len(pool)])
+            return
+        _, nll = graphed.run(pool[i % len(pool)])
+        reduce_bits(nll)
+
     def e2e_step(i):
+        if args.depth > 1:                                    # H2D, replay and D2H all on the lane's stream
+            graphed.submit(host[i % len(host)], host_out[i % len(host_out)])
+            return
         _, nll = graphed.run(host[i % len(host)])             # H2D from pinned memory, then replay
         host_out[i % len(host_out)].copy_(nll, non_blocking=True)   # D2H of the per-image bits/dim
-        if dist is not None:
-            nll_sum.copy_(nll.sum().reshape(1))
-            dist.all_reduce(nll_sum)
+        reduce_bits(nll)
+
+    def latency_step(i):                                      # one batch at a time, same stream: per-batch latency
+        _, nll = single.run(pool[i % len(pool)])
+        reduce_bits(nll)
+
+    def finish_steps():
+        if args.depth > 1:
+            graphed.drain()
+            if dist is not None:                              # one exchange for the whole run of steps
+                reduce_bits(graphed.lanes[0].static_nll)
 
     def timed(step_fn):
         for i in range(args.warmup):
             step_fn(i)
+        finish_steps()
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -318,6 +337,7 @@ def run_flowk(args):
         start.record()
         for i in range(args.steps):
             step_fn(i)
+        finish_steps()
         end.record()
         barrier()
         sampler.stop_flag = True
@@ -331,6 +351,7 @@ def run_flowk(args):
 
     ms_res, clocks = timed(resident_step)
     ms_e2e, _ = timed(e2e_step)
+    ms_lat, _ = timed(latency_step)
     images = batch * world * args.steps
     value = images / (ms_res / 1e3)
     e2e = images / (ms_e2e / 1e3)
@@ -439,12 +460,15 @@ def run_flowk(args):
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": DESCRIBE[args.workload], "batch_per_gpu": batch, "global_batch": batch * world,
-                       "l2": "no explicit flush: one step streams 178 MB of conditioner weights (cfg2) through the "
-                             "126 MB L2 and rotates over 8 input batches",
+                       "batches_in_flight": args.depth,
+                       "l2": "no explicit flush: one step streams 2x178 MB of conditioner weight operands (cfg2) through "
+                             "the 126 MB L2 and rotates over 8 input batches",
                        "prior": "standard normal (mAR ConvLSTM prior is outside the hot path)",
                        "conditioner": "flowk tcgen05 implicit GEMMs (3xTF32) + mma.sync attention, inside the CUDA graph"},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(host[0].numel() * 4),
                     "d2h_bytes_per_step": int(batch * 4), "ms_per_step": ms_e2e / args.steps},
+            "single_stream": {"value": images / (ms_lat / 1e3), "unit": "images/s", "ms_per_step": ms_lat / args.steps,
+                              "note": "one batch in flight: the per-batch latency of the stack"},
             "gpu_launches": int(graphed.flowk_launches * args.steps),
             "flowk_launches_per_step": int(graphed.flowk_launches),
             "clocks": clocks,
@@ -513,6 +537,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-oracle step (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large", action="store_true")
+    ap.add_argument("--depth", type=int, default=6, help="batches in flight (graph instances on separate streams)")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()

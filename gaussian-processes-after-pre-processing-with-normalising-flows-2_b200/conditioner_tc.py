@@ -17,7 +17,8 @@ import torch
 from . import _lib, tc
 
 ENABLED = True      # set False to force the torch/cuDNN conditioner (used by tests to A/B the two paths)
-CHAIN = True        # gate -> in_proj fused into one launch where it fits
+CHAIN = False       # gate -> in_proj fused into one launch (works, tested; measured no faster than two PDL launches: the
+                    # second GEMM's weights cannot be prefetched for lack of shared memory) - off by default
 
 
 def supported(channels, h, w):

@@ -678,9 +678,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         fence_proxy_async();                                         // generic-proxy smem writes -> visible to the MMA unit
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a3_full_bar)) : "memory");
+        if (tracing && threadIdx.x == 64) p.trace[9] = clock64();
         // ---- second epilogue: rows of the chained GEMM, fp32 [M, n2]
         mbar_wait(acc2_full_bar, 0, failed);
         tc_fence_after();
+        if (tracing && threadIdx.x == 64) p.trace[10] = clock64();
         const int n2 = p.n2, pitch2 = n2 + 4;
         float* slab2 = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch2);   // all smem is idle again
         for (int j = sub * 16; j < n2; j += 16 * (EPI_WARPS / 4)) {
