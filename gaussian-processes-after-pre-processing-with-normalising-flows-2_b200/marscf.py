@@ -128,6 +128,10 @@ class FlowNet(nn.Module):
                 self.layers.append(Split2dMsC(C, i + 1))
                 self.output_shapes.append([-1, C // 2, H, W])
                 C = C // 2
+        if prior == "mar":          # the reference's prior (marscf_main.py:147-148), sized from the image instead of 3x32x32
+            from .mar_prior import ChannelPriorMultiScale
+            h0, w0, c0 = image_shape
+            prior = ChannelPriorMultiScale(batch_size, c0, h0, w0, L, mog=False, dp_rate=0, num_layers=3, hidden_size=32)
         self.c_prior = prior if prior is not None else StandardNormalPrior(image_shape, L)
 
     def forward(self, input, logdet=0., reverse=False, eps_std=None):
@@ -136,9 +140,9 @@ class FlowNet(nn.Module):
         return self.decode(input, eps_std)
 
     # -- forward ---------------------------------------------------------------------------------
-    def encode_latents(self, z, logdet=0.0):
+    def encode_latents(self, z, logdet=0.0, pairs=None):
         """Layer loop of FlowNet.encode (marscf_main.py:156-165) without the prior terms.
-        Returns (z_final, [z2 of every split], flow logdet)."""
+        Returns (z_final, [z2 of every split], flow logdet); `pairs` (a list) receives the (z1, z2) of every split."""
         outs = []
         layers = list(self.layers)
         i = 0
@@ -155,15 +159,16 @@ class FlowNet(nn.Module):
             if isinstance(layer, Split2dMsC):
                 z, z2 = z
                 outs.append(z2)
+                if pairs is not None:
+                    pairs.append((z, z2))
             i += 1
         return z, outs, logdet
 
     def encode(self, z, logdet=0.0):
-        z, outs, logdet = self.encode_latents(z, logdet)
-        level = 1
-        for z2 in outs:
-            logdet = logdet + self.c_prior((None, z2), level, reverse=False)
-            level += 1
+        pairs = []
+        z, outs, logdet = self.encode_latents(z, logdet, pairs)
+        for level, pair in enumerate(pairs, start=1):          # marscf_main.py:159-163
+            logdet = logdet + self.c_prior(pair, level, reverse=False)
         logdet = logdet + self.c_prior(z, self.L, reverse=False)
         return z, logdet
 

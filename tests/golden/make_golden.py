@@ -280,7 +280,34 @@ def gen_flownet(name, coupling, image, L, K, hidden, blocks, B, seed):
     save(name, meta, **arrays, **sd_arrays(model))
 
 
+def gen_mar_prior():
+    """mAR channel prior (mar_prior/corr_prior.py) - outside the hot path, pinned for the plug-in port.
+    `collections.Iterable` is aliased first: mar_prior/convolutional_rnn/utils.py:10 predates its removal."""
+    import collections
+    import collections.abc
+    collections.Iterable = collections.abc.Iterable
+    from mar_prior.corr_prior import ChannelPriorMultiScale
+    g = torch.Generator().manual_seed(31)
+    torch.manual_seed(31)
+    B, L = 2, 2
+    prior = ChannelPriorMultiScale(B, 3, 16, 16, L, mog=False, dp_rate=0, num_layers=2, hidden_size=8)
+    prior.eval()
+    z1 = torch.randn(B, 6, 8, 8, generator=g)
+    z2 = torch.randn(B, 6, 8, 8, generator=g)
+    zf = torch.randn(B, 24, 4, 4, generator=g)
+    with torch.no_grad():
+        ll1 = prior((z1, z2), 1, reverse=False)
+        ll2 = prior(zf, 2, reverse=False)
+        torch.manual_seed(77)
+        s2 = prior(None, 2, reverse=True)
+        torch.manual_seed(78)
+        s1 = prior(z1, 1, reverse=True)
+    save("mar_prior", {"B": B, "L": L, "hidden": 8, "num_layers": 2, "image_hwc": [16, 16, 3]}, z1=z1, z2=z2, zf=zf,
+         ll1=ll1, ll2=ll2, s2=s2, s1=s1, **sd_arrays(prior))
+
+
 if __name__ == "__main__":
+    gen_mar_prior()
     gen_squeeze()
     gen_actnorm()
     gen_invconv()

@@ -499,3 +499,30 @@ def test_cfg2_architecture_vs_oracle(F):
         parity(a, b, what="z2")
     parity(ld, ld_ref - float(-math.log(256.0) * 3072), what="logdet")
     assert float((nll.cpu() - nll_ref).abs().max()) < 1e-3
+
+
+def test_marscf_with_mar_prior(F):
+    """MarScfFlow with the reference's mAR channel prior plugged in: bits/dim = -(flow logdet + prior log-lik) /
+    (ln2 D) with the prior evaluated exactly as marscf_main.py:159-164 does, and unconditional sampling runs."""
+    import numpy as np
+    torch.manual_seed(5)
+    np.random.seed(5)
+    B = 4
+    model = F.marscf.MarScfFlow(B, (32, 32, 3), "affine", 3, 2, 32, prior="mar").to(dev())
+    x = torch.rand(B, 3, 32, 32, device=dev()) - 0.5
+    noise = torch.rand_like(x)
+    model.train()
+    with torch.no_grad():
+        model(x, noise=noise)
+    model.eval()
+    with torch.no_grad():
+        z, nll, _ = model(x, noise=noise)
+        pairs = []
+        d = 3 * 32 * 32
+        zf, outs, ld = model.flow.encode_latents(x + noise / 256.0, x.new_full((B,), -math.log(256.0) * d), pairs)
+        total = ld + model.flow.c_prior(zf, 3) + sum(model.flow.c_prior(p, i + 1) for i, p in enumerate(pairs))
+        assert torch.allclose(nll, -total / (math.log(2.0) * d), rtol=1e-5, atol=1e-5)
+        sample = model(None, None, reverse=True, eps_std=1.0)
+    assert sample.shape == (B, 3, 32, 32) and torch.isfinite(sample).all()
+    keys = set(model.state_dict())
+    assert "flow.c_prior.prior_list.0.prior_lstm.lstm.weight_ih_l0" in keys
