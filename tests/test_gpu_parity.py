@@ -526,3 +526,31 @@ def test_marscf_with_mar_prior(F):
     assert sample.shape == (B, 3, 32, 32) and torch.isfinite(sample).all()
     keys = set(model.state_dict())
     assert "flow.c_prior.prior_list.0.prior_lstm.lstm.weight_ih_l0" in keys
+
+
+def test_mixlogcdf_flownet_backward_vs_oracle(F, golden):
+    """Training gradients of a small MixLogCDF FlowNet (conditioner through torch autograd, flow ops through the flowk
+    forward/backward kernels) against float64 autograd through the oracle, for every parameter."""
+    g = golden("flownet_mixlogcdf")
+    model = build_from_golden(F, g, True)
+    m = g.meta
+    sd64 = {k: v.double().requires_grad_(v.dtype.is_floating_point and "is_initialized" not in k and
+                                         not k.endswith(".p") and not k.endswith("sign_s"))
+            for k, v in g.sd.items()}
+    z, outs, ldj, nll = O.normal_flow(sd64, g["x"].double(), g["noise"].double(), m["L"], m["K"], m["coupling"])
+    nll.mean().backward()
+    for p in model.parameters():
+        p.requires_grad_(True)
+    _, nll_d, _ = model(g["x"].to(dev()), noise=g["noise"].to(dev()))      # eval mode: dropout off, like the oracle
+    nll_d.mean().backward()
+    checked = 0
+    for name, p in model.named_parameters():
+        ref = sd64[name].grad
+        if ref is None:
+            continue
+        if name.endswith(".l") or name.endswith(".u"):
+            c = ref.shape[0]
+            ref = ref * (torch.tril(torch.ones(c, c), -1) if name.endswith(".l") else torch.triu(torch.ones(c, c), 1))
+        parity(p.grad, ref, rel=1e-3, what="grad " + name)
+        checked += 1
+    assert checked > 40
