@@ -62,6 +62,7 @@ class GradientBuckets:
             self._seal(cur)
         self._pending = []
         self._ready = [0] * len(self.buckets)
+        self.overlap = True          # False: no all-reduce from the hooks (CUDA-graph capture), call reduce_all()
         self._bucket_of = {}
         for bi, (_, ps) in enumerate(self.buckets):
             for p in ps:
@@ -83,8 +84,17 @@ class GradientBuckets:
             self._launch(bi)
 
     def _launch(self, bi):
-        if self.world > 1:
+        if self.world > 1 and self.overlap:
             self._pending.append(dist.all_reduce(self.buckets[bi][0], async_op=True))
+
+    def reduce_all(self):
+        """All-reduce every bucket now (used after a CUDA-graph replay of forward + backward) and average."""
+        if self.world > 1:
+            handles = [dist.all_reduce(flat, async_op=True) for flat, _ in self.buckets]
+            for h in handles:
+                h.wait()
+            for flat, _ in self.buckets:
+                flat.div_(self.world)
 
     def zero(self):
         for flat, _ in self.buckets:
@@ -109,28 +119,83 @@ class GradientBuckets:
 
 class ShardedTrainer:
     """The reference's training step (marscf_main.py:302-303,331-347): Adamax(lr=1e-4), LambdaLR warm-up on the
-    number of samples seen, loss = mean bits/dim - with the batch sharded over ranks."""
+    number of samples seen, loss = mean bits/dim - with the batch sharded over ranks.
 
-    def __init__(self, model, lr=1e-4, warm_up=10000, global_batch=None, bucket_bytes=32 << 20):
+    `use_graph` (CUDA only): the step is launch-bound in eager mode (thousands of small autograd kernels), so after
+    `graph_after` eager steps the forward + backward and the optimizer update are captured into two CUDA graphs and
+    replayed; the gradient all-reduce runs between them on the flat buckets."""
+
+    def __init__(self, model, lr=1e-4, warm_up=10000, global_batch=None, bucket_bytes=32 << 20, use_graph=None,
+                 graph_after=2):
         self.model = model
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.buckets = GradientBuckets(model.parameters(), bucket_bytes)
-        self.opt = torch.optim.Adamax(model.parameters(), lr=lr)
-        self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s: min(1., s / warm_up))
+        on_cuda = next(model.parameters()).is_cuda
+        self.use_graph = on_cuda if use_graph is None else (use_graph and on_cuda)
+        self.base_lr, self.warm_up = lr, warm_up
+        if self.use_graph:
+            self.lr_t = torch.tensor(lr, device=next(model.parameters()).device)
+            self.opt = torch.optim.Adamax(model.parameters(), lr=self.lr_t, capturable=True, foreach=True)
+            self.sched = None
+        else:
+            self.opt = torch.optim.Adamax(model.parameters(), lr=lr)
+            self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s: min(1., s / warm_up))
         self.global_step = 0
         self.global_batch = global_batch
+        self.graph_after = graph_after
+        self._calls = 0
+        self._graphs = None
+        if self.sched is None:
+            self._set_lr()             # LambdaLR's constructor applies lambda(0) = 0 to the first step, too
 
-    def step(self, x_local):
+    def _set_lr(self):
+        """LambdaLR(min(1, samples_seen / warm_up)), stepped with the sample count like marscf_main.py:346-347."""
+        if self.sched is not None:
+            self.sched.last_epoch = self.global_step - 1
+            self.sched.step()
+        else:
+            self.lr_t.fill_(self.base_lr * min(1., self.global_step / self.warm_up))
+
+    def _eager_step(self, x_local):
         self.buckets.zero()
         _, nll, _ = self.model(x_local)
         loss = nll.mean()
         loss.backward()
         self.buckets.finish()
         self.opt.step()
-        self.global_step += self.global_batch or x_local.shape[0] * self.world
-        self.sched.last_epoch = self.global_step - 1
-        self.sched.step()
         return loss.detach()
+
+    def _capture(self, x_local):
+        self.buckets.overlap = False
+        static_x = x_local.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        fb, up = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fb, stream=side):
+            self.buckets.zero()
+            _, nll, _ = self.model(static_x)
+            loss = nll.mean()
+            loss.backward()
+        with torch.cuda.graph(up, stream=side):
+            self.opt.step()
+        self._graphs = (fb, up, static_x, loss.detach())
+
+    def step(self, x_local):
+        self._calls += 1
+        if not self.use_graph or self._calls <= self.graph_after:
+            loss = self._eager_step(x_local)
+        else:
+            if self._graphs is None:
+                self._capture(x_local)
+            fb, up, static_x, loss = self._graphs
+            static_x.copy_(x_local, non_blocking=True)
+            fb.replay()
+            self.buckets.reduce_all()
+            up.replay()
+        self.global_step += self.global_batch or x_local.shape[0] * self.world
+        self._set_lr()
+        return loss
 
 
 def mean_bits_per_dim(nll_local):
