@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(512) attention_mma_kernel(const float* __restr
                                                             float* __restrict__ out_lo, int HW, int C, int heads,
                                                             int pairs_total, int pairs_per_block, int warps_per_pair,
                                                             int key_tile, float scale) {
-  extern __shared__ __align__(16) float sm[];                  // [pairs_per_block][2][key_tile][D + 4]
+  extern __shared__ __align__(16) float sm[];                  // [pairs_per_block][Khi,Klo,Vhi,Vlo][key_tile][D + 4]
   constexpr int P = D + 4;                                     // row pitch: conflict-free fragment loads
   constexpr int KS = D / 8;                                    // k-steps of QK^T == n-blocks of PV
   griddep_launch();
@@ -166,8 +166,12 @@ __global__ void __launch_bounds__(512) attention_mma_kernel(const float* __restr
   for (int nb = 0; nb < KS; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
   float mx_lo = -INFINITY, mx_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
-  float* Ks = sm + (size_t)(pl < pairs_per_block ? pl : 0) * 2 * key_tile * P;
-  float* Vs = Ks + (size_t)key_tile * P;
+  // K and V are split into their (hi, lo) TF32 parts ONCE, when the tile is staged: every element is consumed by
+  // all 16 warps of the pair, so splitting at the point of use would repeat the work 16 times
+  const uint32_t* Kh = reinterpret_cast<const uint32_t*>(sm) + (size_t)(pl < pairs_per_block ? pl : 0) * 4 * key_tile * P;
+  const uint32_t* Kl = Kh + (size_t)key_tile * P;
+  const uint32_t* Vh = Kl + (size_t)key_tile * P;
+  const uint32_t* Vl = Vh + (size_t)key_tile * P;
   constexpr int V4 = D / 4;
   for (int kt0 = 0; kt0 < HW; kt0 += key_tile) {
     __syncthreads();                                           // previous tile fully consumed
@@ -175,13 +179,18 @@ __global__ void __launch_bounds__(512) attention_mma_kernel(const float* __restr
       const int vec_per_pair = 2 * key_tile * V4;
       for (int i = threadIdx.x; i < pairs_per_block * vec_per_pair; i += blockDim.x) {
         const int pp = i / vec_per_pair, r = i - pp * vec_per_pair;
-        const int which = r / (key_tile * V4), rr = r - which * (key_tile * V4);
+        const int which = r / (key_tile * V4), rr = r - which * (key_tile * V4);      // 0: K, 1: V
         const int j = rr / V4, v4 = rr - j * V4;
         const int pr = blockIdx.x * pairs_per_block + pp;
         if (pr < pairs_total && kt0 + j < HW) {
           const int bb = pr / heads, hh = pr - bb * heads;
           const float4 val = __ldg(reinterpret_cast<const float4*>(qkv + (size_t)(bb * HW + kt0 + j) * row_stride + which * C + hh * D) + v4);
-          *reinterpret_cast<float4*>(sm + ((size_t)(pp * 2 + which) * key_tile + j) * P + v4 * 4) = val;
+          uint4 hi, lo;
+          split_bits(val.x, hi.x, lo.x); split_bits(val.y, hi.y, lo.y);
+          split_bits(val.z, hi.z, lo.z); split_bits(val.w, hi.w, lo.w);
+          uint32_t* base = reinterpret_cast<uint32_t*>(sm) + ((size_t)(pp * 4 + which * 2) * key_tile + j) * P + v4 * 4;
+          *reinterpret_cast<uint4*>(base) = hi;
+          *reinterpret_cast<uint4*>(base + (size_t)key_tile * P) = lo;
         }
       }
     }
@@ -193,12 +202,11 @@ __global__ void __launch_bounds__(512) attention_mma_kernel(const float* __restr
 #pragma unroll
       for (int kb = 0; kb < NKB; ++kb) {
         sc[kb][0] = sc[kb][1] = sc[kb][2] = sc[kb][3] = 0.f;
-        const float* kr = Ks + (size_t)(k0 + kb * 8 + g) * P + t;
+        const size_t ko = (size_t)(k0 + kb * 8 + g) * P + t;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          uint32_t bh0, bl0, bh1, bl1;
-          split_bits(kr[ks * 8], bh0, bl0);
-          split_bits(kr[ks * 8 + 4], bh1, bl1);
+          const uint32_t bh0 = Kh[ko + ks * 8], bh1 = Kh[ko + ks * 8 + 4];
+          const uint32_t bl0 = Kl[ko + ks * 8], bl1 = Kl[ko + ks * 8 + 4];
           mma_tf32(sc[kb], qh[ks], bh0, bh1);
           mma_tf32(sc[kb], ql[ks], bh0, bh1);
           mma_tf32(sc[kb], qh[ks], bl0, bl1);
@@ -231,12 +239,11 @@ __global__ void __launch_bounds__(512) attention_mma_kernel(const float* __restr
         split_bits(p2, ph[1], plo[1]);      // a1 = (row g+8, k = t)   <- key 2t
         split_bits(p1, ph[2], plo[2]);      // a2 = (row g,   k = t+4) <- key 2t+1
         split_bits(p3, ph[3], plo[3]);      // a3 = (row g+8, k = t+4) <- key 2t+1
-        const float* vr = Vs + (size_t)(k0 + kb * 8 + 2 * t) * P + g;
+        const size_t vo = (size_t)(k0 + kb * 8 + 2 * t) * P + g;
 #pragma unroll
         for (int nb = 0; nb < KS; ++nb) {
-          uint32_t bh0, bl0, bh1, bl1;
-          split_bits(vr[nb * 8], bh0, bl0);            // b0 = (k = t,   n = g) <- V[key 2t  ][dim nb*8+g]
-          split_bits(vr[P + nb * 8], bh1, bl1);        // b1 = (k = t+4, n = g) <- V[key 2t+1][dim nb*8+g]
+          const uint32_t bh0 = Vh[vo + nb * 8], bl0 = Vl[vo + nb * 8];            // b0 = (k = t,   n = g) <- V[key 2t  ][dim nb*8+g]
+          const uint32_t bh1 = Vh[vo + P + nb * 8], bl1 = Vl[vo + P + nb * 8];    // b1 = (k = t+4, n = g) <- V[key 2t+1][dim nb*8+g]
           mma_tf32(o[nb], ph, bh0, bh1);
           mma_tf32(o[nb], plo, bh0, bh1);
           mma_tf32(o[nb], ph, bl0, bl1);
@@ -276,7 +283,8 @@ static int launch_attention_mma(const float* qkv, float* out_hi, float* out_lo, 
   int pairs_per_block = 16 / warps_per_pair;
   if (pairs_per_block < 1) pairs_per_block = 1;
   const int key_tile = HW < 256 ? HW : 256;
-  const size_t smem = (size_t)pairs_per_block * 2 * key_tile * (D + 4) * sizeof(float);
+  const size_t smem = (size_t)pairs_per_block * 4 * key_tile * (D + 4) * sizeof(float);      // K, V as (hi, lo)
+  if (smem > 220 * 1024) return FLOWK_ERR_SHAPE;
   dim3 grid((pairs + pairs_per_block - 1) / pairs_per_block, (HW + warps_per_pair * 16 - 1) / (warps_per_pair * 16));
   const int threads = 32 * warps_per_pair * pairs_per_block;
   const float scale = 1.0f / sqrtf((float)D);
