@@ -11,6 +11,7 @@ import flowk  # noqa: E402,F401
 from flowk.marscf import MarScfFlow  # noqa: E402
 
 dev = torch.device("cuda:0")
+torch.backends.cudnn.benchmark = bool(int(os.environ.get("CUDNN_BENCHMARK", "0")))
 torch.manual_seed(0)
 np.random.seed(0)
 model = MarScfFlow(64, (32, 32, 3), "mixlogcdf", 3, 4, 96).to(dev).train()
