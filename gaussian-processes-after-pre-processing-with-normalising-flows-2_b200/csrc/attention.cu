@@ -130,7 +130,7 @@ __device__ __forceinline__ void split_bits(float x, uint32_t& hi, uint32_t& lo) 
 }
 
 template <int D, int NKB>      // NKB key blocks (of 8 keys) per softmax update
-__global__ void __launch_bounds__(512) attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out_hi,
+__global__ void __launch_bounds__(256, 2) attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out_hi,
                                                             float* __restrict__ out_lo, int HW, int C, int heads,
                                                             int pairs_total, int pairs_per_block, int warps_per_pair,
                                                             int key_tile, float scale) {
@@ -177,20 +177,37 @@ __global__ void __launch_bounds__(512) attention_mma_kernel(const float* __restr
     __syncthreads();                                           // previous tile fully consumed
     {                                                          // cooperative K/V tile load, all pairs of the block
       const int vec_per_pair = 2 * key_tile * V4;
-      for (int i = threadIdx.x; i < pairs_per_block * vec_per_pair; i += blockDim.x) {
-        const int pp = i / vec_per_pair, r = i - pp * vec_per_pair;
-        const int which = r / (key_tile * V4), rr = r - which * (key_tile * V4);      // 0: K, 1: V
-        const int j = rr / V4, v4 = rr - j * V4;
-        const int pr = blockIdx.x * pairs_per_block + pp;
-        if (pr < pairs_total && kt0 + j < HW) {
-          const int bb = pr / heads, hh = pr - bb * heads;
-          const float4 val = __ldg(reinterpret_cast<const float4*>(qkv + (size_t)(bb * HW + kt0 + j) * row_stride + which * C + hh * D) + v4);
-          uint4 hi, lo;
-          split_bits(val.x, hi.x, lo.x); split_bits(val.y, hi.y, lo.y);
-          split_bits(val.z, hi.z, lo.z); split_bits(val.w, hi.w, lo.w);
-          uint32_t* base = reinterpret_cast<uint32_t*>(sm) + ((size_t)(pp * 4 + which * 2) * key_tile + j) * P + v4 * 4;
-          *reinterpret_cast<uint4*>(base) = hi;
-          *reinterpret_cast<uint4*>(base + (size_t)key_tile * P) = lo;
+      const int total = pairs_per_block * vec_per_pair;
+      constexpr int U = 4;                                     // loads in flight per thread before the first use
+      for (int i0 = threadIdx.x; i0 < total; i0 += U * blockDim.x) {
+        float4 val[U];
+        uint32_t* dst[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * blockDim.x;
+          dst[u] = nullptr;
+          val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < total) {
+            const int pp = i / vec_per_pair, r = i - pp * vec_per_pair;
+            const int which = r / (key_tile * V4), rr = r - which * (key_tile * V4);      // 0: K, 1: V
+            const int j = rr / V4, v4 = rr - j * V4;
+            const int pr = blockIdx.x * pairs_per_block + pp;
+            if (pr < pairs_total && kt0 + j < HW) {
+              const int bb = pr / heads, hh = pr - bb * heads;
+              val[u] = __ldg(reinterpret_cast<const float4*>(qkv + (size_t)(bb * HW + kt0 + j) * row_stride + which * C + hh * D) + v4);
+              dst[u] = reinterpret_cast<uint32_t*>(sm) + ((size_t)(pp * 4 + which * 2) * key_tile + j) * P + v4 * 4;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (dst[u]) {
+            uint4 hi, lo;
+            split_bits(val[u].x, hi.x, lo.x); split_bits(val[u].y, hi.y, lo.y);
+            split_bits(val[u].z, hi.z, lo.z); split_bits(val[u].w, hi.w, lo.w);
+            *reinterpret_cast<uint4*>(dst[u]) = hi;
+            *reinterpret_cast<uint4*>(dst[u] + (size_t)key_tile * P) = lo;
+          }
         }
       }
     }
@@ -278,11 +295,14 @@ template <int D>
 static int launch_attention_mma(const float* qkv, float* out_hi, float* out_lo, int B, int HW, int C, int heads,
                                 cudaStream_t st) {
   const int pairs = B * heads;
+  // 8 warps (128 queries) per CTA and 128-key tiles: ~21 K registers and <= 57 KB of shared memory per CTA, so three
+  // CTAs share an SM and their dependent MMA chains overlap (one 16-warp CTA per SM left the tensor pipe ~45 % idle)
+  constexpr int kWarps = 8;
   int warps_per_pair = (HW + 15) / 16;
-  if (warps_per_pair > 16) warps_per_pair = 16;                 // 256 queries of a pair per block
-  int pairs_per_block = 16 / warps_per_pair;
+  if (warps_per_pair > kWarps) warps_per_pair = kWarps;
+  int pairs_per_block = kWarps / warps_per_pair;
   if (pairs_per_block < 1) pairs_per_block = 1;
-  const int key_tile = HW < 256 ? HW : 256;
+  const int key_tile = HW < 128 ? HW : 128;
   const size_t smem = (size_t)pairs_per_block * 4 * key_tile * (D + 4) * sizeof(float);      // K, V as (hi, lo)
   if (smem > 220 * 1024) return FLOWK_ERR_SHAPE;
   dim3 grid((pairs + pairs_per_block - 1) / pairs_per_block, (HW + warps_per_pair * 16 - 1) / (warps_per_pair * 16));
