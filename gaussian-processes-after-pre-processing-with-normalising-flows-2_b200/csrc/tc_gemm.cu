@@ -851,7 +851,7 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     p.n_chunk = per;
     p.n_chunks = 1;
     const int m_tiles = (B * H * W + BLOCK_M - 1) / BLOCK_M;
-    if (n_tiles == 2 && !(a->out_mask & OUT_NCHW) && m_tiles * 2 > 148) {
+    if (n_tiles == 2 && !(a->out_mask & OUT_NCHW) && m_tiles * 2 > 148 && n16 <= 384) {   // (epilogue slab must fit)
       n_tiles = 1;                                       // 256 < N <= 512 on a full machine: one CTA, two accumulator
       p.n_chunks = 2;                                    // chunks -> one wave instead of two
     }

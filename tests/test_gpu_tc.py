@@ -193,3 +193,15 @@ def test_chained_gate_in_proj(tc, B, C, H, W):
     ref = (ln + pos.double().repeat(B, 1)) @ w2.double().t()
     assert rel_err(x1, ln) < 1e-5
     assert rel_err(qkv, ref) < 1e-5, rel_err(qkv, ref)
+
+
+def test_wide_linear_many_rows(tc):
+    """N = 480 (in_proj of a 160-channel conditioner) with more M tiles than SMs: must take the two-N-tile path, the
+    single-CTA two-chunk variant would not fit its epilogue slab in shared memory."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(64, 160, 16, 16, generator=g).to(dev)
+    w = (torch.randn(480, 160, 1, 1, generator=g) / 160 ** 0.5).to(dev)
+    outs = run_conv(tc, x, w, None, 1, out_mask=tc.OUT_F32)
+    ref = nhwc(F.conv2d(x.double(), w.double())).reshape(-1, 480)
+    assert rel_err(outs["out_f32"], ref) < 1e-5
