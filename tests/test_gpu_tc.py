@@ -30,7 +30,7 @@ def run_conv(tc, x, w, bias, taps, out_mask=None, **kw):
     nout = N // 2 if pre == tc.PRE_GLU_RES_LN else N
     if mask & tc.OUT_F32:
         outs["out_f32"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
-    if mask & (tc.OUT_HILO | tc.OUT_HILO_POS):
+    if mask & (tc.OUT_HILO | tc.OUT_HILO_POS | tc.OUT_HILO_RELU):
         outs["out_hi"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
         outs["out_lo"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
     if mask & tc.OUT_HILO_CELU:
@@ -205,3 +205,58 @@ def test_wide_linear_many_rows(tc):
     outs = run_conv(tc, x, w, None, 1, out_mask=tc.OUT_F32)
     ref = nhwc(F.conv2d(x.double(), w.double())).reshape(-1, 480)
     assert rel_err(outs["out_f32"], ref) < 1e-5
+
+
+def test_conv_gemm_random_configuration_sweep(tc):
+    """Host-side tiling decisions (N tiles / chunks, dx-split, stage counts, epilogue staging) over a seeded sweep of
+    layer shapes; every configuration must either be refused with a shape error or match the fp64 convolution."""
+    import random
+    rnd = random.Random(1234)
+    dev = torch.device("cuda:0")
+    ran = 0
+    for trial in range(28):
+        H, W = rnd.choice([(2, 2), (4, 4), (8, 8), (16, 16), (32, 32), (8, 16), (4, 32)])
+        B = rnd.choice([1, 3, 16, 64, 130]) if H * W <= 256 else rnd.choice([1, 3, 9])
+        Cin = rnd.choice([32, 64, 96, 160, 192, 256])
+        taps = rnd.choice([1, 9])
+        pre = rnd.choice([tc.PRE_BIAS, tc.PRE_BIAS, tc.PRE_GLU_RES_LN])
+        if pre == tc.PRE_GLU_RES_LN:
+            C = rnd.choice([32, 64, 96, 160, 256])
+            N = 2 * C
+            mask = rnd.choice([tc.OUT_F32, tc.OUT_F32 | tc.OUT_HILO_CELU, tc.OUT_HILO])
+        else:
+            N = 16 * rnd.randint(1, 40)
+            mask = rnd.choice([tc.OUT_F32, tc.OUT_NCHW, tc.OUT_F32 | tc.OUT_HILO_RELU, tc.OUT_HILO_CELU])
+        g = torch.Generator(device="cpu").manual_seed(trial)
+        k = 3 if taps == 9 else 1
+        x = torch.randn(B, Cin, H, W, generator=g).to(dev)
+        w = (torch.randn(N, Cin, k, k, generator=g) / (Cin * taps) ** 0.5).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        kw = {}
+        if pre == tc.PRE_GLU_RES_LN:
+            kw = dict(pre=pre, res=torch.randn(B * H * W, N // 2, generator=g).to(dev),
+                      gamma=(torch.rand(N // 2, generator=g) + 0.5).to(dev), beta=torch.randn(N // 2, generator=g).to(dev))
+        try:
+            outs = run_conv(tc, x, w, bias, taps, out_mask=mask, **kw)
+        except AssertionError as e:
+            assert "bad shape" in str(e), e          # an honest refusal is fine; anything else is a bug
+            continue
+        ran += 1
+        y = nhwc(F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)).reshape(B * H * W, N)
+        if pre == tc.PRE_GLU_RES_LN:
+            C = N // 2
+            y = F.layer_norm(y[:, :C] * torch.sigmoid(y[:, C:]) + kw["res"].double(), (C,), kw["gamma"].double(),
+                             kw["beta"].double())
+        tol = 3e-5
+        desc = (trial, B, H, W, Cin, N, taps, pre, mask)
+        if mask & tc.OUT_F32:
+            assert rel_err(outs["out_f32"], y) < tol, desc
+        if mask & tc.OUT_NCHW:
+            assert rel_err(outs["out_nchw"], y.view(B, H, W, N).permute(0, 3, 1, 2)) < tol, desc
+        if mask & tc.OUT_HILO:
+            assert rel_err(outs["out_hi"] + outs["out_lo"], y) < tol, desc
+        if mask & tc.OUT_HILO_RELU:
+            assert rel_err(outs["out_hi"] + outs["out_lo"], torch.relu(y)) < tol, desc
+        if mask & tc.OUT_HILO_CELU:
+            assert rel_err(outs["out_hi"] + outs["out_lo"], F.elu(torch.cat((y, -y), dim=-1))) < tol, desc
+    assert ran >= 20, ran
