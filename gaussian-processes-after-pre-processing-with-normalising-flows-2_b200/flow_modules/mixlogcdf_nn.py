@@ -54,7 +54,11 @@ class _WNConvCore(_WeightNormed):
         self.padding = padding
 
     def forward(self, x):
-        return F.conv2d(x, self.normed_weight(), self.bias, padding=self.padding)
+        from .. import tc_autograd
+        w = self.normed_weight()
+        if torch.is_grad_enabled() and self.padding == w.shape[2] // 2 and tc_autograd.conv_supported(x, w):
+            return tc_autograd.conv2d(x, w, self.bias, self.padding)     # training: forward + dgrad on tcgen05
+        return F.conv2d(x, w, self.bias, padding=self.padding)
 
 
 class _WNLinear(_WeightNormed):
@@ -63,7 +67,11 @@ class _WNLinear(_WeightNormed):
         super().__init__(ref.weight, ref.bias)
 
     def forward(self, x):
-        return F.linear(x, self.normed_weight(), self.bias)
+        from .. import tc_autograd
+        w = self.normed_weight()
+        if torch.is_grad_enabled() and tc_autograd.linear_supported(x, w):
+            return tc_autograd.linear(x, w, self.bias)
+        return F.linear(x, w, self.bias)
 
 
 class WNConv2d(nn.Module):

@@ -16,6 +16,8 @@ def _stream():
 def split_hilo(t):
     """t = hi + lo with both parts rounded to nearest TF32 (13 low mantissa bits zero), like the device-side split."""
     t = t.contiguous().float()
+    if t.is_cuda and t.numel():
+        return split_rows(t)                      # one kernel (the training path re-splits weights every step)
 
     def rna(v):
         return ((v.view(torch.int32) + 0x1000) & -8192).view(torch.float32)

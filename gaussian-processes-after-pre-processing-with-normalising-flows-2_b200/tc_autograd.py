@@ -1,0 +1,133 @@
+"""Differentiable convolution / linear layers on the tcgen05 GEMM kernel, for the TRAINING path of the conditioners.
+
+The training forward keeps torch's module graph (dropout, autograd), but its dense contractions - forward and
+input-gradient (dgrad) of every conv / Linear - run through `flowk_conv_gemm` (3xTF32, fp32-accurate) instead of
+cuDNN / cuBLAS fp32 SIMT kernels; the weight gradient stays a library call (`torch.nn.grad.conv2d_weight` / matmul).
+
+    conv2d(x, w, b, padding)   x NCHW fp32  ->  NHWC (hi, lo) operand (one elementwise kernel)  ->  GEMM  ->  NCHW fp32
+    linear(x, w, b)            x [.., K] rows ->  (hi, lo) operand                               ->  GEMM  ->  rows
+
+dgrad of a 3x3 "same" conv is the same implicit GEMM on dL/dy with the taps flipped and the weight transposed.
+"""
+import torch
+
+from . import _lib, tc
+
+ENABLED = True
+
+
+def conv_supported(x, w):
+    if not (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+        return False
+    n, cin, kh, kw = w.shape
+    if (kh, kw) not in ((1, 1), (3, 3)) or n < 8 or cin < 8:          # both serve as the GEMM N (forward / dgrad)
+        return False
+    b, _, h, ww = x.shape
+    if ww > 128 or 128 % ww:
+        return False
+    hw = h * ww
+    return (hw % 128 == 0) if hw >= 128 else (128 % hw == 0)
+
+
+def _nchw_operand(x, c_pad):
+    x = x.contiguous()
+    return tc.nchw_to_nhwc_hilo(x, c_pad)
+
+
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
+class _Conv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        b, cin, h, ww = x.shape
+        n, _, kh, kw = w.shape
+        taps = kh * kw
+        cp = _pad32(cin)
+        a_hi, a_lo = _nchw_operand(x, cp)
+        w_hi, w_lo = tc.conv_weight_operand(w.detach(), cp)
+        y = torch.empty(b, n, h, ww, device=x.device, dtype=torch.float32)
+        tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, b, h, ww, cp, n, taps, tc.PRE_BIAS, tc.OUT_NCHW,
+                     bias=None if bias is None else bias.detach().contiguous(), out_nchw=y)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        b, cin, h, ww = x.shape
+        n, _, kh, kw = w.shape
+        taps = kh * kw
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # dL/dx = conv(dL/dy, w^T with the taps flipped): weight [cin, n, kh, kw] from w[n, cin, ::-1, ::-1]
+            np_ = _pad32(n)
+            g_hi, g_lo = _nchw_operand(gy, np_)
+            wt = w.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous()
+            wt_hi, wt_lo = tc.conv_weight_operand(wt, np_)
+            gx = torch.empty(x.shape, device=x.device, dtype=torch.float32)      # contiguous NCHW whatever x's strides
+            tc.conv_gemm(g_hi, g_lo, wt_hi, wt_lo, b, h, ww, np_, cin, taps, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx)
+        if ctx.needs_input_grad[1]:
+            gw = torch.nn.grad.conv2d_weight(x, w.shape, gy, padding=kh // 2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum((0, 2, 3))
+        return gx, gw, gb
+
+
+def conv2d(x, w, bias, padding):
+    """F.conv2d(x, w, bias, padding='same') for 1x1 / 3x3 kernels, stride 1."""
+    assert padding == w.shape[2] // 2
+    return _Conv2d.apply(x, w, bias)
+
+
+def linear_supported(x, w):
+    if not (ENABLED and x.is_cuda and x.dtype == torch.float32):
+        return False
+    m = x.numel() // x.shape[-1]
+    return m % 128 == 0 and w.shape[0] % 4 == 0 and w.shape[1] % 32 == 0 and x.shape[-1] == w.shape[1]
+
+
+def _rows_gemm(a, wmat, bias, n):
+    """[M, K] rows (K % 32 == 0, M % 128 == 0) times wmat[n, K]^T -> [M, n] fp32."""
+    m, k = a.shape
+    a_hi, a_lo = tc.split_rows(a.contiguous())
+    w_hi, w_lo = tc.split_hilo(wmat)
+    y = torch.empty(m, n, device=a.device, dtype=torch.float32)
+    tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, m // 128, 8, 16, k, n, 1, tc.PRE_BIAS, tc.OUT_F32, bias=bias, out_f32=y)
+    return y
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        y = _rows_gemm(x2, w.detach(), None if bias is None else bias.detach().contiguous(), w.shape[0])
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = bias is not None
+        ctx.shape = shape
+        return y.view(*shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w = ctx.saved_tensors
+        n, k = w.shape
+        g2 = gy.reshape(-1, n).contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if n % 32 == 0:
+                gx = _rows_gemm(g2, w.detach().t().contiguous(), None, k).view(ctx.shape)
+            else:
+                gx = (g2 @ w).view(ctx.shape)
+        if ctx.needs_input_grad[1]:
+            gw = g2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb
+
+
+def linear(x, w, bias):
+    return _Linear.apply(x, w, bias)

@@ -260,3 +260,35 @@ def test_conv_gemm_random_configuration_sweep(tc):
         if mask & tc.OUT_HILO_CELU:
             assert rel_err(outs["out_hi"] + outs["out_lo"], F.elu(torch.cat((y, -y), dim=-1))) < tol, desc
     assert ran >= 20, ran
+
+
+def test_training_conv_and_linear_on_tcgen05_match_torch_autograd(tc):
+    """tc_autograd.conv2d / linear (forward and input gradient on the tcgen05 kernel) against torch's float64 autograd."""
+    from flowk import tc_autograd
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(21)
+    for (B, Cin, H, W, N, k) in ((8, 192, 16, 16, 96, 3), (8, 12, 16, 16, 96, 3), (16, 96, 8, 8, 588, 3), (8, 192, 16, 16, 192, 1)):
+        x = torch.randn(B, Cin, H, W, generator=g).to(dev).requires_grad_()
+        w = (torch.randn(N, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev).requires_grad_()
+        b = torch.randn(N, generator=g).to(dev).requires_grad_()
+        gy = torch.randn(B, N, H, W, generator=g).to(dev)
+        assert tc_autograd.conv_supported(x, w)
+        y = tc_autograd.conv2d(x, w, b, k // 2)
+        y.backward(gy)
+        x64, w64, b64 = (t.detach().double().requires_grad_() for t in (x, w, b))
+        y64 = F.conv2d(x64, w64, b64, padding=k // 2)
+        y64.backward(gy.double())
+        assert rel_err(y, y64.detach()) < 2e-5
+        assert rel_err(x.grad, x64.grad) < 6e-5          # dgrad K = 9 * Cout, tensor-core fp32 accumulation order
+        assert rel_err(w.grad, w64.grad) < 2e-5
+        assert rel_err(b.grad, b64.grad) < 2e-5
+    x = torch.randn(4, 16, 16, 96, generator=g).to(dev).requires_grad_()
+    w = (torch.randn(288, 96, generator=g) / 10).to(dev).requires_grad_()
+    gy = torch.randn(4, 16, 16, 288, generator=g).to(dev)
+    assert tc_autograd.linear_supported(x, w)
+    y = tc_autograd.linear(x, w, None)
+    y.backward(gy)
+    x64, w64 = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+    y64 = F.linear(x64, w64)
+    y64.backward(gy.double())
+    assert rel_err(y, y64.detach()) < 1e-5 and rel_err(x.grad, x64.grad) < 1e-5 and rel_err(w.grad, w64.grad) < 2e-5
