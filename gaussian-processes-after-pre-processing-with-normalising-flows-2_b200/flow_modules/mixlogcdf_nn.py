@@ -15,7 +15,18 @@ import torch.nn.functional as F
 
 
 def concat_elu(x, dim=1):
+    from .. import tc_autograd
+    if tc_autograd.pointwise_ok(x):
+        return tc_autograd.concat_elu(x, dim)          # one fused kernel each way instead of neg + cat + elu
     return F.elu(torch.cat((x, -x), dim=dim))
+
+
+def _glu(x, dim):
+    from .. import tc_autograd
+    if tc_autograd.pointwise_ok(x):
+        return tc_autograd.glu(x, dim)
+    a, b = x.chunk(2, dim=dim)
+    return a * torch.sigmoid(b)
 
 
 class _WeightNormed(nn.Module):
@@ -102,8 +113,7 @@ class GatedConv(nn.Module):
         if aux is not None:
             x = x + self.aux_conv(self.nlin(aux))
         x = self.gate(self.drop(self.nlin(x)))
-        a, b = x.chunk(2, dim=1)
-        return a * torch.sigmoid(b)
+        return _glu(x, 1)
 
 
 class GatedAttn(nn.Module):
@@ -149,8 +159,7 @@ class GatedAttn(nn.Module):
         weights = torch.softmax(q @ heads_first(k).transpose(-1, -2), dim=-1)
         weights = F.dropout(weights, self.drop_prob, self.training)
         att = (weights @ heads_first(v)).permute(0, 2, 1, 3).reshape(b, h, w, c)
-        a, gate = self.gate(att).chunk(2, dim=-1)
-        return a * torch.sigmoid(gate)
+        return _glu(self.gate(att), -1)
 
 
 class ConvAttnBlock(nn.Module):

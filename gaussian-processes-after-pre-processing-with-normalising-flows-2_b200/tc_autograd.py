@@ -131,3 +131,73 @@ class _Linear(torch.autograd.Function):
 
 def linear(x, w, bias):
     return _Linear.apply(x, w, bias)
+
+
+def _oci(x, dim):
+    """(outer, channels, inner) view of splitting / concatenating along `dim`."""
+    dim = dim % x.dim()
+    outer = 1
+    for d in x.shape[:dim]:
+        outer *= int(d)
+    inner = 1
+    for d in x.shape[dim + 1:]:
+        inner *= int(d)
+    return outer, int(x.shape[dim]), inner
+
+
+class _ConcatElu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dim):
+        x = x.contiguous()
+        outer, c, inner = _oci(x, dim)
+        shape = list(x.shape)
+        shape[dim] = 2 * c
+        y = torch.empty(shape, device=x.device, dtype=torch.float32)
+        _lib.call("flowk_concat_elu_fwd", x.data_ptr(), y.data_ptr(), outer, c, inner, tc._stream())
+        ctx.save_for_backward(x)
+        ctx.dim = dim
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        outer, c, inner = _oci(x, ctx.dim)
+        gx = torch.empty_like(x)
+        _lib.call("flowk_concat_elu_bwd", x.data_ptr(), gy.contiguous().data_ptr(), gx.data_ptr(), outer, c, inner,
+                  tc._stream())
+        return gx, None
+
+
+class _Glu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dim):
+        x = x.contiguous()
+        outer, c2, inner = _oci(x, dim)
+        shape = list(x.shape)
+        shape[dim] = c2 // 2
+        y = torch.empty(shape, device=x.device, dtype=torch.float32)
+        _lib.call("flowk_glu_fwd", x.data_ptr(), y.data_ptr(), outer, c2 // 2, inner, tc._stream())
+        ctx.save_for_backward(x)
+        ctx.dim = dim
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        outer, c2, inner = _oci(x, ctx.dim)
+        gx = torch.empty_like(x)
+        _lib.call("flowk_glu_bwd", x.data_ptr(), gy.contiguous().data_ptr(), gx.data_ptr(), outer, c2 // 2, inner,
+                  tc._stream())
+        return gx, None
+
+
+def pointwise_ok(x):
+    return ENABLED and x.is_cuda and x.dtype == torch.float32
+
+
+def concat_elu(x, dim=1):
+    return _ConcatElu.apply(x, dim)
+
+
+def glu(x, dim):
+    return _Glu.apply(x, dim)

@@ -174,6 +174,18 @@ int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, int B, int C
 /* fp32 array -> (hi, lo) operand pair. */
 int flowk_split_hilo(const float* x, float* hi, float* lo, long long n, flowk_stream_t stream);
 
+/* Fused pointwise layers of the Flow++ conditioner (training path), tensors viewed as [outer, channels, inner]
+ * (inner = H*W for NCHW / dim 1, inner = 1 for NHWC / last dim):
+ *   concat_elu: x [outer, C, inner] -> y [outer, 2C, inner] = elu(cat(x, -x))        mixlogcdf_nn.py:8-10
+ *   glu:        x [outer, 2C, inner] -> y [outer, C, inner] = x[:, :C] * sigmoid(x[:, C:])   mixlogcdf_nn.py:149-151,257-258
+ * and their backward passes (gx from x and gy). */
+int flowk_concat_elu_fwd(const float* x, float* y, long long outer, int C, long long inner, flowk_stream_t stream);
+int flowk_concat_elu_bwd(const float* x, const float* gy, float* gx, long long outer, int C, long long inner,
+                         flowk_stream_t stream);
+int flowk_glu_fwd(const float* x, float* y, long long outer, int C, long long inner, flowk_stream_t stream);
+int flowk_glu_bwd(const float* x, const float* gy, float* gx, long long outer, int C, long long inner,
+                  flowk_stream_t stream);
+
 /* Self-attention core of GatedAttn (mixlogcdf_nn.py:134-147,154-173), inference: qkv = in_proj rows [B*HW, 3C] in the
  * reference's (k | v | q) column order; out_hi/out_lo [B*HW, C] = softmax(q k^T / sqrt(C/heads)) v as an operand pair.
  * C/heads in {8,16,24,32,40,64}; HW <= 256 or a multiple of 256. */

@@ -292,3 +292,27 @@ def test_training_conv_and_linear_on_tcgen05_match_torch_autograd(tc):
     y64 = F.linear(x64, w64)
     y64.backward(gy.double())
     assert rel_err(y, y64.detach()) < 1e-5 and rel_err(x.grad, x64.grad) < 1e-5 and rel_err(w.grad, w64.grad) < 2e-5
+
+
+def test_fused_pointwise_layers_match_torch_autograd():
+    from flowk import tc_autograd
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(9)
+    for shape, dim in (((3, 8, 4, 5), 1), ((2, 4, 4, 12), -1), ((64, 96, 16, 16), 1)):
+        x = torch.randn(shape, generator=g).to(dev).requires_grad_()
+        y = tc_autograd.concat_elu(x, dim)
+        gy = torch.randn(y.shape, generator=g).to(dev)
+        y.backward(gy)
+        x64 = x.detach().double().requires_grad_()
+        y64 = F.elu(torch.cat((x64, -x64), dim=dim))
+        y64.backward(gy.double())
+        assert rel_err(y, y64.detach()) < 1e-6 and rel_err(x.grad, x64.grad) < 1e-6
+        x2 = torch.randn(y.shape, generator=g).to(dev).requires_grad_()
+        z = tc_autograd.glu(x2, dim)
+        gz = torch.randn(z.shape, generator=g).to(dev)
+        z.backward(gz)
+        x264 = x2.detach().double().requires_grad_()
+        a, b = x264.chunk(2, dim=dim)
+        z64 = a * torch.sigmoid(b)
+        z64.backward(gz.double())
+        assert rel_err(z, z64.detach()) < 1e-6 and rel_err(x2.grad, x264.grad) < 1e-6
