@@ -66,10 +66,11 @@ class _WNConvCore(_WeightNormed):
 
     def forward(self, x):
         from .. import tc_autograd
-        w = self.normed_weight()
-        if torch.is_grad_enabled() and self.padding == w.shape[2] // 2 and tc_autograd.conv_supported(x, w):
-            return tc_autograd.conv2d(x, w, self.bias, self.padding)     # training: forward + dgrad on tcgen05
-        return F.conv2d(x, w, self.bias, padding=self.padding)
+        v = self.weight_v
+        if torch.is_grad_enabled() and self.padding == v.shape[2] // 2 and tc_autograd.conv_supported(x, v):
+            # training: weight norm + operands fused, forward + dgrad on tcgen05
+            return tc_autograd.wn_conv2d(x, v, self.weight_g, self.bias)
+        return F.conv2d(x, self.normed_weight(), self.bias, padding=self.padding)
 
 
 class _WNLinear(_WeightNormed):
@@ -79,10 +80,9 @@ class _WNLinear(_WeightNormed):
 
     def forward(self, x):
         from .. import tc_autograd
-        w = self.normed_weight()
-        if torch.is_grad_enabled() and tc_autograd.linear_supported(x, w):
-            return tc_autograd.linear(x, w, self.bias)
-        return F.linear(x, w, self.bias)
+        if torch.is_grad_enabled() and tc_autograd.linear_supported(x, self.weight_v):
+            return tc_autograd.wn_linear(x, self.weight_v, self.weight_g, self.bias)
+        return F.linear(x, self.normed_weight(), self.bias)
 
 
 class WNConv2d(nn.Module):

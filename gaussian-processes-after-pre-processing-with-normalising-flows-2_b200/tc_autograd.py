@@ -133,6 +133,115 @@ def linear(x, w, bias):
     return _Linear.apply(x, w, bias)
 
 
+def _wn_operands(v, g, cin_pad, n_pad, want_w=False, want_dg=True):
+    """Fused weight norm + GEMM operands (two launches): returns norm, w (or None), (fwd_hi, fwd_lo), (dg_hi, dg_lo)."""
+    n, cin = v.shape[0], v.shape[1]
+    taps = v.numel() // (n * cin)
+    dev = v.device
+    norm = torch.empty(n, device=dev, dtype=torch.float32)
+    w = torch.empty(v.shape, device=dev, dtype=torch.float32) if want_w else None
+    fwd = torch.empty(2, n, taps * cin_pad, device=dev, dtype=torch.float32)
+    dg = torch.empty(2, cin, taps * n_pad, device=dev, dtype=torch.float32) if want_dg else None
+    _lib.call("flowk_weight_norm_operands", v.data_ptr(), g.data_ptr(), n, cin, taps, cin_pad, n_pad, norm.data_ptr(),
+              tc._p(w), fwd[0].data_ptr(), fwd[1].data_ptr(), None if dg is None else dg[0].data_ptr(),
+              None if dg is None else dg[1].data_ptr(), tc._stream())
+    return norm, w, fwd, dg
+
+
+def _wn_backward(v, g, norm, gw):
+    gv = torch.empty(v.shape, device=v.device, dtype=torch.float32)
+    gg = torch.empty(g.shape, device=v.device, dtype=torch.float32)
+    _lib.call("flowk_weight_norm_bwd", v.data_ptr(), g.data_ptr(), norm.data_ptr(), gw.contiguous().data_ptr(),
+              gv.data_ptr(), gg.data_ptr(), v.shape[0], v.numel() // v.shape[0], tc._stream())
+    return gv, gg
+
+
+class _WNConv2d(torch.autograd.Function):
+    """conv2d(x, v * g / ||v||, bias) with weight norm, operand construction, forward and dgrad on libflowk."""
+
+    @staticmethod
+    def forward(ctx, x, v, g, bias):
+        b, cin, h, ww = x.shape
+        n, _, kh, kw = v.shape
+        cp, np_ = _pad32(cin), _pad32(n)
+        vd, gd = v.detach().contiguous(), g.detach().contiguous()
+        norm, _, fwd, dg = _wn_operands(vd, gd, cp, np_, want_dg=ctx.needs_input_grad[0])
+        a_hi, a_lo = _nchw_operand(x, cp)
+        y = torch.empty(b, n, h, ww, device=x.device, dtype=torch.float32)
+        tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], b, h, ww, cp, n, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW,
+                     bias=None if bias is None else bias.detach().contiguous(), out_nchw=y)
+        ctx.save_for_backward(x, vd, gd, norm, dg)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, v, g, norm, dg = ctx.saved_tensors
+        b, cin, h, ww = x.shape
+        n, _, kh, kw = v.shape
+        gy = gy.contiguous()
+        gx = gv = gg = gb = None
+        if ctx.needs_input_grad[0]:
+            np_ = _pad32(n)
+            g_hi, g_lo = _nchw_operand(gy, np_)
+            gx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+            tc.conv_gemm(g_hi, g_lo, dg[0], dg[1], b, h, ww, np_, cin, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            gw = torch.nn.grad.conv2d_weight(x, v.shape, gy, padding=kh // 2)
+            gv, gg = _wn_backward(v, g, norm, gw)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            gb = gy.sum((0, 2, 3))
+        return gx, gv, gg, gb
+
+
+class _WNLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v, g, bias):
+        shape = x.shape
+        n, k = v.shape
+        x2 = x.reshape(-1, k).contiguous()
+        vd, gd = v.detach().contiguous(), g.detach().contiguous()
+        tc_dgrad = n % 32 == 0
+        norm, w, fwd, dg = _wn_operands(vd, gd, k, n, want_w=not tc_dgrad, want_dg=tc_dgrad)
+        a_hi, a_lo = tc.split_rows(x2)
+        y = torch.empty(x2.shape[0], n, device=x.device, dtype=torch.float32)
+        tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], x2.shape[0] // 128, 8, 16, k, n, 1, tc.PRE_BIAS, tc.OUT_F32,
+                     bias=None if bias is None else bias.detach().contiguous(), out_f32=y)
+        ctx.save_for_backward(x2, vd, gd, norm, dg if tc_dgrad else w)
+        ctx.tc_dgrad, ctx.has_bias, ctx.shape = tc_dgrad, bias is not None, shape
+        return y.view(*shape[:-1], n)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, v, g, norm, wd = ctx.saved_tensors
+        n, k = v.shape
+        g2 = gy.reshape(-1, n).contiguous()
+        gx = gv = gg = gb = None
+        if ctx.needs_input_grad[0]:
+            if ctx.tc_dgrad:
+                g_hi, g_lo = tc.split_rows(g2)
+                gx = torch.empty(g2.shape[0], k, device=g2.device, dtype=torch.float32)
+                tc.conv_gemm(g_hi, g_lo, wd[0], wd[1], g2.shape[0] // 128, 8, 16, n, k, 1, tc.PRE_BIAS, tc.OUT_F32,
+                             out_f32=gx)
+                gx = gx.view(ctx.shape)
+            else:
+                gx = (g2 @ wd).view(ctx.shape)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            gv, gg = _wn_backward(v, g, norm, g2.t() @ x2)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            gb = g2.sum(0)
+        return gx, gv, gg, gb
+
+
+def wn_conv2d(x, v, g, bias):
+    """F.conv2d(x, weight_norm(v, g), bias, padding='same'), 1x1 / 3x3, stride 1 (mixlogcdf_nn.py:12-29)."""
+    return _WNConv2d.apply(x, v, g, bias)
+
+
+def wn_linear(x, v, g, bias):
+    return _WNLinearFn.apply(x, v, g, bias)
+
+
 def _oci(x, dim):
     """(outer, channels, inner) view of splitting / concatenating along `dim`."""
     dim = dim % x.dim()

@@ -186,6 +186,17 @@ int flowk_glu_fwd(const float* x, float* y, long long outer, int C, long long in
 int flowk_glu_bwd(const float* x, const float* gy, float* gx, long long outer, int C, long long inner,
                   flowk_stream_t stream);
 
+/* Weight normalisation w = v * g / ||v|| (norm over all dims but 0; `weight_norm(nn.Conv2d)`, mixlogcdf_nn.py:19-21)
+ * fused with building the flowk_conv_gemm weight operands.  v [N, cin, taps] (torch conv / linear weight), g [N].
+ * Outputs (each pair nullable): norm [N]; w [N, cin, taps] fp32; forward operand [N, taps, cin_pad] hi/lo;
+ * input-gradient operand [cin, taps, n_pad] hi/lo (taps flipped, weight transposed).  Pads are zero-filled.
+ * flowk_weight_norm_bwd: from gw = dL/dw returns gv [N, cols] and gg [N]. */
+int flowk_weight_norm_operands(const float* v, const float* g, int N, int cin, int taps, int cin_pad, int n_pad,
+                               float* norm, float* w, float* fwd_hi, float* fwd_lo, float* dg_hi, float* dg_lo,
+                               flowk_stream_t stream);
+int flowk_weight_norm_bwd(const float* v, const float* g, const float* norm, const float* gw, float* gv, float* gg,
+                          int N, int cols, flowk_stream_t stream);
+
 /* Self-attention core of GatedAttn (mixlogcdf_nn.py:134-147,154-173), inference: qkv = in_proj rows [B*HW, 3C] in the
  * reference's (k | v | q) column order; out_hi/out_lo [B*HW, C] = softmax(q k^T / sqrt(C/heads)) v as an operand pair.
  * C/heads in {8,16,24,32,40,64}; HW <= 256 or a multiple of 256. */

@@ -316,3 +316,41 @@ def test_fused_pointwise_layers_match_torch_autograd():
         z64 = a * torch.sigmoid(b)
         z64.backward(gz.double())
         assert rel_err(z, z64.detach()) < 1e-6 and rel_err(x2.grad, x264.grad) < 1e-6
+
+
+def test_weight_norm_conv_and_linear_autograd_match_fp64():
+    from flowk import tc_autograd
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(21)
+
+    def wn64(v, gg):
+        nrm = v.reshape(v.shape[0], -1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+        return v * (gg / nrm)
+
+    for (b, cin, n, k, hw) in ((4, 32, 24, 3, 16), (2, 40, 64, 1, 16), (8, 16, 588, 3, 8)):
+        x = torch.randn(b, cin, hw, hw, generator=g).to(dev).requires_grad_()
+        v = (0.2 * torch.randn(n, cin, k, k, generator=g)).to(dev).requires_grad_()
+        gg = (1 + 0.1 * torch.randn(n, 1, 1, 1, generator=g)).to(dev).requires_grad_()
+        bias = torch.randn(n, generator=g).to(dev).requires_grad_()
+        y = tc_autograd.wn_conv2d(x, v, gg, bias)
+        gy = torch.randn(y.shape, generator=g).to(dev)
+        y.backward(gy)
+        x6, v6, g6, b6 = (t.detach().double().requires_grad_() for t in (x, v, gg, bias))
+        y6 = F.conv2d(x6, wn64(v6, g6), b6, padding=k // 2)
+        y6.backward(gy.double())
+        assert rel_err(y, y6.detach()) < 2e-5
+        for a, r in ((x.grad, x6.grad), (v.grad, v6.grad), (gg.grad, g6.grad), (bias.grad, b6.grad)):
+            assert rel_err(a, r) < 1e-4, rel_err(a, r)
+    for (m, kdim, n) in ((256, 96, 288), (128, 64, 100)):
+        x = torch.randn(2, m // 2, kdim, generator=g).to(dev).requires_grad_()
+        v = (0.2 * torch.randn(n, kdim, generator=g)).to(dev).requires_grad_()
+        gg = (1 + 0.1 * torch.randn(n, 1, generator=g)).to(dev).requires_grad_()
+        y = tc_autograd.wn_linear(x, v, gg, None)
+        gy = torch.randn(y.shape, generator=g).to(dev)
+        y.backward(gy)
+        x6, v6, g6 = (t.detach().double().requires_grad_() for t in (x, v, gg))
+        y6 = F.linear(x6, wn64(v6, g6))
+        y6.backward(gy.double())
+        assert rel_err(y, y6.detach()) < 2e-5
+        for a, r in ((x.grad, x6.grad), (v.grad, v6.grad), (gg.grad, g6.grad)):
+            assert rel_err(a, r) < 1e-4, rel_err(a, r)
