@@ -195,3 +195,183 @@ extern "C" int flowk_weight_norm_bwd(const float* v, const float* g, const float
   wn_bwd_kernel<<<N, 128, 0, stream>>>(v, g, norm, gw, gv, gg, cols);
   return launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Residual add + LayerNorm over channels (ConvAttnBlock, mixlogcdf_nn.py:226-234): y = LN_C(a + b) * gamma + beta.
+// Rows are pixels m = (b, h, w); either side may be NCHW ([B, C, HW]) or NHWC rows ([M, C]) so the block's two
+// permutes cost nothing: the tile of 32 pixels x C channels is transposed through shared memory.
+// Forward also stores s = a + b (rows) and mean / rstd for the backward pass.
+namespace flowk {
+
+constexpr int kLnPix = 32;
+constexpr int kLnThreads = 256;
+
+__device__ __forceinline__ size_t ln_addr(bool nchw, long long m, int c, int C, int HW) {
+  if (!nchw) return (size_t)m * C + c;
+  const long long b = m / HW;
+  return ((size_t)b * C + c) * HW + (size_t)(m - b * HW);
+}
+
+// tile[c * 33 + p]
+template <typename F>
+__device__ __forceinline__ void ln_tile_io(bool nchw, long long m0, long long M, int C, int HW, F f) {
+  if (nchw) {
+    for (int i = threadIdx.x; i < C * kLnPix; i += kLnThreads) {
+      const int c = i >> 5, p = i & 31;
+      if (m0 + p < M) f(c, p, ln_addr(true, m0 + p, c, C, HW));
+    }
+  } else {
+    for (int i = threadIdx.x; i < C * kLnPix; i += kLnThreads) {
+      const int p = i / C, c = i - p * C;
+      if (m0 + p < M) f(c, p, (size_t)(m0 + p) * C + c);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kLnThreads) add_layernorm_fwd_kernel(
+    const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* __restrict__ y, float* __restrict__ s_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+    long long M, int C, int HW, int in_nchw, int out_nchw, float eps) {
+  extern __shared__ float tile[];
+  __shared__ float s_mean[kLnPix], s_rstd[kLnPix];
+  const long long m0 = (long long)blockIdx.x * kLnPix;
+  ln_tile_io(in_nchw, m0, M, C, HW, [&](int c, int p, size_t at) { tile[c * 33 + p] = a[at] + (b ? b[at] : 0.f); });
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int p = warp; p < kLnPix; p += kLnThreads / 32) {
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += tile[c * 33 + p];
+    const float mean = warp_sum(sum) / C;
+    float var = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = tile[c * 33 + p] - mean;
+      var = fmaf(d, d, var);
+    }
+    const float rstd = rsqrtf(warp_sum(var) / C + eps);
+    if (lane == 0) {
+      s_mean[p] = mean;
+      s_rstd[p] = rstd;
+      if (m0 + p < M) {
+        mean_out[m0 + p] = mean;
+        rstd_out[m0 + p] = rstd;
+      }
+    }
+  }
+  __syncthreads();
+  ln_tile_io(false, m0, M, C, HW, [&](int c, int p, size_t at) { s_out[at] = tile[c * 33 + p]; });
+  ln_tile_io(out_nchw, m0, M, C, HW, [&](int c, int p, size_t at) {
+    y[at] = (tile[c * 33 + p] - s_mean[p]) * s_rstd[p] * gamma[c] + beta[c];
+  });
+}
+
+// gs = rstd * (gamma*gy - mean_c(gamma*gy) - xhat * mean_c(gamma*gy*xhat));  partial dgamma/dbeta per CTA
+__global__ void __launch_bounds__(kLnThreads) add_layernorm_bwd_kernel(
+    const float* __restrict__ gy, const float* __restrict__ s, const float* __restrict__ mean, const float* __restrict__ rstd,
+    const float* __restrict__ gamma, float* __restrict__ gs, float* __restrict__ part, long long M, int C, int HW,
+    int in_nchw, int out_nchw) {
+  extern __shared__ float tile[];
+  float* tg = tile;                 // gy
+  float* tx = tile + C * 33;        // xhat
+  __shared__ float s_m1[kLnPix], s_m2[kLnPix], s_rstd[kLnPix];
+  const long long m0 = (long long)blockIdx.x * kLnPix;
+  for (int i = threadIdx.x; i < C * 33; i += kLnThreads) tg[i] = tx[i] = 0.f;      // pixels past M contribute zero
+  __syncthreads();
+  ln_tile_io(out_nchw, m0, M, C, HW, [&](int c, int p, size_t at) { tg[c * 33 + p] = gy[at]; });
+  ln_tile_io(false, m0, M, C, HW, [&](int c, int p, size_t at) {
+    tx[c * 33 + p] = (s[at] - mean[m0 + p]) * rstd[m0 + p];
+  });
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int p = warp; p < kLnPix; p += kLnThreads / 32) {
+    float m1 = 0.f, m2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float gg = gamma[c] * tg[c * 33 + p];
+      m1 += gg;
+      m2 = fmaf(gg, tx[c * 33 + p], m2);
+    }
+    m1 = warp_sum(m1) / C;
+    m2 = warp_sum(m2) / C;
+    if (lane == 0) {
+      s_m1[p] = m1;
+      s_m2[p] = m2;
+      s_rstd[p] = (m0 + p < M) ? rstd[m0 + p] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kLnThreads) {
+    float dg = 0.f, db = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < kLnPix; ++p) {
+      const float g = tg[c * 33 + p];
+      dg = fmaf(g, tx[c * 33 + p], dg);
+      db += g;
+    }
+    part[((size_t)blockIdx.x * 2) * C + c] = dg;
+    part[((size_t)blockIdx.x * 2 + 1) * C + c] = db;
+  }
+  ln_tile_io(in_nchw, m0, M, C, HW, [&](int c, int p, size_t at) {
+    gs[at] = s_rstd[p] * (gamma[c] * tg[c * 33 + p] - s_m1[p] - tx[c * 33 + p] * s_m2[p]);
+  });
+}
+
+// dgamma[c] = sum over CTAs of part[cta][0][c], dbeta likewise; fixed order -> deterministic
+__global__ void layernorm_param_grad_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, int ctas, int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), which = blockIdx.y, slice = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (c < C)
+    for (int i = slice; i < ctas; i += 8) acc += part[((size_t)i * 2 + which) * C + c];
+  red[slice][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    (which ? dbeta : dgamma)[c] = t;
+  }
+}
+
+}  // namespace flowk
+
+extern "C" long long flowk_add_layernorm_workspace_bytes(long long M, int C) {
+  return ((M + kLnPix - 1) / kLnPix) * 2 * (long long)C * (long long)sizeof(float);
+}
+
+extern "C" int flowk_add_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* y,
+                                       float* s, float* mean, float* rstd, long long M, int C, int HW, int in_nchw,
+                                       int out_nchw, float eps, flowk_stream_t stream) {
+  if (M < 0 || C < 1 || C > 512 || HW < 1 || M % HW) return FLOWK_ERR_SHAPE;
+  if (M == 0) return FLOWK_OK;
+  if (!a || !gamma || !beta || !y || !s || !mean || !rstd) return FLOWK_ERR_ARG;
+  const size_t smem = (size_t)C * 33 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(add_layernorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 33 * 4));
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(add_layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 512 * 33 * 4));
+    attr = true;
+  }
+  add_layernorm_fwd_kernel<<<(unsigned)((M + kLnPix - 1) / kLnPix), kLnThreads, smem, stream>>>(
+      a, b, gamma, beta, y, s, mean, rstd, M, C, HW, in_nchw, out_nchw, eps);
+  return launch_status();
+}
+
+extern "C" int flowk_add_layernorm_bwd(const float* gy, const float* s, const float* mean, const float* rstd,
+                                       const float* gamma, float* gs, float* dgamma, float* dbeta, void* workspace,
+                                       long long M, int C, int HW, int in_nchw, int out_nchw, flowk_stream_t stream) {
+  if (M < 1 || C < 1 || C > 512 || HW < 1 || M % HW) return FLOWK_ERR_SHAPE;
+  if (!gy || !s || !mean || !rstd || !gamma || !gs || !dgamma || !dbeta || !workspace) return FLOWK_ERR_ARG;
+  const size_t smem = (size_t)2 * C * 33 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(add_layernorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 33 * 4));
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(add_layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 512 * 33 * 4));
+    attr = true;
+  }
+  const unsigned ctas = (unsigned)((M + kLnPix - 1) / kLnPix);
+  add_layernorm_bwd_kernel<<<ctas, kLnThreads, smem, stream>>>(gy, s, mean, rstd, gamma, gs, (float*)workspace, M, C, HW,
+                                                                in_nchw, out_nchw);
+  layernorm_param_grad_kernel<<<dim3((C + 31) / 32, 2), 256, 0, stream>>>((const float*)workspace, dgamma, dbeta,
+                                                                           (int)ctas, C);
+  return launch_status();
+}

@@ -174,6 +174,13 @@ class ConvAttnBlock(nn.Module):
             self.attn = None
 
     def forward(self, x, aux=None):
+        from .. import tc_autograd
+        if tc_autograd.pointwise_ok(x) and x.size(1) <= 512:
+            # residual + LayerNorm (+ both permutes) as one kernel each way
+            x = tc_autograd.add_layernorm(self.conv(x, aux), x, self.norm_1, True, self.attn is None)
+            if self.attn:
+                x = tc_autograd.add_layernorm(self.attn(x), x, self.norm_2, False, True)
+            return x
         x = self.conv(x, aux) + x
         x = self.norm_1(x.permute(0, 2, 3, 1))
         if self.attn:

@@ -300,6 +300,48 @@ class _Glu(torch.autograd.Function):
         return gx, None
 
 
+class _AddLayerNorm(torch.autograd.Function):
+    """y = LayerNorm_C(a + b); a, b NCHW [B,C,H,W] (in_nchw) or NHWC [B,H,W,C]; y NCHW or NHWC by out_nchw."""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps, in_nchw, out_nchw):
+        a, b = a.contiguous(), b.contiguous()
+        if in_nchw:
+            bsz, c, h, w = a.shape
+        else:
+            bsz, h, w, c = a.shape
+        m, hw = bsz * h * w, h * w
+        dev = a.device
+        y = torch.empty((bsz, c, h, w) if out_nchw else (bsz, h, w, c), device=dev, dtype=torch.float32)
+        s = torch.empty(m, c, device=dev, dtype=torch.float32)
+        stats = torch.empty(2, m, device=dev, dtype=torch.float32)
+        gd, bd = gamma.detach().contiguous(), beta.detach().contiguous()
+        _lib.call("flowk_add_layernorm_fwd", a.data_ptr(), b.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(),
+                  s.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), m, c, hw, int(in_nchw), int(out_nchw),
+                  float(eps), tc._stream())
+        ctx.save_for_backward(s, stats, gd)
+        ctx.cfg = (tuple(a.shape), m, c, hw, in_nchw, out_nchw)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        s, stats, gamma = ctx.saved_tensors
+        shape, m, c, hw, in_nchw, out_nchw = ctx.cfg
+        dev = gy.device
+        gs = torch.empty(shape, device=dev, dtype=torch.float32)
+        dgb = torch.empty(2, c, device=dev, dtype=torch.float32)
+        ws = torch.empty(_lib.lib.flowk_add_layernorm_workspace_bytes(m, c) // 4, device=dev, dtype=torch.float32)
+        _lib.call("flowk_add_layernorm_bwd", gy.contiguous().data_ptr(), s.data_ptr(), stats[0].data_ptr(),
+                  stats[1].data_ptr(), gamma.data_ptr(), gs.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(),
+                  ws.data_ptr(), m, c, hw, int(in_nchw), int(out_nchw), tc._stream())
+        return gs, gs, dgb[0], dgb[1], None, None, None
+
+
+def add_layernorm(a, b, norm, in_nchw, out_nchw):
+    """`norm(a + b)` for an nn.LayerNorm over the channel dim, with the NCHW<->NHWC permutes of ConvAttnBlock folded in."""
+    return _AddLayerNorm.apply(a, b, norm.weight, norm.bias, norm.eps, in_nchw, out_nchw)
+
+
 def pointwise_ok(x):
     return ENABLED and x.is_cuda and x.dtype == torch.float32
 

@@ -197,6 +197,19 @@ int flowk_weight_norm_operands(const float* v, const float* g, int N, int cin, i
 int flowk_weight_norm_bwd(const float* v, const float* g, const float* norm, const float* gw, float* gv, float* gg,
                           int N, int cols, flowk_stream_t stream);
 
+/* Residual add + LayerNorm over channels (ConvAttnBlock, mixlogcdf_nn.py:226-234): y = LN_C(a + b) * gamma + beta.
+ * M = B*HW pixel rows; a, b (b nullable) are NCHW [B, C, HW] when in_nchw else rows [M, C]; y likewise by out_nchw.
+ * Forward also returns s = a + b as rows [M, C] and mean / rstd [M] for the backward pass, which yields
+ * gs = dL/da = dL/db (input layout) and dgamma / dbeta [C] (deterministic two-stage sum; workspace of
+ * flowk_add_layernorm_workspace_bytes(M, C) bytes, caller-owned). */
+long long flowk_add_layernorm_workspace_bytes(long long M, int C);
+int flowk_add_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* y, float* s,
+                            float* mean, float* rstd, long long M, int C, int HW, int in_nchw, int out_nchw, float eps,
+                            flowk_stream_t stream);
+int flowk_add_layernorm_bwd(const float* gy, const float* s, const float* mean, const float* rstd, const float* gamma,
+                            float* gs, float* dgamma, float* dbeta, void* workspace, long long M, int C, int HW,
+                            int in_nchw, int out_nchw, flowk_stream_t stream);
+
 /* Self-attention core of GatedAttn (mixlogcdf_nn.py:134-147,154-173), inference: qkv = in_proj rows [B*HW, 3C] in the
  * reference's (k | v | q) column order; out_hi/out_lo [B*HW, C] = softmax(q k^T / sqrt(C/heads)) v as an operand pair.
  * C/heads in {8,16,24,32,40,64}; HW <= 256 or a multiple of 256. */

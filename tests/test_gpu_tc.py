@@ -354,3 +354,33 @@ def test_weight_norm_conv_and_linear_autograd_match_fp64():
         assert rel_err(y, y6.detach()) < 2e-5
         for a, r in ((x.grad, x6.grad), (v.grad, v6.grad), (gg.grad, g6.grad)):
             assert rel_err(a, r) < 1e-4, rel_err(a, r)
+
+
+@pytest.mark.parametrize("in_nchw,out_nchw", [(True, False), (False, True), (True, True), (False, False)])
+def test_add_layernorm_matches_torch_autograd(in_nchw, out_nchw):
+    from flowk import tc_autograd
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(33)
+    for (b, c, h, w) in ((3, 96, 4, 4), (2, 24, 8, 16), (5, 160, 4, 4)):
+        norm = torch.nn.LayerNorm(c).to(dev)
+        with torch.no_grad():
+            norm.weight.copy_(1 + 0.2 * torch.randn(c, generator=g))
+            norm.bias.copy_(0.2 * torch.randn(c, generator=g))
+        shape = (b, c, h, w) if in_nchw else (b, h, w, c)
+        a = torch.randn(shape, generator=g).to(dev).requires_grad_()
+        r = torch.randn(shape, generator=g).to(dev).requires_grad_()
+        y = tc_autograd.add_layernorm(a, r, norm, in_nchw, out_nchw)
+        gy = torch.randn(y.shape, generator=g).to(dev)
+        y.backward(gy)
+        got = (y.detach(), a.grad, r.grad, norm.weight.grad.clone(), norm.bias.grad.clone())
+        a6, r6 = a.detach().double().requires_grad_(), r.detach().double().requires_grad_()
+        n6 = torch.nn.LayerNorm(c).to(dev).double()
+        n6.load_state_dict({k: v.double() for k, v in norm.state_dict().items()})
+        s6 = a6 + r6
+        y6 = n6(s6.permute(0, 2, 3, 1) if in_nchw else s6)
+        if out_nchw:
+            y6 = y6.permute(0, 3, 1, 2)
+        y6.backward(gy.double())
+        ref = (y6.detach(), a6.grad, r6.grad, n6.weight.grad, n6.bias.grad)
+        for u, v in zip(got, ref):
+            assert u.shape == v.shape and rel_err(u, v) < 5e-6, rel_err(u, v)
