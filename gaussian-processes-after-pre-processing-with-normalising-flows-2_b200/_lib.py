@@ -53,6 +53,8 @@ SIGNATURES = {
     "flowk_add_layernorm_fwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, ctypes.c_longlong, _i, _i, _i, _i,
                                  ctypes.c_float, _st], _i),
     "flowk_add_layernorm_bwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, ctypes.c_longlong, _i, _i, _i, _i, _st], _i),
+    "flowk_channel_sum_workspace_bytes": ([_i], ctypes.c_longlong),
+    "flowk_channel_sum": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
     "flowk_glu_bwd": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
 }
 

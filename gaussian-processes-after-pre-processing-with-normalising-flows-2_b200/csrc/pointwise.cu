@@ -375,3 +375,79 @@ extern "C" int flowk_add_layernorm_bwd(const float* gy, const float* s, const fl
                                                                            (int)ctas, C);
   return launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bias gradient: out[c] = sum over (b, p) of x[b, c, p]  (NCHW, inner = H*W)  or  sum over rows of x[m, c] (inner = 1).
+// Stage 1: grid (chunks, C-tiles) of fixed-order partial sums; stage 2 adds the chunks in index order (deterministic).
+namespace flowk {
+
+constexpr int kSumChunks = 64;
+
+__global__ void channel_sum_nchw_kernel(const float* __restrict__ x, float* __restrict__ part, int B, int C, int HW) {
+  // one CTA per (channel, chunk of samples)
+  __shared__ float red[8];
+  const int c = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
+  const int b0 = (int)((long long)B * chunk / chunks), b1 = (int)((long long)B * (chunk + 1) / chunks);
+  float acc = 0.f;
+  for (int b = b0; b < b1; ++b) {
+    const float* p = x + ((size_t)b * C + c) * HW;
+    for (int i = threadIdx.x; i < HW; i += 256) acc += p[i];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k];
+    part[(size_t)chunk * C + c] = t;
+  }
+}
+
+__global__ void channel_sum_rows_kernel(const float* __restrict__ x, float* __restrict__ part, long long M, int C) {
+  // CTA = 32 columns x 8 row-slices; chunk of rows per blockIdx.y
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5, chunk = blockIdx.y, chunks = gridDim.y;
+  const long long m0 = M * chunk / chunks, m1 = M * (chunk + 1) / chunks;
+  float acc = 0.f;
+  if (c < C)
+    for (long long m = m0 + slice; m < m1; m += 8) acc += x[(size_t)m * C + c];
+  red[slice][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    part[(size_t)chunk * C + c] = t;
+  }
+}
+
+__global__ void channel_sum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int chunks, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int k = 0; k < chunks; ++k) t += part[(size_t)k * C + c];
+  out[c] = t;
+}
+
+}  // namespace flowk
+
+extern "C" long long flowk_channel_sum_workspace_bytes(int C) { return (long long)kSumChunks * C * (long long)sizeof(float); }
+
+extern "C" int flowk_channel_sum(const float* x, float* out, void* workspace, long long outer, int C, long long inner,
+                                 flowk_stream_t stream) {
+  if (outer < 1 || C < 1 || inner < 1 || inner > 0x7fffffff || outer > 0x7fffffff) return FLOWK_ERR_SHAPE;
+  if (!x || !out || !workspace) return FLOWK_ERR_ARG;
+  float* part = (float*)workspace;
+  int chunks;
+  if (inner > 1) {
+    chunks = (int)(outer < kSumChunks ? outer : kSumChunks);
+    while (chunks > 1 && (long long)chunks * C > 148 * 16) chunks >>= 1;
+    channel_sum_nchw_kernel<<<dim3(C, chunks), 256, 0, stream>>>(x, part, (int)outer, C, (int)inner);
+  } else {
+    chunks = (int)(outer / 64 < 1 ? 1 : (outer / 64 > kSumChunks ? kSumChunks : outer / 64));
+    channel_sum_rows_kernel<<<dim3((C + 31) / 32, chunks), 256, 0, stream>>>(x, part, outer, C);
+  }
+  channel_sum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, out, chunks, C);
+  return launch_status();
+}

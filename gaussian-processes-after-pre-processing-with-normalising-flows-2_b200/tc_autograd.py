@@ -73,7 +73,7 @@ class _Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = torch.nn.grad.conv2d_weight(x, w.shape, gy, padding=kh // 2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum((0, 2, 3))
+            gb = channel_sum(gy, True)
         return gx, gw, gb
 
 
@@ -125,12 +125,24 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = g2.t() @ x2
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0)
+            gb = channel_sum(g2, False)
         return gx, gw, gb
 
 
 def linear(x, w, bias):
     return _Linear.apply(x, w, bias)
+
+
+def channel_sum(x, nchw):
+    """Bias gradient: x [B, C, H, W] summed over (0, 2, 3) when nchw, else rows [M, C] summed over 0; contiguous fp32."""
+    if nchw:
+        outer, c, inner = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    else:
+        outer, c, inner = x.shape[0], x.shape[1], 1
+    out = torch.empty(c, device=x.device, dtype=torch.float32)
+    ws = torch.empty(_lib.lib.flowk_channel_sum_workspace_bytes(c) // 4, device=x.device, dtype=torch.float32)
+    _lib.call("flowk_channel_sum", x.data_ptr(), out.data_ptr(), ws.data_ptr(), outer, c, inner, tc._stream())
+    return out
 
 
 def _wn_operands(v, g, cin_pad, n_pad, want_w=False, want_dg=True):
@@ -190,7 +202,7 @@ class _WNConv2d(torch.autograd.Function):
             gw = torch.nn.grad.conv2d_weight(x, v.shape, gy, padding=kh // 2)
             gv, gg = _wn_backward(v, g, norm, gw)
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            gb = gy.sum((0, 2, 3))
+            gb = channel_sum(gy, True)
         return gx, gv, gg, gb
 
 
@@ -229,7 +241,7 @@ class _WNLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             gv, gg = _wn_backward(v, g, norm, g2.t() @ x2)
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            gb = g2.sum(0)
+            gb = channel_sum(g2, False)
         return gx, gv, gg, gb
 
 

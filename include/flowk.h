@@ -210,6 +210,12 @@ int flowk_add_layernorm_bwd(const float* gy, const float* s, const float* mean, 
                             float* gs, float* dgamma, float* dbeta, void* workspace, long long M, int C, int HW,
                             int in_nchw, int out_nchw, flowk_stream_t stream);
 
+/* Bias gradient: out[c] = sum of x[o, c, i] over o < outer, i < inner (NCHW: outer = B, inner = H*W; rows: inner = 1).
+ * Deterministic two-stage sum; workspace of flowk_channel_sum_workspace_bytes(C) bytes, caller-owned. */
+long long flowk_channel_sum_workspace_bytes(int C);
+int flowk_channel_sum(const float* x, float* out, void* workspace, long long outer, int C, long long inner,
+                      flowk_stream_t stream);
+
 /* Self-attention core of GatedAttn (mixlogcdf_nn.py:134-147,154-173), inference: qkv = in_proj rows [B*HW, 3C] in the
  * reference's (k | v | q) column order; out_hi/out_lo [B*HW, C] = softmax(q k^T / sqrt(C/heads)) v as an operand pair.
  * C/heads in {8,16,24,32,40,64}; HW <= 256 or a multiple of 256. */
