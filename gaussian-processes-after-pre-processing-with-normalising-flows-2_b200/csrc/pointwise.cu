@@ -169,7 +169,49 @@ __global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restri
   for (int i = threadIdx.x; i < cols; i += 128) gv[(size_t)row * cols + i] = pg[i] * s - pv[i] * k;
 }
 
+// Same, with gw given as the split-K partial sums of flowk_conv_wgrad: partial[s][t][n][c]; added in index order.
+__global__ void wn_bwd_partials_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norm,
+                                       const float* __restrict__ partial, float* __restrict__ gv, float* __restrict__ gg,
+                                       int N, int cin, int taps, int splits, int transposed) {
+  __shared__ float part[4];
+  const int row = blockIdx.x, cols = cin * taps;
+  const size_t split_stride = (size_t)taps * N * cin;
+  auto gw_at = [&](int j) {
+    const int t = j / cin, c = j - t * cin;
+    const float* q = transposed ? partial + ((size_t)t * cin + c) * N + row : partial + ((size_t)t * N + row) * cin + c;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += q[s * split_stride];
+    return acc;
+  };
+  auto v_index = [&](int j) {
+    const int t = j / cin, c = j - t * cin;
+    return (size_t)row * cols + (size_t)c * taps + t;
+  };
+  float d = 0.f;
+  for (int j = threadIdx.x; j < cols; j += 128) d = fmaf(gw_at(j), v[v_index(j)], d);
+  d = warp_sum(d);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = d;
+  __syncthreads();
+  const float dot = (part[0] + part[1]) + (part[2] + part[3]);
+  const float nr = norm[row], gr = g[row];
+  const float s = gr / nr, k = dot * gr / (nr * nr * nr);
+  if (threadIdx.x == 0) gg[row] = dot / nr;
+  for (int j = threadIdx.x; j < cols; j += 128) {
+    const size_t at = v_index(j);
+    gv[at] = gw_at(j) * s - v[at] * k;
+  }
+}
+
 }  // namespace flowk
+
+extern "C" int flowk_weight_norm_bwd_partials(const float* v, const float* g, const float* norm, const float* partial,
+                                              float* gv, float* gg, int N, int cin, int taps, int splits,
+                                              int transposed, flowk_stream_t stream) {
+  if (N < 1 || cin < 1 || taps < 1 || splits < 1) return FLOWK_ERR_SHAPE;
+  if (!v || !g || !norm || !partial || !gv || !gg) return FLOWK_ERR_ARG;
+  wn_bwd_partials_kernel<<<N, 128, 0, stream>>>(v, g, norm, partial, gv, gg, N, cin, taps, splits, transposed);
+  return launch_status();
+}
 
 extern "C" int flowk_weight_norm_operands(const float* v, const float* g, int N, int cin, int taps, int cin_pad, int n_pad,
                                           float* norm, float* w, float* fwd_hi, float* fwd_lo, float* dg_hi, float* dg_lo,

@@ -9,6 +9,8 @@ cuDNN / cuBLAS fp32 SIMT kernels; the weight gradient stays a library call (`tor
 
 dgrad of a 3x3 "same" conv is the same implicit GEMM on dL/dy with the taps flipped and the weight transposed.
 """
+import ctypes
+
 import torch
 
 from . import _lib, tc
@@ -160,6 +162,45 @@ def _wn_operands(v, g, cin_pad, n_pad, want_w=False, want_dg=True):
     return norm, w, fwd, dg
 
 
+WGRAD_LINEAR_TC = False   # the two transposes cost more than the cuBLAS fp32 GEMM they would replace
+WGRAD_TC = True      # weight gradients on the tcgen05 split-K kernel (else cuDNN / cuBLAS fp32)
+
+
+def wgrad_partials(x_cm, gy_cm, taps):
+    """Split-K partial weight gradients from channel-major fp32 x [B,Cin,H,W], gy [B,N,H,W]: (partial, transposed) with
+    partial [S, taps, N, Cin] (or [S, taps, Cin, N] when transposed); None when the tcgen05 kernel does not take the shape."""
+    b, cin, h, w = x_cm.shape
+    n = gy_cm.shape[1]
+    if not WGRAD_TC:
+        return None
+    transposed = ctypes.c_int(0)
+    splits = _lib.lib.flowk_conv_wgrad_splits(b, h, w, cin, n, taps, ctypes.byref(transposed))
+    if splits <= 0:
+        return None
+    transposed = bool(transposed.value)
+    partial = torch.empty((splits, taps, cin, n) if transposed else (splits, taps, n, cin), device=x_cm.device,
+                          dtype=torch.float32)
+    xl = xr = None
+    if taps == 9:
+        shifted = torch.empty((2,) + tuple(x_cm.shape), device=x_cm.device, dtype=torch.float32)
+        xl, xr = shifted[0], shifted[1]
+        _lib.call("flowk_shift_columns", x_cm.data_ptr(), xl.data_ptr(), xr.data_ptr(), x_cm.numel(), w, tc._stream())
+    _lib.call("flowk_conv_wgrad", x_cm.data_ptr(), tc._p(xl), tc._p(xr), gy_cm.data_ptr(), partial.data_ptr(), None,
+              b, h, w, cin, n, taps, tc._stream())
+    return partial, transposed
+
+
+def _wn_backward_partials(v, g, norm, partial_t):
+    partial, transposed = partial_t
+    n, cin = v.shape[0], v.shape[1]
+    taps = v.numel() // (n * cin)
+    gv = torch.empty(v.shape, device=v.device, dtype=torch.float32)
+    gg = torch.empty(g.shape, device=v.device, dtype=torch.float32)
+    _lib.call("flowk_weight_norm_bwd_partials", v.data_ptr(), g.data_ptr(), norm.data_ptr(), partial.data_ptr(),
+              gv.data_ptr(), gg.data_ptr(), n, cin, taps, partial.shape[0], int(transposed), tc._stream())
+    return gv, gg
+
+
 def _wn_backward(v, g, norm, gw):
     gv = torch.empty(v.shape, device=v.device, dtype=torch.float32)
     gg = torch.empty(g.shape, device=v.device, dtype=torch.float32)
@@ -199,8 +240,11 @@ class _WNConv2d(torch.autograd.Function):
             gx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
             tc.conv_gemm(g_hi, g_lo, dg[0], dg[1], b, h, ww, np_, cin, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            gw = torch.nn.grad.conv2d_weight(x, v.shape, gy, padding=kh // 2)
-            gv, gg = _wn_backward(v, g, norm, gw)
+            partial = wgrad_partials(x.contiguous(), gy, kh * kw)
+            if partial is not None:
+                gv, gg = _wn_backward_partials(v, g, norm, partial)
+            else:
+                gv, gg = _wn_backward(v, g, norm, torch.nn.grad.conv2d_weight(x, v.shape, gy, padding=kh // 2))
         if ctx.has_bias and ctx.needs_input_grad[3]:
             gb = channel_sum(gy, True)
         return gx, gv, gg, gb
@@ -239,7 +283,15 @@ class _WNLinearFn(torch.autograd.Function):
             else:
                 gx = (g2 @ wd).view(ctx.shape)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            gv, gg = _wn_backward(v, g, norm, g2.t() @ x2)
+            m = x2.shape[0]
+            partial = None
+            if WGRAD_LINEAR_TC and m % 32 == 0:      # needs both operands transposed to channel-major first
+                partial = wgrad_partials(x2.t().contiguous().view(1, k, m // 32, 32),
+                                         g2.t().contiguous().view(1, n, m // 32, 32), 1)
+            if partial is not None:
+                gv, gg = _wn_backward_partials(v, g, norm, partial)
+            else:
+                gv, gg = _wn_backward(v, g, norm, g2.t() @ x2)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             gb = channel_sum(g2, False)
         return gx, gv, gg, gb

@@ -216,6 +216,24 @@ long long flowk_channel_sum_workspace_bytes(int C);
 int flowk_channel_sum(const float* x, float* out, void* workspace, long long outer, int C, long long inner,
                       flowk_stream_t stream);
 
+/* Weight gradient of a stride-1 "same" convolution (taps = 1 or 9) / linear layer on tcgen05 (3xTF32, fp32-accurate):
+ *   partial[s][t][n][c] = sum over the s-th slice of (b, pixel) of gy[b, n, p] * x[b, c, p + shift(t)]
+ * x [B, Cin, H, W] and gy [B, N, H, W] are plain fp32 channel-major (NCHW) tensors (W % 4 == 0, H*W % 32 == 0); a
+ * linear layer passes its transposed operands as B = 1, H = M / 32, W = 32.  For taps = 9 the caller also passes the
+ * column-shifted copies of x made by flowk_shift_columns: x_left[.., w] = x[.., w-1], x_right[.., w] = x[.., w+1],
+ * zero at the image border (a TMA box cannot start at an unaligned innermost coordinate).  flowk_conv_wgrad_splits returns how many split-K slices the
+ * launch writes (0: shape not supported) and whether the kernel puts x on the 128-row side of the MMA, in which case
+ * the slices are stored transposed, [splits, taps, Cin, N] (*transposed = 1); the caller allocates partial
+ * [splits, taps, N, Cin] floats and sums the slices in index order (flowk_weight_norm_bwd_partials does, fused with the weight-norm backward).
+ * status: optional device int, set to 1 if a pipeline wait timed out (protocol bug; never hangs). */
+int flowk_conv_wgrad_splits(int B, int H, int W, int Cin, int N, int taps, int* transposed);
+int flowk_conv_wgrad(const float* x, const float* x_left, const float* x_right, const float* gy, float* partial,
+                     int* status, int B, int H, int W, int Cin, int N, int taps, flowk_stream_t stream);
+int flowk_shift_columns(const float* x, float* x_left, float* x_right, long long total, int W, flowk_stream_t stream);
+int flowk_weight_norm_bwd_partials(const float* v, const float* g, const float* norm, const float* partial, float* gv,
+                                   float* gg, int N, int cin, int taps, int splits, int transposed,
+                                   flowk_stream_t stream);
+
 /* Self-attention core of GatedAttn (mixlogcdf_nn.py:134-147,154-173), inference: qkv = in_proj rows [B*HW, 3C] in the
  * reference's (k | v | q) column order; out_hi/out_lo [B*HW, C] = softmax(q k^T / sqrt(C/heads)) v as an operand pair.
  * C/heads in {8,16,24,32,40,64}; HW <= 256 or a multiple of 256. */

@@ -384,3 +384,21 @@ def test_add_layernorm_matches_torch_autograd(in_nchw, out_nchw):
         ref = (y6.detach(), a6.grad, r6.grad, n6.weight.grad, n6.bias.grad)
         for u, v in zip(got, ref):
             assert u.shape == v.shape and rel_err(u, v) < 5e-6, rel_err(u, v)
+
+
+@pytest.mark.parametrize("b,cin,n,k,h,w", [(2, 32, 32, 1, 8, 16), (4, 24, 40, 3, 16, 16), (8, 192, 96, 3, 8, 8),
+                                           (3, 96, 588, 3, 8, 8), (2, 320, 160, 3, 8, 8), (1, 96, 288, 1, 64, 32)])
+def test_conv_wgrad_tcgen05_matches_fp64(b, cin, n, k, h, w):
+    from flowk import tc_autograd
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(b, cin, h, w, generator=g).to(dev)
+    gy = torch.randn(b, n, h, w, generator=g).to(dev)
+    out = tc_autograd.wgrad_partials(x, gy, k * k)
+    assert out is not None
+    partial, transposed = out
+    got = (partial.sum(0).permute(2, 1, 0) if transposed else partial.sum(0).permute(1, 2, 0)).reshape(n, cin, k, k)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (n, cin, k, k), gy.double(), padding=k // 2)
+    assert rel_err(got, ref) < 2e-5
+    again, _ = tc_autograd.wgrad_partials(x, gy, k * k)
+    assert torch.equal(again, partial)                       # split-K partials are deterministic
