@@ -169,36 +169,45 @@ __global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restri
   for (int i = threadIdx.x; i < cols; i += 128) gv[(size_t)row * cols + i] = pg[i] * s - pv[i] * k;
 }
 
-// Same, with gw given as the split-K partial sums of flowk_conv_wgrad: partial[s][t][n][c]; added in index order.
-__global__ void wn_bwd_partials_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norm,
-                                       const float* __restrict__ partial, float* __restrict__ gv, float* __restrict__ gg,
-                                       int N, int cin, int taps, int splits, int transposed) {
-  __shared__ float part[4];
+// Same, with gw given as the split-K partial sums of flowk_conv_wgrad: partial[s][t][n][c] (or [s][t][c][n] when
+// transposed); the slices are added in index order.  The reduced row is staged in shared memory (cols floats).
+__global__ void __launch_bounds__(256) wn_bwd_partials_kernel(
+    const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norm,
+    const float* __restrict__ partial, float* __restrict__ gv, float* __restrict__ gg, int N, int cin, int taps, int splits,
+    int transposed) {
+  extern __shared__ float gw_row[];           // [cols] in (t, c) order
+  __shared__ float part[8];
   const int row = blockIdx.x, cols = cin * taps;
   const size_t split_stride = (size_t)taps * N * cin;
-  auto gw_at = [&](int j) {
+  float d = 0.f;
+  for (int j = threadIdx.x; j < cols; j += 256) {
     const int t = j / cin, c = j - t * cin;
     const float* q = transposed ? partial + ((size_t)t * cin + c) * N + row : partial + ((size_t)t * N + row) * cin + c;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += q[s * split_stride];
-    return acc;
-  };
-  auto v_index = [&](int j) {
-    const int t = j / cin, c = j - t * cin;
-    return (size_t)row * cols + (size_t)c * taps + t;
-  };
-  float d = 0.f;
-  for (int j = threadIdx.x; j < cols; j += 128) d = fmaf(gw_at(j), v[v_index(j)], d);
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {          // four independent loads in flight, summed in index order
+      const float a0 = q[(size_t)s * split_stride], a1 = q[(size_t)(s + 1) * split_stride];
+      const float a2 = q[(size_t)(s + 2) * split_stride], a3 = q[(size_t)(s + 3) * split_stride];
+      acc = (((acc + a0) + a1) + a2) + a3;
+    }
+    for (; s < splits; ++s) acc += q[(size_t)s * split_stride];
+    gw_row[j] = acc;
+    d = fmaf(acc, v[(size_t)row * cols + (size_t)c * taps + t], d);
+  }
   d = warp_sum(d);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = d;
   __syncthreads();
-  const float dot = (part[0] + part[1]) + (part[2] + part[3]);
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dot += part[k];
   const float nr = norm[row], gr = g[row];
-  const float s = gr / nr, k = dot * gr / (nr * nr * nr);
+  const float sc = gr / nr, k3 = dot * gr / (nr * nr * nr);
   if (threadIdx.x == 0) gg[row] = dot / nr;
-  for (int j = threadIdx.x; j < cols; j += 128) {
-    const size_t at = v_index(j);
-    gv[at] = gw_at(j) * s - v[at] * k;
+  // second pass in v's own (c, t) order so the gv stores coalesce
+  for (int i = threadIdx.x; i < cols; i += 256) {
+    const int c = i / taps, t = i - c * taps;
+    const size_t at = (size_t)row * cols + i;
+    gv[at] = gw_row[t * cin + c] * sc - v[at] * k3;
   }
 }
 
@@ -209,7 +218,9 @@ extern "C" int flowk_weight_norm_bwd_partials(const float* v, const float* g, co
                                               int transposed, flowk_stream_t stream) {
   if (N < 1 || cin < 1 || taps < 1 || splits < 1) return FLOWK_ERR_SHAPE;
   if (!v || !g || !norm || !partial || !gv || !gg) return FLOWK_ERR_ARG;
-  wn_bwd_partials_kernel<<<N, 128, 0, stream>>>(v, g, norm, partial, gv, gg, N, cin, taps, splits, transposed);
+  if ((size_t)cin * taps * sizeof(float) > 48 * 1024) return FLOWK_ERR_SHAPE;
+  wn_bwd_partials_kernel<<<N, 256, (size_t)cin * taps * sizeof(float), stream>>>(v, g, norm, partial, gv, gg, N, cin, taps,
+                                                                              splits, transposed);
   return launch_status();
 }
 
