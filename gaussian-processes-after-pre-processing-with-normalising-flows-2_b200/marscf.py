@@ -3,9 +3,10 @@
 
 This is variant "A minus attention" of SURVEY.md section 0: ActNorm -> invertible 1x1 conv ->
 (affine | MixLogCDF) coupling (-> TupleFlip), the stack BASELINE.json's north_star names.  The
-fork's two `Transformer_attn` layers and the ConvLSTM channel prior are outside that path; the
-prior is a plug-in (`prior=`) with the reference's `c_prior(z, level, reverse)` call signature and
-defaults to a standard normal.
+fork's two `Transformer_attn` layers and the ConvLSTM channel prior are outside that path; both are
+plug-ins: `attn=True` inserts the patch-attention layers (flow_modules/transformer.py) where the fork
+has them, and `prior=` takes anything with the reference's `c_prior(z, level, reverse)` call
+signature (`"mar"` = the ConvLSTM channel prior port), defaulting to a standard normal.
 
 Per FlowStep the activations are touched twice: one fused ActNorm∘InvConv (∘Squeeze) channel-mix
 kernel and one fused coupling kernel (which also applies the TupleFlip and accumulates the log-det).
@@ -20,13 +21,18 @@ from .flow_modules.affine_coupling import AffineCoupling
 from .flow_modules.common_modules import (Actnormlayer, GaussianDiag, InvertibleConv1x1, Split2dMsC, SqueezeLayer,
                                           TupleFlip, _batch_ldj, fold_actnorm_invconv, squeeze2d)
 from .flow_modules.mixlogcdf_coupling import MixLogCDFCoupling
+from .flow_modules.transformer import Transformer_attn
 
 
 class FlowStep(nn.Module):
     def __init__(self, H, W, C, in_channels, out_channels, hidden_channels, actnorm_scale, coupling_type,
-                 num_blocks=10, num_components=32, drop_prob=0.2):
+                 num_blocks=10, num_components=32, drop_prob=0.2, attn=False):
         super().__init__()
         self.coupling_type = coupling_type
+        # attn=True adds the fork's two invertible patch-attention layers after the 1x1 conv (marscf_main.py:50-51,
+        # 69-70); they are outside the north-star path, so the default stack is variant A minus Transformer_attn
+        self.attn1 = Transformer_attn(in_channels) if attn else None
+        self.attn2 = Transformer_attn(in_channels) if attn else None
         if coupling_type == 'mixlogcdf':
             self.coupling = MixLogCDFCoupling(in_channels, hidden_channels, num_blocks=num_blocks,
                                               num_components=num_components, drop_prob=drop_prob)
@@ -61,6 +67,9 @@ class FlowStep(nn.Module):
         hw = (x.size(2) // 2, x.size(3) // 2) if squeeze_input else (x.size(2), x.size(3))
         mat, bias, add = self._folded(hw, False)
         x, ldj = ops.channel_mix(x, mat, bias, ldj, add, bool(squeeze_input), False)
+        if self.attn1 is not None:
+            x, ldj = self.attn1(x, logdet=ldj, reverse=False)
+            x, ldj = self.attn2(x, logdet=ldj, reverse=False, permute=True)
         if self.coupling_type == 'mixlogcdf':
             x, ldj = self.coupling(x, ldj, False, flip=True)
         else:
@@ -73,6 +82,9 @@ class FlowStep(nn.Module):
             x, ldj = self.coupling(x, ldj, True, flip=True)
         else:
             x, ldj = self.coupling(x, ldj, True)
+        if self.attn1 is not None:
+            x, ldj = self.attn2(x, logdet=ldj, reverse=True, permute=True)
+            x, ldj = self.attn1(x, logdet=ldj, reverse=True)
         mat, bias, add = self._folded((x.size(2), x.size(3)), True)
         x, ldj = ops.channel_mix(x, mat, bias, ldj, add, False, bool(unsqueeze_output))
         return x, (ldj if had else None)
@@ -105,7 +117,7 @@ class StandardNormalPrior(nn.Module):
 
 class FlowNet(nn.Module):
     def __init__(self, batch_size, image_shape, hidden_channels, K, L, coupling_type, actnorm_scale=1.0,
-                 prior=None, num_blocks=10, fuse_squeeze=True):
+                 prior=None, num_blocks=10, fuse_squeeze=True, attn=False):
         super().__init__()
         self.layers = nn.ModuleList()
         self.output_shapes = []
@@ -122,7 +134,7 @@ class FlowNet(nn.Module):
             for _ in range(K):
                 self.layers.append(FlowStep(H, W, C, in_channels=C, out_channels=C, hidden_channels=hidden_channels,
                                             actnorm_scale=actnorm_scale, coupling_type=coupling_type,
-                                            num_blocks=num_blocks))
+                                            num_blocks=num_blocks, attn=attn))
                 self.output_shapes.append([-1, C, H, W])
             if i < L - 1:
                 self.layers.append(Split2dMsC(C, i + 1))
@@ -219,11 +231,11 @@ class FlowNet(nn.Module):
 
 class MarScfFlow(nn.Module):
     def __init__(self, batch_size, image_shape, coupling_type, L, K, C, prior=None, num_blocks=10,
-                 fuse_squeeze=True):
+                 fuse_squeeze=True, attn=False):
         super().__init__()
         self.flow = FlowNet(batch_size, image_shape=image_shape, hidden_channels=C, K=K, L=L,
                             coupling_type=coupling_type, prior=prior, num_blocks=num_blocks,
-                            fuse_squeeze=fuse_squeeze)
+                            fuse_squeeze=fuse_squeeze, attn=attn)
         self.batch_size = batch_size
 
     def forward(self, x=None, z=None, eps_std=None, reverse=False, noise=None):

@@ -389,10 +389,75 @@ def tuple_flip(x: Tensor) -> Tensor:
 
 
 # --------------------------------------------------------------------------
-# FlowStep / FlowNet / MarScfFlow (marscf_main.py:35-206), variant A minus the
-# fork's Transformer_attn add-on
+# Transformer_attn, the fork's invertible patch attention (flow_modules/transformer.py:31-326;
+# SURVEY.md section 8f-2).  Not on the north-star path; pinned for the optional plug-in.
 # --------------------------------------------------------------------------
-def flow_step(sd: State, pre: str, x: Tensor, ldj: Tensor, coupling: str, reverse: bool = False):
+def _patches(x: Tensor, p: int) -> Tensor:
+    """'b c (h p1) (w p2) -> b (h w) (c p1 p2)' (transformer.py:132)."""
+    b, c, hh, ww = x.shape
+    return x.reshape(b, c, hh // p, p, ww // p, p).permute(0, 2, 4, 1, 3, 5).reshape(b, (hh // p) * (ww // p), c * p * p)
+
+
+def _unpatches(t: Tensor, p: int, shape) -> Tensor:
+    """Inverse of `_patches` (reverse_rearrange, transformer.py:14-29)."""
+    b, c, hh, ww = shape
+    return t.reshape(b, hh // p, ww // p, c, p, p).permute(0, 3, 1, 4, 2, 5).reshape(b, c, hh, ww)
+
+
+def _checker(rows: int, cols: int, like: Tensor) -> Tensor:
+    """checkerboard(shape) = 1 - (i + j) % 2 (transformer.py:10-11)."""
+    i = torch.arange(rows).view(-1, 1)
+    j = torch.arange(cols).view(1, -1)
+    return (1 - (i + j) % 2).to(like.dtype)
+
+
+def transformer_attn(sd: State, pre: str, z: Tensor, ldj: Tensor, reverse: bool = False, permute: bool = False):
+    """Masked patch attention with 2x2 block-invertible mixing (transformer.py:124-326).
+
+    Patches: a 2x2 grid of (W/2)-sized patches, flattened to [B, 4, L].  Entries with (patch + index) even (odd when
+    `permute`) condition the attention and pass through; the others are mixed between patches of equal parity by the
+    2x2 matrices M1 (patches 0, 2) and M2 (patches 1, 3): attn = (sigmoid(sum_i Q_i K_i^T / scale + offset2) +
+    offset3), plus `offset` on the diagonal.  logdet += (log|det M1| + log|det M2|) * p * (p // 2) * C."""
+    b, c, hh, ww = z.shape
+    p = ww // 2
+    full = _patches(z, p)                                      # [B, 4, L]
+    n, length = full.shape[1], full.shape[2]
+    mask = _checker(n, length, z)
+    if permute:
+        mask = 1 - mask
+    z_m = _unpatches(full * mask, p, z.shape)
+    score = 0
+    for i in (1, 2, 3):
+        q = _patches(F.conv2d(z_m, sd[pre + "convq%d" % i]), p)
+        k = _patches(F.conv2d(z_m, sd[pre + "convk%d" % i]), p)
+        score = score + torch.matmul(q, k.permute(0, 2, 1)) / sd[pre + "scale"]
+    attn = torch.sigmoid(score + sd[pre + "offset2"]) + sd[pre + "offset3"]          # [B, 4, 4]; only equal-parity entries used
+    off = sd[pre + "offset"].reshape(())
+    eye = torch.eye(2, dtype=z.dtype)
+    m1 = attn[:, 0::2, 0::2] + eye * off                       # patches (0, 2)
+    m2 = attn[:, 1::2, 1::2] + eye * off                       # patches (1, 3)
+    scale_ld = p * (p // 2) * c
+    ld = (torch.slogdet(m1)[1] + torch.slogdet(m2)[1]) * scale_ld
+    free = full * (1 - mask)
+    if not reverse:
+        mixed = torch.empty_like(full)
+        mixed[:, 0::2] = torch.matmul(m1, free[:, 0::2])
+        mixed[:, 1::2] = torch.matmul(m2, free[:, 1::2])
+        ldj = ldj + ld
+    else:
+        mixed = torch.empty_like(full)
+        mixed[:, 0::2] = torch.matmul(torch.inverse(m1), free[:, 0::2])
+        mixed[:, 1::2] = torch.matmul(torch.inverse(m2), free[:, 1::2])
+        ldj = ldj - ld
+    out = mixed * (1 - mask) + full * mask
+    return _unpatches(out, p, z.shape), ldj
+
+
+# --------------------------------------------------------------------------
+# FlowStep / FlowNet / MarScfFlow (marscf_main.py:35-206).  `attn=True` adds the fork's two
+# Transformer_attn layers after the 1x1 conv (marscf_main.py:69-70, 89-90).
+# --------------------------------------------------------------------------
+def flow_step(sd: State, pre: str, x: Tensor, ldj: Tensor, coupling: str, reverse: bool = False, attn: bool = False):
     """actnorm -> invconv -> coupling (-> flip if mixlogcdf); exact mirror in reverse
     (marscf_main.py:62-106)."""
     an = (sd[pre + "actnormlayer.bias"], sd[pre + "actnormlayer.logs"])
@@ -400,6 +465,9 @@ def flow_step(sd: State, pre: str, x: Tensor, ldj: Tensor, coupling: str, revers
     if not reverse:
         x, ldj = actnorm(x, *an, ldj, False)
         x, ldj = invconv(x, *ic, ldj, False)
+        if attn:
+            x, ldj = transformer_attn(sd, pre + "attn1.", x, ldj, False, False)
+            x, ldj = transformer_attn(sd, pre + "attn2.", x, ldj, False, True)
         if coupling == "mixlogcdf":
             x, ldj = mixlogcdf_coupling(sd, pre + "coupling.", x, ldj, False)
             x = tuple_flip(x)
@@ -411,6 +479,9 @@ def flow_step(sd: State, pre: str, x: Tensor, ldj: Tensor, coupling: str, revers
             x, ldj = mixlogcdf_coupling(sd, pre + "coupling.", x, ldj, True)
         else:
             x, ldj = affine_coupling(sd, pre + "coupling.", x, ldj, True)
+        if attn:
+            x, ldj = transformer_attn(sd, pre + "attn2.", x, ldj, True, True)
+            x, ldj = transformer_attn(sd, pre + "attn1.", x, ldj, True, False)
         x, ldj = invconv(x, *ic, ldj, True)
         x, ldj = actnorm(x, *an, ldj, True)
     return x, ldj
@@ -436,7 +507,7 @@ def gaussian_logp(z: Tensor) -> Tensor:
 
 
 def flownet_encode(sd: State, x: Tensor, ldj: Tensor, L: int, K: int, coupling: str,
-                   pre: str = "flow.layers."):
+                   pre: str = "flow.layers.", attn: bool = False):
     """FlowNet.encode (marscf_main.py:156-165) without the prior term: returns
     (z_final, [z2 of every split, in order], flow logdet)."""
     outs: List[Tensor] = []
@@ -444,7 +515,7 @@ def flownet_encode(sd: State, x: Tensor, ldj: Tensor, L: int, K: int, coupling: 
         if kind == "squeeze":
             x = squeeze2d(x)
         elif kind == "step":
-            x, ldj = flow_step(sd, "%s%d." % (pre, i), x, ldj, coupling, False)
+            x, ldj = flow_step(sd, "%s%d." % (pre, i), x, ldj, coupling, False, attn=attn)
         else:
             c = x.shape[1] // 2
             outs.append(x[:, c:])
@@ -453,7 +524,7 @@ def flownet_encode(sd: State, x: Tensor, ldj: Tensor, L: int, K: int, coupling: 
 
 
 def flownet_decode(sd: State, z: Tensor, z2s: Sequence[Tensor], L: int, K: int, coupling: str,
-                   pre: str = "flow.layers."):
+                   pre: str = "flow.layers.", attn: bool = False):
     """FlowNet.decode (marscf_main.py:167-175) with the factored-out halves supplied by the
     caller instead of sampled from the prior.  logdet restarts from 0 at every layer in the
     reference (:174) and is discarded; here it is accumulated and returned for testing."""
@@ -465,13 +536,13 @@ def flownet_decode(sd: State, z: Tensor, z2s: Sequence[Tensor], L: int, K: int, 
         if kind == "split":
             z = torch.cat((z, z2s.pop()), dim=1)
         elif kind == "step":
-            z, ldj = flow_step(sd, "%s%d." % (pre, i), z, ldj, coupling, True)
+            z, ldj = flow_step(sd, "%s%d." % (pre, i), z, ldj, coupling, True, attn=attn)
         else:
             z = unsqueeze2d(z)
     return z, ldj
 
 
-def normal_flow(sd: State, x: Tensor, noise: Tensor, L: int, K: int, coupling: str):
+def normal_flow(sd: State, x: Tensor, noise: Tensor, L: int, K: int, coupling: str, attn: bool = False):
     """MarScfFlow.normal_flow (marscf_main.py:192-206) with the dequantisation noise supplied
     (``noise`` ~ U[0,1), added as noise/256) and a standard-normal prior on every latent.
 
@@ -480,7 +551,7 @@ def normal_flow(sd: State, x: Tensor, noise: Tensor, L: int, K: int, coupling: s
     d = x.shape[1] * x.shape[2] * x.shape[3]
     z = x + noise * (1.0 / 256.0)
     ldj = torch.zeros(x.shape[0], dtype=x.dtype) + float(-math.log(256.0) * d)
-    z, outs, ldj = flownet_encode(sd, z, ldj, L, K, coupling)
+    z, outs, ldj = flownet_encode(sd, z, ldj, L, K, coupling, attn=attn)
     objective = ldj + gaussian_logp(z)
     for o in outs:
         objective = objective + gaussian_logp(o)

@@ -306,7 +306,38 @@ def gen_mar_prior():
          ll1=ll1, ll2=ll2, s2=s2, s1=s1, **sd_arrays(prior))
 
 
+def gen_transformer_attn():
+    """The fork's invertible patch attention (flow_modules/transformer.py) - SURVEY.md section 8f-2.  Its constructor and
+    forward call `.cuda()` throughout; with `Tensor.cuda` patched to the identity its own lines run on CPU."""
+    from flow_modules.transformer import Transformer_attn
+    g = torch.Generator().manual_seed(41)
+    cases = {}
+    for tag, (B, C, H) in {"c12": (3, 12, 8), "c24": (2, 24, 4)}.items():
+        torch.manual_seed(41 + C)
+        m = Transformer_attn(C)
+        with torch.no_grad():
+            # spread the attention logits: the default scale=100 leaves sigmoid() almost constant
+            m.scale.fill_(3.0)
+            m.offset.fill_(0.9)
+            m.offset2.fill_(0.4)
+            m.offset3.fill_(-0.55)
+        x = torch.randn(B, C, H, H, generator=g)
+        ld0 = torch.randn(B, generator=g)
+        arrays = {"x": x, "ld0": ld0}
+        with torch.no_grad():
+            for permute in (False, True):
+                y, ld = m(x.clone(), logdet=ld0.clone(), reverse=False, permute=permute)
+                xr, ldr = m(y.clone(), logdet=ld.clone(), reverse=True, permute=permute)
+                sfx = "_perm" if permute else ""
+                arrays.update({"y" + sfx: y, "ld" + sfx: ld, "xr" + sfx: xr, "ldr" + sfx: ldr})
+        arrays.update(sd_arrays(m))
+        cases[tag] = arrays
+    for tag, arrays in cases.items():
+        save("transformer_attn_" + tag, {"case": tag}, **arrays)
+
+
 if __name__ == "__main__":
+    gen_transformer_attn()
     gen_mar_prior()
     gen_squeeze()
     gen_actnorm()

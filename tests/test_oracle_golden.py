@@ -146,3 +146,16 @@ def test_float64_oracle_agrees_with_fp32_reference(golden):
     y, ldj = O.mixlogcdf_elementwise(g["x"].double(), *p, g["ldj0"].double())
     close(y.float(), g["y"], rtol=1e-4, atol=1e-4)
     close(ldj.float(), g["ldj"], rtol=1e-4, atol=1e-3)
+
+
+def test_transformer_attn(golden):
+    """The fork's invertible patch attention (flow_modules/transformer.py), SURVEY.md section 8f-2."""
+    for name in ("transformer_attn_c12", "transformer_attn_c24"):
+        g = golden(name)
+        for permute, sfx in ((False, ""), (True, "_perm")):
+            y, ld = O.transformer_attn(g.sd, "", g["x"], g["ld0"], False, permute)
+            close(y, g["y" + sfx], rtol=1e-5, atol=1e-5)
+            close(ld, g["ld" + sfx], rtol=1e-5, atol=1e-4)
+            xr, ldr = O.transformer_attn(g.sd, "", g["y" + sfx], g["ld" + sfx], True, permute)
+            close(xr, g["xr" + sfx], rtol=1e-5, atol=1e-5)
+            close(ldr, g["ldr" + sfx], rtol=1e-5, atol=1e-4)
