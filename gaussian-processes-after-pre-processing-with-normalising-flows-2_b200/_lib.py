@@ -59,6 +59,7 @@ SIGNATURES = {
     "flowk_conv_wgrad": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _st], _i),
     "flowk_shift_columns": ([_fp, _fp, _fp, ctypes.c_longlong, _i, _st], _i),
     "flowk_weight_norm_bwd_partials": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _st], _i),
+    "flowk_conv_gemm_splitk_slices": ([_fp], _i),
     "flowk_glu_bwd": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
 }
 
@@ -69,7 +70,8 @@ class ConvGemmArgs(ctypes.Structure):
                 ("a_hi", "a_lo", "w_hi", "w_lo", "bias", "res", "gamma", "beta", "pos",
                  "out_f32", "out_hi", "out_lo", "out_nchw", "status", "trace")] + \
                [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")] + \
-               [(n, ctypes.c_void_p) for n in ("w2_hi", "w2_lo", "out2_f32")] + [("N2", ctypes.c_int)]
+               [(n, ctypes.c_void_p) for n in ("w2_hi", "w2_lo", "out2_f32")] + [("N2", ctypes.c_int)] + \
+               [("splitk_ws", ctypes.c_void_p)]
 
 
 PRE_BIAS, PRE_GLU_RES_LN = 0, 1

@@ -62,6 +62,8 @@ struct Params {
   // operand tiles and are multiplied by a second weight matrix [n2, C] in the same CTA (gate -> in_proj fusion)
   int chain, n2, n2_chunk, n2_chunks, a3_offset, w2_offset;
   float* out2_f32;                 // [M, n2]
+  int ksplit;                      // > 1: blockIdx.z takes a slice of every tap's channel blocks; fp32 partial rows go to
+                                   // out_f32 + z*M*N (no bias) and flowk's split-K reduce kernel finishes the layer
   int* status;                     // set to 1 if a barrier wait timed out
   long long* trace;                // optional [16] clock64 stamps of CTA (0,0): setup, first full, last mma, epi start, epi end
 };
@@ -94,7 +96,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, n_tile = blockIdx.y;
   const int n_base = n_tile * p.n_chunk * p.n_chunks;
-  const int num_kb = p.taps * p.kblocks_per_tap;
+  // split-K (normal pipeline only): this CTA's slice [cb0, cb0 + kpt) of every tap's channel blocks
+  const int ksp = p.ksplit > 1 ? p.ksplit : 1;
+  const int cb0 = (int)((long long)p.kblocks_per_tap * blockIdx.z / ksp);
+  const int kpt = (int)((long long)p.kblocks_per_tap * (blockIdx.z + 1) / ksp) - cb0;
+  const int num_kb = p.taps * kpt;
+  float* const out_f32 = p.out_f32 ? p.out_f32 + (size_t)blockIdx.z * p.M * p.N : nullptr;
 
   if (threadIdx.x == 0) {
     *failed = 0;
@@ -165,12 +172,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u, failed);
         uint8_t* st = smem + (size_t)s * stage_bytes;
-        const int tap = kb / p.kblocks_per_tap, cb = kb % p.kblocks_per_tap;
+        const int tap = kb / kpt, cb = cb0 + kb % kpt;
         const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
         mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
         tma_load_4d(st, &map_a_hi, &full_bar[s], cb * BLOCK_K, dx, h0 + dy, b0);
         tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[s], cb * BLOCK_K, dx, h0 + dy, b0);
-        const int kcol = kb * BLOCK_K;                               // weights are [N, taps*Cin], (tap, c) order
+        const int kcol = (tap * p.kblocks_per_tap + cb) * BLOCK_K;   // weights are [N, taps*Cin], (tap, c) order
         for (int c = 0; c < p.n_chunks; ++c) {
           const int chunk_bytes = p.n_chunk * BLOCK_K * 4;
           tma_load_2d(st + 2 * A_TILE_BYTES + c * chunk_bytes, &map_w_hi, &full_bar[s], kcol, n_base + c * p.n_chunk);
@@ -375,7 +382,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const float4 y = *reinterpret_cast<const float4*>(slab + r * pitch + c4);
             const float ys[4] = {y.x, y.y, y.z, y.w};
             const size_t o = (size_t)m * p.N + n;
-            if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(p.out_f32 + o) = y;
+            if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(out_f32 + o) = y;
             if (p.out_mask & (OUT_HILO | OUT_HILO_RELU)) {             // RELU: NN_net's activations (affine_coupling.py:77-78)
               float h[4], l[4];
 #pragma unroll
@@ -504,7 +511,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) y[i] = (g[rr][v][i] - mean[rr]) * rstd[rr] * gs[i] + bs[i];
           const size_t o = (size_t)m * C + c4;
-          if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+          if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
           if (p.out_mask & (OUT_HILO | OUT_HILO_POS)) {
             float h[4], l[4];
 #pragma unroll
@@ -635,15 +642,64 @@ static bool make_map_w(CUtensorMap* map, const float* base, int N, int Ktot, int
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// split-K finish: out = sum_s partial[s][m][n] + bias[n], as fp32 rows [M, N] or NCHW [B, N, HW]; slices in index order
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                     float* __restrict__ out_f32, float* __restrict__ out_nchw, int M, int N, int HW,
+                                     int splits) {
+  griddep_wait();
+  const long long total = (long long)M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long m, n;
+    if (out_nchw) {                      // thread order follows the NCHW output: (b, n, hw)
+      const long long b = i / ((long long)N * HW), r = i - b * (long long)N * HW;
+      n = r / HW;
+      m = b * HW + (r - n * HW);
+    } else {
+      m = i / N;
+      n = i - m * N;
+    }
+    float acc = bias ? bias[n] : 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * M + m) * N + n];
+    if (out_nchw) out_nchw[i] = acc;
+    else out_f32[i] = acc;
+  }
+}
+
+// How many K slices flowk_conv_gemm would use for this layer given a workspace (1 = no split-K).  Split-K serves the
+// latency of single-stream (training) steps: layers with few 128-row tiles and a long K loop (deep levels, the
+// out_conv input-gradient with K = 9 * 98c) otherwise run on a handful of SMs.
+static int plan_ksplit(int m_tiles, int n_tiles, int kpt, int taps) {
+  const int ctas = m_tiles * n_tiles, num_kb = taps * kpt;
+  if (ctas * 2 > 148 || num_kb < 32) return 1;
+  int ks = 148 / ctas;
+  if (ks > kpt) ks = kpt;
+  if (ks > num_kb / 8) ks = num_kb / 8;
+  return ks < 2 ? 1 : ks;
+}
+
 }  // namespace tc
 }  // namespace flowk
 
 using namespace flowk;
 using namespace flowk::tc;
 
+static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, int* plan_only);
+
 extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t stream) {
+  return conv_gemm_impl(a, stream, nullptr);
+}
+
+// Number of split-K slices flowk_conv_gemm will use for `args` IF args->splitk_ws is non-null (>= 1; the workspace
+// must then hold slices * B*H*W * N floats).  Pointers in `args` are not dereferenced.
+extern "C" int flowk_conv_gemm_splitk_slices(const flowk_conv_gemm_args* a) {
+  int ks = 1;
+  const int st = conv_gemm_impl(a, nullptr, &ks);
+  return st == FLOWK_OK ? ks : 1;
+}
+
+static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, int* plan_only) {
   if (!a) return FLOWK_ERR_ARG;
-  if (!a->a_hi || !a->a_lo || !a->w_hi || !a->w_lo) return FLOWK_ERR_ARG;
+  if (!plan_only && (!a->a_hi || !a->a_lo || !a->w_hi || !a->w_lo)) return FLOWK_ERR_ARG;
   const int B = a->B, H = a->H, W = a->W, Cin = a->Cin, N = a->N;
   if (B < 1 || H < 1 || W < 1 || Cin < BLOCK_K || Cin % BLOCK_K || N < 8) return FLOWK_ERR_SHAPE;
   if (a->taps != 1 && a->taps != 9) return FLOWK_ERR_ARG;
@@ -714,6 +770,21 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     }
   }
   if (p.n_chunk % 16 || p.n_chunk > 256) return FLOWK_ERR_SHAPE;
+  // split-K: only the plain bias epilogue with a single fp32 destination, and only when the caller lends a workspace
+  p.ksplit = 1;
+  if (a->pre == PRE_BIAS && p.n_chunks == 1 && (a->out_mask == OUT_NCHW || a->out_mask == OUT_F32) && !(N & 3) &&
+      (plan_only || a->splitk_ws))
+    p.ksplit = plan_ksplit((B * H * W + BLOCK_M - 1) / BLOCK_M, n_tiles, p.kblocks_per_tap, a->taps);
+  if (plan_only) {
+    *plan_only = p.ksplit;
+    return FLOWK_OK;
+  }
+  if (p.ksplit > 1) {                 // partial rows [slice][M][N] into the workspace; the reduce kernel adds the bias
+    p.out_mask = OUT_F32;
+    p.out_f32 = a->splitk_ws;
+    p.out_nchw = nullptr;
+    p.bias = nullptr;
+  }
   const int cols = p.n_chunk * p.n_chunks;
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * cols * BLOCK_K * 4;
@@ -722,7 +793,7 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   if (stages < 1) return FLOWK_ERR_SHAPE;
   // 3x3 dx-split mode: three accumulators (one per column shift) so that an activation tile serves three taps
   p.dxsplit = (a->taps == 9 && a->pre == PRE_BIAS && !(a->out_mask & OUT_NCHW) && W <= 32 && 32 % W == 0 &&
-               p.n_chunks == 1 && 3 * p.n_chunk <= 512) ? 1 : 0;
+               p.n_chunks == 1 && 3 * p.n_chunk <= 512 && p.ksplit == 1) ? 1 : 0;
   if (p.dxsplit) {
     p.tmem_cols = 3 * p.n_chunk <= 256 ? 256 : 512;
     if (3 * p.n_chunk <= 128) p.tmem_cols = 128;
@@ -736,7 +807,7 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
   // epilogue staging (reuses the pipeline stages once the accumulator is complete)
   size_t epi_bytes = (size_t)4 * 32 * (cols + 4) * sizeof(float);
   if (a->pre == PRE_GLU_RES_LN) epi_bytes = (size_t)4 * 32 * (N / 2 + 4) * sizeof(float);
-  if ((a->out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_POS | OUT_HILO_CELU | OUT_HILO_RELU)) && (N & 3)) return FLOWK_ERR_SHAPE;
+  if ((p.out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_POS | OUT_HILO_CELU | OUT_HILO_RELU)) && (N & 3)) return FLOWK_ERR_SHAPE;
   while (stages > 1 && (size_t)stages * stage_bytes + 2048 > 227 * 1024) --stages;
   size_t region = (size_t)stages * stage_bytes;
   if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 6 * cols * BLOCK_K * 4;
@@ -779,7 +850,7 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     mw2_lo = mw_lo;
   }
 
-  dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, n_tiles);
+  dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, n_tiles, p.ksplit);
   static size_t smem_set[3] = {0, 0, 0};               // largest dynamic-smem opt-in requested so far, per variant
   const int variant = a->pre == PRE_GLU_RES_LN ? (N / 2 > 128 ? 2 : 1) : 0;
   const bool need_attr = smem_bytes > smem_set[variant];
@@ -799,6 +870,13 @@ extern "C" int flowk_conv_gemm(const flowk_conv_gemm_args* a, flowk_stream_t str
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_BIAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
     FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_BIAS, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));
+  }
+  if (p.ksplit > 1) {
+    const long long total = (long long)p.M * N;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    FLOWK_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, (const float*)a->splitk_ws, a->bias,
+                             a->out_mask == OUT_F32 ? a->out_f32 : (float*)nullptr,
+                             a->out_mask == OUT_NCHW ? a->out_nchw : (float*)nullptr, p.M, N, p.HW, p.ksplit));
   }
   return launch_status();
 }

@@ -43,10 +43,17 @@ def _p(t):
 
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias=None, res=None, gamma=None,
               beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None, trace=None,
-              w2_hi=None, w2_lo=None, out2_f32=None, n2=0):
+              w2_hi=None, w2_lo=None, out2_f32=None, n2=0, split_k=False):
+    """`split_k=True` (training path: one stream, kernel latency matters) lends the kernel a workspace so that layers
+    with few 128-row tiles and a long K loop are shared by several CTAs per output tile."""
     args = _lib.ConvGemmArgs(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(res), _p(gamma), _p(beta), _p(pos),
                              _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status), _p(trace),
-                             B, H, W, Cin, N, taps, pre, out_mask, _p(w2_hi), _p(w2_lo), _p(out2_f32), n2)
+                             B, H, W, Cin, N, taps, pre, out_mask, _p(w2_hi), _p(w2_lo), _p(out2_f32), n2, None)
+    if split_k:
+        slices = _lib.lib.flowk_conv_gemm_splitk_slices(ctypes.addressof(args))
+        if slices > 1:
+            ws = torch.empty(slices * B * H * W * N, device=a_hi.device, dtype=torch.float32)
+            args.splitk_ws = ws.data_ptr()
     _lib.call("flowk_conv_gemm", ctypes.addressof(args), _stream(), meta=(B, H, W, Cin, N, taps, pre))
 
 

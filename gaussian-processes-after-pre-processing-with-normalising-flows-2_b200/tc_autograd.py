@@ -51,7 +51,7 @@ class _Conv2d(torch.autograd.Function):
         w_hi, w_lo = tc.conv_weight_operand(w.detach(), cp)
         y = torch.empty(b, n, h, ww, device=x.device, dtype=torch.float32)
         tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, b, h, ww, cp, n, taps, tc.PRE_BIAS, tc.OUT_NCHW,
-                     bias=None if bias is None else bias.detach().contiguous(), out_nchw=y)
+                     bias=None if bias is None else bias.detach().contiguous(), out_nchw=y, split_k=True)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         return y
@@ -71,7 +71,7 @@ class _Conv2d(torch.autograd.Function):
             wt = w.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous()
             wt_hi, wt_lo = tc.conv_weight_operand(wt, np_)
             gx = torch.empty(x.shape, device=x.device, dtype=torch.float32)      # contiguous NCHW whatever x's strides
-            tc.conv_gemm(g_hi, g_lo, wt_hi, wt_lo, b, h, ww, np_, cin, taps, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx)
+            tc.conv_gemm(g_hi, g_lo, wt_hi, wt_lo, b, h, ww, np_, cin, taps, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx, split_k=True)
         if ctx.needs_input_grad[1]:
             gw = torch.nn.grad.conv2d_weight(x, w.shape, gy, padding=kh // 2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -98,7 +98,7 @@ def _rows_gemm(a, wmat, bias, n):
     a_hi, a_lo = tc.split_rows(a.contiguous())
     w_hi, w_lo = tc.split_hilo(wmat)
     y = torch.empty(m, n, device=a.device, dtype=torch.float32)
-    tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, m // 128, 8, 16, k, n, 1, tc.PRE_BIAS, tc.OUT_F32, bias=bias, out_f32=y)
+    tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, m // 128, 8, 16, k, n, 1, tc.PRE_BIAS, tc.OUT_F32, bias=bias, out_f32=y, split_k=True)
     return y
 
 
@@ -222,7 +222,7 @@ class _WNConv2d(torch.autograd.Function):
         a_hi, a_lo = _nchw_operand(x, cp)
         y = torch.empty(b, n, h, ww, device=x.device, dtype=torch.float32)
         tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], b, h, ww, cp, n, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW,
-                     bias=None if bias is None else bias.detach().contiguous(), out_nchw=y)
+                     bias=None if bias is None else bias.detach().contiguous(), out_nchw=y, split_k=True)
         ctx.save_for_backward(x, vd, gd, norm, dg)
         ctx.has_bias = bias is not None
         return y
@@ -238,7 +238,7 @@ class _WNConv2d(torch.autograd.Function):
             np_ = _pad32(n)
             g_hi, g_lo = _nchw_operand(gy, np_)
             gx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
-            tc.conv_gemm(g_hi, g_lo, dg[0], dg[1], b, h, ww, np_, cin, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx)
+            tc.conv_gemm(g_hi, g_lo, dg[0], dg[1], b, h, ww, np_, cin, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx, split_k=True)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             partial = wgrad_partials(x.contiguous(), gy, kh * kw)
             if partial is not None:
@@ -262,7 +262,7 @@ class _WNLinearFn(torch.autograd.Function):
         a_hi, a_lo = tc.split_rows(x2)
         y = torch.empty(x2.shape[0], n, device=x.device, dtype=torch.float32)
         tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], x2.shape[0] // 128, 8, 16, k, n, 1, tc.PRE_BIAS, tc.OUT_F32,
-                     bias=None if bias is None else bias.detach().contiguous(), out_f32=y)
+                     bias=None if bias is None else bias.detach().contiguous(), out_f32=y, split_k=True)
         ctx.save_for_backward(x2, vd, gd, norm, dg if tc_dgrad else w)
         ctx.tc_dgrad, ctx.has_bias, ctx.shape = tc_dgrad, bias is not None, shape
         return y.view(*shape[:-1], n)
@@ -278,7 +278,7 @@ class _WNLinearFn(torch.autograd.Function):
                 g_hi, g_lo = tc.split_rows(g2)
                 gx = torch.empty(g2.shape[0], k, device=g2.device, dtype=torch.float32)
                 tc.conv_gemm(g_hi, g_lo, wd[0], wd[1], g2.shape[0] // 128, 8, 16, n, k, 1, tc.PRE_BIAS, tc.OUT_F32,
-                             out_f32=gx)
+                             out_f32=gx, split_k=True)
                 gx = gx.view(ctx.shape)
             else:
                 gx = (g2 @ wd).view(ctx.shape)

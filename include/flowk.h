@@ -164,9 +164,16 @@ typedef struct flowk_conv_gemm_args {
   const float* w2_lo;
   float* out2_f32;
   int N2;
+  /* optional split-K workspace (FLOWK_PRE_BIAS with out_mask == FLOWK_OUT_F32 or FLOWK_OUT_NCHW only): when non-null
+   * and the layer has few 128-row tiles and a long K loop, flowk_conv_gemm_splitk_slices(args) CTAs share every output
+   * tile, each writing fp32 partial rows here ([slices, B*H*W, N] floats), and a second kernel adds the slices in index
+   * order plus the bias into the destination.  Serves the latency of single-stream (training) steps. */
+  float* splitk_ws;
 } flowk_conv_gemm_args;
 
 int flowk_conv_gemm(const flowk_conv_gemm_args* args, flowk_stream_t stream);
+/* Slices flowk_conv_gemm would use for `args` if args->splitk_ws were non-null (1 = no split-K); no pointer is read. */
+int flowk_conv_gemm_splitk_slices(const flowk_conv_gemm_args* args);
 
 /* x[b, ch, p] (NCHW, `batch_stride` floats between samples, ch < C) -> NHWC hi/lo [B*HW, C_pad], zero-padded channels. */
 int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, int B, int C, int HW, int C_pad,

@@ -402,3 +402,38 @@ def test_conv_wgrad_tcgen05_matches_fp64(b, cin, n, k, h, w):
     assert rel_err(got, ref) < 2e-5
     again, _ = tc_autograd.wgrad_partials(x, gy, k * k)
     assert torch.equal(again, partial)                       # split-K partials are deterministic
+
+
+@pytest.mark.parametrize("B,Cin,H,W,N,taps,nchw", [(64, 192, 4, 4, 96, 9, True), (16, 2368, 4, 4, 96, 9, True),
+                                                   (8, 192, 8, 8, 192, 9, True), (4, 1536, 8, 16, 96, 1, False)])
+def test_conv_gemm_split_k_matches_fp64_and_unsplit(B, Cin, H, W, N, taps, nchw):
+    """Split-K (training path): few 128-row tiles, long K loop -> several CTAs per output tile + ordered reduce."""
+    from flowk import _lib, tc
+    import ctypes
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(17)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn(N, Cin, k, k, generator=g) / (Cin * taps) ** 0.5).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    a_hi, a_lo = tc.nchw_to_nhwc_hilo(x, Cin)
+    w_hi, w_lo = tc.conv_weight_operand(w, Cin)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)
+    outs = []
+    for split in (False, True):
+        if nchw:
+            y = torch.empty(B, N, H, W, device=dev)
+            tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, tc.PRE_BIAS, tc.OUT_NCHW, bias=bias, out_nchw=y,
+                         split_k=split)
+        else:
+            rows = torch.empty(B * H * W, N, device=dev)
+            tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, tc.PRE_BIAS, tc.OUT_F32, bias=bias, out_f32=rows,
+                         split_k=split)
+            y = rows.view(B, H, W, N).permute(0, 3, 1, 2)
+        outs.append(y)
+        # fp32 accumulation in TMEM over K/8 MMA steps: the error grows with K (K = 21 312 for the out_conv dgrad)
+        assert rel_err(y, ref) < (2e-5 if Cin * taps < 5000 else 1.5e-4), (split, rel_err(y, ref))
+    args = _lib.ConvGemmArgs(None, None, None, None, None, None, None, None, None, None, None, None, None, None, None,
+                             B, H, W, Cin, N, taps, tc.PRE_BIAS, tc.OUT_NCHW if nchw else tc.OUT_F32, None, None, None, 0, None)
+    assert _lib.lib.flowk_conv_gemm_splitk_slices(ctypes.addressof(args)) > 1        # these shapes do split
+    assert rel_err(outs[1], ref) <= 1.5 * rel_err(outs[0], ref) + 1e-6           # shorter chains: split-K is no less accurate
