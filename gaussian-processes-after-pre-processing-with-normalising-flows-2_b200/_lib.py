@@ -57,6 +57,8 @@ SIGNATURES = {
     "flowk_channel_sum": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
     "flowk_conv_wgrad_splits": ([_i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)], _i),
     "flowk_conv_wgrad": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _st], _i),
+    "flowk_linear_wgrad_splits": ([ctypes.c_longlong, _i, _i, ctypes.POINTER(ctypes.c_int)], _i),
+    "flowk_linear_wgrad": ([_fp, _fp, _fp, _fp, ctypes.c_longlong, _i, _i, _st], _i),
     "flowk_shift_columns": ([_fp, _fp, _fp, ctypes.c_longlong, _i, _st], _i),
     "flowk_weight_norm_bwd_partials": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _st], _i),
     "flowk_conv_gemm_splitk_slices": ([_fp], _i),

@@ -32,6 +32,8 @@ constexpr int WG_MAX_STAGES = 4;
 struct WgradParams {
   int N, Cin, taps;               // here N = channels of the A-side tensor, Cin = channels of the B-side tensor
   int shift_a;                    // 1: the A side is x (carries the tap shift), 0: the B side is
+  int rows;                       // 1: row-major operands [M, C] (Linear layers): MN-major tiles of [32 rows x 32 channels]
+                                  //    blocks, 3-D TMA boxes (32 ch, 32 rows, blocks), transposed UMMA descriptors
   int g_tile_bytes;               // shared-memory bytes reserved for the A tile (its real rows, rounded to 8)
   int W;                          // image width: a row shift is W pixels
   int kb_per_image, total_kb;     // k-block = 32 consecutive pixels of one image
@@ -96,7 +98,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
         mbar_expect_tx(&full_raw[s], (uint32_t)(g_bytes + x_bytes));
         const CUtensorMap* mx = dx < 0 ? &map_xm : dx > 0 ? &map_xp : &map_x;
-        if (p.shift_a) {
+        if (p.rows) {                 // k-block = rows [32 kb, 32 kb + 32); A side = map_g when !shift_a
+          tma_load_3d(st, p.shift_a ? &map_x : &map_g, &full_raw[s], 0, kb * BLOCK_K, mt * (BLOCK_M / 32));
+          tma_load_3d(st + x_off, p.shift_a ? &map_g : &map_x, &full_raw[s], 0, kb * BLOCK_K, ct * (p.c_tile / 32));
+        } else if (p.shift_a) {
           tma_load_4d(st, mx, &full_raw[s], p0 + dy * p.W, mt * BLOCK_M, b, 0);
           tma_load_4d(st + x_off, &map_g, &full_raw[s], p0, ct * p.c_tile, b, 0);
         } else {
@@ -107,7 +112,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.c_tile);
+      const uint32_t idesc = p.rows ? make_idesc_mn(p.c_tile) : make_idesc(p.c_tile);
       for (int kb = kb0; kb < kb1; ++kb) {
         const int i = kb - kb0, s = i % p.stages;
         const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
@@ -115,11 +120,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         mbar_wait(&full_lo[s], ph, failed);
         tc_fence_after();
         const uint32_t base = smem_u32(smem + (size_t)s * p.stage_bytes);
-        const uint64_t dg_hi = make_smem_desc(base), dx_hi = make_smem_desc(base + x_off);
-        const uint64_t dg_lo = make_smem_desc(base + lo_off), dx_lo = make_smem_desc(base + lo_off + x_off);
+        uint64_t dg_hi, dx_hi, dg_lo, dx_lo;
+        if (p.rows) {
+          dg_hi = make_smem_desc_mn(base, 4096), dx_hi = make_smem_desc_mn(base + x_off, 4096);
+          dg_lo = make_smem_desc_mn(base + lo_off, 4096), dx_lo = make_smem_desc_mn(base + lo_off + x_off, 4096);
+        } else {
+          dg_hi = make_smem_desc(base), dx_hi = make_smem_desc(base + x_off);
+          dg_lo = make_smem_desc(base + lo_off), dx_lo = make_smem_desc(base + lo_off + x_off);
+        }
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
+          // K-major: 32 bytes further inside the 128-byte row; MN-major: 8 rows = 1024 bytes further
+          const uint64_t ko = p.rows ? (uint64_t)(k * 1024 >> 4) : (uint64_t)(k * UMMA_K * 4 >> 4);
           if ((i | k) == 0) umma_tf32(tmem_base, dg_hi + ko, dx_hi + ko, idesc, 0u);
           else umma_tf32_acc(tmem_base, dg_hi + ko, dx_hi + ko, idesc);
           umma_tf32_acc(tmem_base, dg_lo + ko, dx_hi + ko, idesc);
@@ -271,6 +283,95 @@ extern "C" int flowk_shift_columns(const float* x, float* x_left, float* x_right
   return launch_status();
 }
 
+static size_t g_wgrad_smem_attr = 0;      // largest dynamic shared memory opted into so far (both entry points)
+
+// row-major operand [M, C] (C % 32 == 0) viewed by TMA as dims (32, M, C/32); box (32 channels, 32 rows, blocks):
+// per 32-channel block a [32 rows x 128 B] tile, swizzled in 32-byte atoms as transposed tf32 operands need
+static bool make_map_rows(CUtensorMap* map, const float* base, long long M, int C, int blocks) {
+  cuuint64_t dims[3] = {32, (cuuint64_t)M, (cuuint64_t)(C / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 4, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)BLOCK_K, (cuuint32_t)blocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return encode_fn() && encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static WgradPlan plan_linear_wgrad(long long M, int K, int N) {
+  WgradPlan pl = {};
+  if (M < BLOCK_K || M % BLOCK_K || M > 0x7fffffff || K < 32 || K % 32 || N < 32 || N % 32) return pl;
+  auto tiles_of = [](int a, int b) { return ((a + BLOCK_M - 1) / BLOCK_M) * ((b + 255) / 256); };
+  pl.swap = tiles_of(K, N) < tiles_of(N, K) ? 1 : 0;
+  pl.a_ch = pl.swap ? K : N;
+  pl.b_ch = pl.swap ? N : K;
+  pl.c_tiles = (pl.b_ch + 255) / 256;
+  pl.c_tile = ((pl.b_ch + pl.c_tiles - 1) / pl.c_tiles + 31) / 32 * 32;
+  pl.m_tiles = (pl.a_ch + BLOCK_M - 1) / BLOCK_M;
+  pl.g_tile_bytes = (pl.a_ch < BLOCK_M ? pl.a_ch : BLOCK_M) / 32 * 4096;
+  pl.stage_bytes = 2 * (pl.g_tile_bytes + pl.c_tile * 128);
+  pl.stages = (225 * 1024 - (BLOCK_M * 128 - pl.g_tile_bytes)) / pl.stage_bytes;
+  if (pl.stages > WG_MAX_STAGES) pl.stages = WG_MAX_STAGES;
+  if (pl.stages < 2) return pl;
+  pl.tmem_cols = 32;
+  while (pl.tmem_cols < pl.c_tile) pl.tmem_cols <<= 1;
+  const long long total_kb = M / BLOCK_K;
+  const int tiles = pl.m_tiles * pl.c_tiles;
+  long long s = (148 + tiles / 2) / tiles;
+  if (s > total_kb / 4) s = total_kb / 4;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  pl.splits = (int)s;
+  pl.ok = true;
+  return pl;
+}
+
+extern "C" int flowk_linear_wgrad_splits(long long M, int K, int N, int* transposed) {
+  const WgradPlan pl = plan_linear_wgrad(M, K, N);
+  if (transposed) *transposed = pl.ok ? pl.swap : 0;
+  return pl.ok ? pl.splits : 0;
+}
+
+extern "C" int flowk_linear_wgrad(const float* x, const float* gy, float* partial, int* status, long long M, int K, int N,
+                                  flowk_stream_t stream) {
+  const WgradPlan pl = plan_linear_wgrad(M, K, N);
+  if (!pl.ok) return FLOWK_ERR_SHAPE;
+  if (!x || !gy || !partial) return FLOWK_ERR_ARG;
+  if (!aligned16(x) || !aligned16(gy) || !aligned16(partial)) return FLOWK_ERR_ALIGN;
+  WgradParams p = {};
+  p.N = pl.a_ch;
+  p.Cin = pl.b_ch;
+  p.shift_a = pl.swap;
+  p.rows = 1;
+  p.g_tile_bytes = pl.g_tile_bytes;
+  p.taps = 1;
+  p.W = 32;
+  p.kb_per_image = (int)(M / BLOCK_K);
+  p.total_kb = p.kb_per_image;
+  const int a_blocks = pl.g_tile_bytes / 4096, b_blocks = (pl.b_ch < pl.c_tile ? pl.b_ch : pl.c_tile) / 32;
+  p.g_rows = a_blocks * 32;          // bytes per box = rows * 128 (32 rows x 128 B per block)
+  p.x_rows = b_blocks * 32;
+  p.c_tile = pl.c_tile;
+  p.c_tiles = pl.c_tiles;
+  p.m_tiles = pl.m_tiles;
+  p.stages = pl.stages;
+  p.stage_bytes = pl.stage_bytes;
+  p.tmem_cols = pl.tmem_cols;
+  p.partial = partial;
+  p.status = status;
+  CUtensorMap mg, mx;
+  // map_g always describes gy, map_x always x; their box depths follow the side (A: 128 channels, B: c_tile) they feed
+  if (!make_map_rows(&mg, gy, M, N, pl.swap ? b_blocks : a_blocks) || !make_map_rows(&mx, x, M, K, pl.swap ? a_blocks : b_blocks))
+    return FLOWK_ERR_ARG;
+  const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + (BLOCK_M * 128 - pl.g_tile_bytes);
+  if (smem > g_wgrad_smem_attr) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    g_wgrad_smem_attr = smem;
+  }
+  FLOWK_CUDA_OK(launch_pdl(conv_wgrad_kernel, dim3(pl.m_tiles * pl.c_tiles, pl.splits), dim3(WG_THREADS), smem, stream, mg, mx,
+                           mx, mx, p));
+  return FLOWK_OK;
+}
+
 extern "C" int flowk_conv_wgrad_splits(int B, int H, int W, int Cin, int N, int taps, int* transposed) {
   const WgradPlan pl = plan_wgrad(B, H, W, Cin, N, taps);
   if (transposed) *transposed = pl.ok ? pl.swap : 0;
@@ -310,10 +411,9 @@ extern "C" int flowk_conv_wgrad(const float* x, const float* x_left, const float
       !make_map_cm(&mxm, x_left, B, Cin, H * W, xx_rows) || !make_map_cm(&mxp, x_right, B, Cin, H * W, xx_rows))
     return FLOWK_ERR_ARG;
   const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + (BLOCK_M * 128 - pl.g_tile_bytes);
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
+  if (smem > g_wgrad_smem_attr) {
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
+    g_wgrad_smem_attr = smem;
   }
   FLOWK_CUDA_OK(launch_pdl(conv_wgrad_kernel, dim3(pl.m_tiles * taps * pl.c_tiles, pl.splits), dim3(WG_THREADS), smem,
                            stream, mg, mx, mxm, mxp, p));

@@ -54,6 +54,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, 
       ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -128,6 +134,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
   return d;
+}
+// MN-major tf32 operand (the contraction index is the ROW of the tile, 32 channels = 128 B are contiguous): tiles of
+// [32 rows x 128 B] per 32-channel block, loaded by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and described with the
+// matching UMMA layout type 1 (SWIZZLE_128B_BASE32B): LBO = bytes between channel blocks, SBO = 512 B between groups of
+// four rows; one K=8 MMA consumes 8 rows = 1024 B.  (Measured: profiles/dbg/umma_mn_probe.cu - the plain 128-byte
+// swizzle, layout type 2, silently yields zeros for transposed tf32 operands.)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t block_stride_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((block_stride_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) {       // both operands MN-major (bits 15, 16)
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 // cute::UMMA::InstrDescriptor: c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int n) {

@@ -162,7 +162,7 @@ def _wn_operands(v, g, cin_pad, n_pad, want_w=False, want_dg=True):
     return norm, w, fwd, dg
 
 
-WGRAD_LINEAR_TC = False   # the two transposes cost more than the cuBLAS fp32 GEMM they would replace
+WGRAD_LINEAR_TC = True    # Linear weight gradients on the tcgen05 kernel, row-major operands as MN-major tiles
 WGRAD_TC = True      # weight gradients on the tcgen05 split-K kernel (else cuDNN / cuBLAS fp32)
 
 
@@ -187,6 +187,23 @@ def wgrad_partials(x_cm, gy_cm, taps):
         _lib.call("flowk_shift_columns", x_cm.data_ptr(), xl.data_ptr(), xr.data_ptr(), x_cm.numel(), w, tc._stream())
     _lib.call("flowk_conv_wgrad", x_cm.data_ptr(), tc._p(xl), tc._p(xr), gy_cm.data_ptr(), partial.data_ptr(), None,
               b, h, w, cin, n, taps, tc._stream())
+    return partial, transposed
+
+
+def linear_wgrad_partials(x2, g2):
+    """Split-K partial weight gradients of y = x2 @ w^T from row-major x2 [M, K], g2 [M, N]: (partial, transposed) with
+    partial [S, 1, N, K] (or [S, 1, K, N]); None when the tcgen05 kernel does not take the shape."""
+    m, k = x2.shape
+    n = g2.shape[1]
+    if not (WGRAD_TC and WGRAD_LINEAR_TC):
+        return None
+    transposed = ctypes.c_int(0)
+    splits = _lib.lib.flowk_linear_wgrad_splits(m, k, n, ctypes.byref(transposed))
+    if splits <= 0:
+        return None
+    transposed = bool(transposed.value)
+    partial = torch.empty((splits, 1, k, n) if transposed else (splits, 1, n, k), device=x2.device, dtype=torch.float32)
+    _lib.call("flowk_linear_wgrad", x2.data_ptr(), g2.data_ptr(), partial.data_ptr(), None, m, k, n, tc._stream())
     return partial, transposed
 
 
@@ -283,11 +300,7 @@ class _WNLinearFn(torch.autograd.Function):
             else:
                 gx = (g2 @ wd).view(ctx.shape)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            m = x2.shape[0]
-            partial = None
-            if WGRAD_LINEAR_TC and m % 32 == 0:      # needs both operands transposed to channel-major first
-                partial = wgrad_partials(x2.t().contiguous().view(1, k, m // 32, 32),
-                                         g2.t().contiguous().view(1, n, m // 32, 32), 1)
+            partial = linear_wgrad_partials(x2, g2)
             if partial is not None:
                 gv, gg = _wn_backward_partials(v, g, norm, partial)
             else:

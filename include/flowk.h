@@ -236,6 +236,12 @@ int flowk_channel_sum(const float* x, float* out, void* workspace, long long out
 int flowk_conv_wgrad_splits(int B, int H, int W, int Cin, int N, int taps, int* transposed);
 int flowk_conv_wgrad(const float* x, const float* x_left, const float* x_right, const float* gy, float* partial,
                      int* status, int B, int H, int W, int Cin, int N, int taps, flowk_stream_t stream);
+/* Same for a Linear layer with ROW-major operands x [M, K], gy [M, N] (M % 32 == 0, K % 32 == 0, N % 32 == 0): the
+ * contraction index is the row, so the tiles are MN-major (transposed) tf32 operands - no transposed copies needed.
+ * partial [splits, N, K] (or [splits, K, N] when *transposed). */
+int flowk_linear_wgrad_splits(long long M, int K, int N, int* transposed);
+int flowk_linear_wgrad(const float* x, const float* gy, float* partial, int* status, long long M, int K, int N,
+                       flowk_stream_t stream);
 int flowk_shift_columns(const float* x, float* x_left, float* x_right, long long total, int W, flowk_stream_t stream);
 int flowk_weight_norm_bwd_partials(const float* v, const float* g, const float* norm, const float* partial, float* gv,
                                    float* gg, int N, int cin, int taps, int splits, int transposed,

@@ -437,3 +437,20 @@ def test_conv_gemm_split_k_matches_fp64_and_unsplit(B, Cin, H, W, N, taps, nchw)
                              B, H, W, Cin, N, taps, tc.PRE_BIAS, tc.OUT_NCHW if nchw else tc.OUT_F32, None, None, None, 0, None)
     assert _lib.lib.flowk_conv_gemm_splitk_slices(ctypes.addressof(args)) > 1        # these shapes do split
     assert rel_err(outs[1], ref) <= 1.5 * rel_err(outs[0], ref) + 1e-6           # shorter chains: split-K is no less accurate
+
+
+@pytest.mark.parametrize("m,k,n", [(128, 32, 32), (256, 96, 288), (16384, 96, 192), (1024, 96, 288), (512, 160, 480)])
+def test_linear_wgrad_tcgen05_mn_major_matches_fp64(m, k, n):
+    """Row-major operands as MN-major (transposed) tf32 tiles: 32-byte-atom 128-byte swizzle on both the TMA and UMMA side."""
+    from flowk import tc_autograd
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(8)
+    x = torch.randn(m, k, generator=g).to(dev)
+    gy = torch.randn(m, n, generator=g).to(dev)
+    out = tc_autograd.linear_wgrad_partials(x, gy)
+    assert out is not None
+    partial, transposed = out
+    got = partial.sum(0)[0]
+    got = got.t() if transposed else got
+    ref = gy.double().t() @ x.double()
+    assert got.shape == ref.shape and rel_err(got, ref) < 2e-5
