@@ -48,6 +48,7 @@ SIGNATURES = {
     "flowk_concat_elu_bwd": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
     "flowk_glu_fwd": ([_fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
     "flowk_weight_norm_operands": ([_fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _st], _i),
+    "flowk_weight_norm_operands_batched": ([_fp, _i, _i, _st], _i),
     "flowk_weight_norm_bwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _st], _i),
     "flowk_add_layernorm_workspace_bytes": ([ctypes.c_longlong, _i], ctypes.c_longlong),
     "flowk_add_layernorm_fwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, ctypes.c_longlong, _i, _i, _i, _i,
@@ -74,6 +75,12 @@ class ConvGemmArgs(ctypes.Structure):
                [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")] + \
                [(n, ctypes.c_void_p) for n in ("w2_hi", "w2_lo", "out2_f32")] + [("N2", ctypes.c_int)] + \
                [("splitk_ws", ctypes.c_void_p)]
+
+
+class WnJob(ctypes.Structure):
+    """Mirror of `flowk_wn_job` (include/flowk.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("v", "g", "norm", "w", "fwd_hi", "fwd_lo", "dg_hi", "dg_lo")] + \
+               [(n, ctypes.c_int) for n in ("N", "cin", "taps", "cin_pad", "n_pad", "reserved")]
 
 
 PRE_BIAS, PRE_GLU_RES_LN = 0, 1

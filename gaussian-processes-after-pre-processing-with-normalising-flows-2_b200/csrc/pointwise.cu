@@ -224,6 +224,76 @@ extern "C" int flowk_weight_norm_bwd_partials(const float* v, const float* g, co
   return launch_status();
 }
 
+// ---- all layers of a model in two launches: the per-layer kernels above are launch-bound (N*cols is tiny), and a
+// training step re-normalises ~500 weight tensors.  jobs: device array, one entry per layer (pointers are stable: the
+// optimizer updates parameters in place and the outputs are preallocated by the caller).
+namespace flowk {
+
+__global__ void wn_norm_batched_kernel(const flowk_wn_job* __restrict__ jobs) {
+  const flowk_wn_job j = jobs[blockIdx.y];
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= j.N) return;
+  const int cols = j.cin * j.taps;
+  const float* p = j.v + (size_t)row * cols;
+  float s = 0.f;
+  for (int i = threadIdx.x & 31; i < cols; i += 32) s = fmaf(p[i], p[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) j.norm[row] = sqrtf(s);
+}
+
+__global__ void wn_operands_batched_kernel(const flowk_wn_job* __restrict__ jobs) {
+  const flowk_wn_job j = jobs[blockIdx.y];
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int N = j.N, cin = j.cin, taps = j.taps, cin_pad = j.cin_pad, n_pad = j.n_pad;
+  if (j.w) {
+    const long long total = (long long)N * cin * taps, per = (long long)cin * taps;
+    for (long long i = t0; i < total; i += stride) {
+      const int n = (int)(i / per);
+      j.w[i] = j.v[i] * (j.g[n] / j.norm[n]);
+    }
+  }
+  if (j.fwd_hi) {
+    const long long total = (long long)N * taps * cin_pad;
+    for (long long i = t0; i < total; i += stride) {
+      const int c = (int)(i % cin_pad);
+      const int t = (int)((i / cin_pad) % taps);
+      const int n = (int)(i / ((long long)cin_pad * taps));
+      float val = 0.f;
+      if (c < cin) val = j.v[((size_t)n * cin + c) * taps + t] * (j.g[n] / j.norm[n]);
+      float hi, lo;
+      split_tf32_rna(val, hi, lo);
+      j.fwd_hi[i] = hi;
+      j.fwd_lo[i] = lo;
+    }
+  }
+  if (j.dg_hi) {
+    const long long total = (long long)cin * taps * n_pad;
+    for (long long i = t0; i < total; i += stride) {
+      const int n = (int)(i % n_pad);
+      const int t = (int)((i / n_pad) % taps);
+      const int c = (int)(i / ((long long)n_pad * taps));
+      float val = 0.f;
+      if (n < N) val = j.v[((size_t)n * cin + c) * taps + (taps - 1 - t)] * (j.g[n] / j.norm[n]);
+      float hi, lo;
+      split_tf32_rna(val, hi, lo);
+      j.dg_hi[i] = hi;
+      j.dg_lo[i] = lo;
+    }
+  }
+}
+
+}  // namespace flowk
+
+extern "C" int flowk_weight_norm_operands_batched(const flowk_wn_job* jobs_device, int njobs, int max_rows,
+                                                  flowk_stream_t stream) {
+  if (njobs < 0 || max_rows < 1) return FLOWK_ERR_SHAPE;
+  if (njobs == 0) return FLOWK_OK;
+  if (!jobs_device) return FLOWK_ERR_ARG;
+  wn_norm_batched_kernel<<<dim3((max_rows + 3) / 4, njobs), 128, 0, stream>>>(jobs_device);
+  wn_operands_batched_kernel<<<dim3(12, njobs), 256, 0, stream>>>(jobs_device);
+  return launch_status();
+}
+
 extern "C" int flowk_weight_norm_operands(const float* v, const float* g, int N, int cin, int taps, int cin_pad, int n_pad,
                                           float* norm, float* w, float* fwd_hi, float* fwd_lo, float* dg_hi, float* dg_lo,
                                           flowk_stream_t stream) {

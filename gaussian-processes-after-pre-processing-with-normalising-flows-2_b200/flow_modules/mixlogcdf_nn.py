@@ -67,9 +67,10 @@ class _WNConvCore(_WeightNormed):
     def forward(self, x):
         from .. import tc_autograd
         v = self.weight_v
+        prepared = tc_autograd.take_prepared(self)      # always consumed: operands are valid for ONE forward after a refresh
         if torch.is_grad_enabled() and self.padding == v.shape[2] // 2 and tc_autograd.conv_supported(x, v):
             # training: weight norm + operands fused, forward + dgrad on tcgen05
-            return tc_autograd.wn_conv2d(x, v, self.weight_g, self.bias)
+            return tc_autograd.wn_conv2d(x, v, self.weight_g, self.bias, prepared)
         return F.conv2d(x, self.normed_weight(), self.bias, padding=self.padding)
 
 
@@ -80,8 +81,9 @@ class _WNLinear(_WeightNormed):
 
     def forward(self, x):
         from .. import tc_autograd
+        prepared = tc_autograd.take_prepared(self)
         if torch.is_grad_enabled() and tc_autograd.linear_supported(x, self.weight_v):
-            return tc_autograd.wn_linear(x, self.weight_v, self.weight_g, self.bias)
+            return tc_autograd.wn_linear(x, self.weight_v, self.weight_g, self.bias, prepared)
         return F.linear(x, self.normed_weight(), self.bias)
 
 

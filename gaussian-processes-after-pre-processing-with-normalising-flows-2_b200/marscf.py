@@ -247,6 +247,8 @@ class MarScfFlow(nn.Module):
         """Uniform dequantisation, logdet0 = -ln(256) D, encode, bits/dim (marscf_main.py:192-206).
         `noise` (U[0,1), same shape as x) can be injected for reproducible parity runs."""
         d = x.size(1) * x.size(2) * x.size(3)
+        if self.training and torch.is_grad_enabled() and x.is_cuda:
+            self._weight_norm_batch().refresh()         # every weight-normed layer's GEMM operands in two launches
         if noise is None:
             noise = torch.rand_like(x)
         z = x + noise * (1. / 256.)
@@ -254,6 +256,13 @@ class MarScfFlow(nn.Module):
         z, objective = self.flow(z, logdet=logdet, reverse=False)
         nll = (-objective) / float(math.log(2.) * d)
         return z, nll, None
+
+    def _weight_norm_batch(self):
+        from . import tc_autograd
+        from .flow_modules.mixlogcdf_nn import _WNConvCore, _WNLinear
+        if getattr(self, "_wn_batch", None) is None:
+            self._wn_batch = tc_autograd.WeightNormBatch([m for m in self.modules() if isinstance(m, (_WNConvCore, _WNLinear))])
+        return self._wn_batch
 
     def reverse_flow(self, z, eps_std):
         with torch.no_grad():

@@ -226,16 +226,90 @@ def _wn_backward(v, g, norm, gw):
     return gv, gg
 
 
+class WeightNormBatch:
+    """All weight-normalised conv / Linear layers of a model, normalised and turned into GEMM operands in TWO launches
+    per training step (instead of two per layer).  `refresh()` fills the preallocated outputs and hands each module its
+    (norm, w, fwd, dg) tuple through `module._prepared`; the module's next forward consumes it (one use per refresh, so
+    a forward that was not preceded by a refresh falls back to the per-layer path and can never see stale weights)."""
+
+    def __init__(self, modules):
+        self.modules = [m for m in modules if self._eligible(m)]
+        self._key = None
+        self._build()
+
+    @staticmethod
+    def _eligible(m):
+        v = m.weight_v
+        if not (ENABLED and v.is_cuda and v.dtype == torch.float32 and v.dim() in (2, 4)):
+            return False
+        n, cin = v.shape[0], v.shape[1]
+        if v.dim() == 4:
+            return (v.shape[2], v.shape[3]) in ((1, 1), (3, 3)) and n >= 8 and cin >= 8
+        return n % 4 == 0 and cin % 32 == 0
+
+    def _pointers(self):
+        return tuple((m.weight_v.data_ptr(), m.weight_g.data_ptr()) for m in self.modules)
+
+    def _build(self):
+        self._key = self._pointers()
+        self.slots = []
+        if not self.modules:
+            return
+        dev = self.modules[0].weight_v.device
+        jobs = (_lib.WnJob * len(self.modules))()
+        self.max_rows = 1
+        for i, m in enumerate(self.modules):
+            v, g = m.weight_v, m.weight_g
+            n, cin = v.shape[0], v.shape[1]
+            taps = v.numel() // (n * cin)
+            linear = v.dim() == 2
+            cin_pad = cin if linear else _pad32(cin)
+            n_pad = n if linear else _pad32(n)
+            want_w = linear and n % 32 != 0                      # the Linear dgrad falls back to g2 @ w
+            norm = torch.empty(n, device=dev, dtype=torch.float32)
+            w = torch.empty(v.shape, device=dev, dtype=torch.float32) if want_w else None
+            fwd = torch.empty(2, n, taps * cin_pad, device=dev, dtype=torch.float32)
+            dg = None if want_w else torch.empty(2, cin, taps * n_pad, device=dev, dtype=torch.float32)
+            jobs[i] = _lib.WnJob(v.data_ptr(), g.data_ptr(), norm.data_ptr(), tc._p(w), fwd[0].data_ptr(), fwd[1].data_ptr(),
+                                 None if dg is None else dg[0].data_ptr(), None if dg is None else dg[1].data_ptr(),
+                                 n, cin, taps, cin_pad, n_pad, 0)
+            self.max_rows = max(self.max_rows, n)
+            self.slots.append((norm, w, fwd, dg))
+        raw = bytes(jobs)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+
+    def refresh(self):
+        if not self.modules:
+            return
+        if self._pointers() != self._key:          # parameters were re-allocated (.to(), load with assign=True, ...)
+            self._build()
+        _lib.call("flowk_weight_norm_operands_batched", self.table.data_ptr(), len(self.modules), self.max_rows,
+                  tc._stream())
+        for m, slot in zip(self.modules, self.slots):
+            m._prepared = slot
+
+
+def take_prepared(module):
+    """The (norm, w, fwd, dg) tuple the last WeightNormBatch.refresh() left for this module, at most once."""
+    slot = getattr(module, "_prepared", None)
+    if slot is not None:
+        module._prepared = None
+    return slot
+
+
 class _WNConv2d(torch.autograd.Function):
     """conv2d(x, v * g / ||v||, bias) with weight norm, operand construction, forward and dgrad on libflowk."""
 
     @staticmethod
-    def forward(ctx, x, v, g, bias):
+    def forward(ctx, x, v, g, bias, prepared=None):
         b, cin, h, ww = x.shape
         n, _, kh, kw = v.shape
         cp, np_ = _pad32(cin), _pad32(n)
         vd, gd = v.detach().contiguous(), g.detach().contiguous()
-        norm, _, fwd, dg = _wn_operands(vd, gd, cp, np_, want_dg=ctx.needs_input_grad[0])
+        if prepared is not None:
+            norm, _, fwd, dg = prepared
+        else:
+            norm, _, fwd, dg = _wn_operands(vd, gd, cp, np_, want_dg=ctx.needs_input_grad[0])
         a_hi, a_lo = _nchw_operand(x, cp)
         y = torch.empty(b, n, h, ww, device=x.device, dtype=torch.float32)
         tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], b, h, ww, cp, n, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW,
@@ -264,18 +338,21 @@ class _WNConv2d(torch.autograd.Function):
                 gv, gg = _wn_backward(v, g, norm, torch.nn.grad.conv2d_weight(x, v.shape, gy, padding=kh // 2))
         if ctx.has_bias and ctx.needs_input_grad[3]:
             gb = channel_sum(gy, True)
-        return gx, gv, gg, gb
+        return gx, gv, gg, gb, None
 
 
 class _WNLinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, v, g, bias):
+    def forward(ctx, x, v, g, bias, prepared=None):
         shape = x.shape
         n, k = v.shape
         x2 = x.reshape(-1, k).contiguous()
         vd, gd = v.detach().contiguous(), g.detach().contiguous()
         tc_dgrad = n % 32 == 0
-        norm, w, fwd, dg = _wn_operands(vd, gd, k, n, want_w=not tc_dgrad, want_dg=tc_dgrad)
+        if prepared is not None:
+            norm, w, fwd, dg = prepared
+        else:
+            norm, w, fwd, dg = _wn_operands(vd, gd, k, n, want_w=not tc_dgrad, want_dg=tc_dgrad)
         a_hi, a_lo = tc.split_rows(x2)
         y = torch.empty(x2.shape[0], n, device=x.device, dtype=torch.float32)
         tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], x2.shape[0] // 128, 8, 16, k, n, 1, tc.PRE_BIAS, tc.OUT_F32,
@@ -307,16 +384,16 @@ class _WNLinearFn(torch.autograd.Function):
                 gv, gg = _wn_backward(v, g, norm, g2.t() @ x2)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             gb = channel_sum(g2, False)
-        return gx, gv, gg, gb
+        return gx, gv, gg, gb, None
 
 
-def wn_conv2d(x, v, g, bias):
+def wn_conv2d(x, v, g, bias, prepared=None):
     """F.conv2d(x, weight_norm(v, g), bias, padding='same'), 1x1 / 3x3, stride 1 (mixlogcdf_nn.py:12-29)."""
-    return _WNConv2d.apply(x, v, g, bias)
+    return _WNConv2d.apply(x, v, g, bias, prepared)
 
 
-def wn_linear(x, v, g, bias):
-    return _WNLinearFn.apply(x, v, g, bias)
+def wn_linear(x, v, g, bias, prepared=None):
+    return _WNLinearFn.apply(x, v, g, bias, prepared)
 
 
 def _oci(x, dim):

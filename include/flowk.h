@@ -201,6 +201,21 @@ int flowk_glu_bwd(const float* x, const float* gy, float* gx, long long outer, i
 int flowk_weight_norm_operands(const float* v, const float* g, int N, int cin, int taps, int cin_pad, int n_pad,
                                float* norm, float* w, float* fwd_hi, float* fwd_lo, float* dg_hi, float* dg_lo,
                                flowk_stream_t stream);
+/* The same for every layer of a model in two launches (a training step re-normalises ~500 tiny weight tensors and the
+ * per-layer kernels are launch-bound).  `jobs_device` is a DEVICE array of njobs entries; w / fwd_* / dg_* may be null
+ * per entry; max_rows = the largest N among the jobs. */
+typedef struct flowk_wn_job {
+  const float* v;
+  const float* g;
+  float* norm;
+  float* w;
+  float* fwd_hi;
+  float* fwd_lo;
+  float* dg_hi;
+  float* dg_lo;
+  int N, cin, taps, cin_pad, n_pad, reserved;
+} flowk_wn_job;
+int flowk_weight_norm_operands_batched(const flowk_wn_job* jobs_device, int njobs, int max_rows, flowk_stream_t stream);
 int flowk_weight_norm_bwd(const float* v, const float* g, const float* norm, const float* gw, float* gv, float* gg,
                           int N, int cols, flowk_stream_t stream);
 

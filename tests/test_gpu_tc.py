@@ -1,4 +1,6 @@
 """tcgen05 implicit-GEMM conv kernel against torch float64 convolutions."""
+import math
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -454,3 +456,41 @@ def test_linear_wgrad_tcgen05_mn_major_matches_fp64(m, k, n):
     got = got.t() if transposed else got
     ref = gy.double().t() @ x.double()
     assert got.shape == ref.shape and rel_err(got, ref) < 2e-5
+
+
+def test_weight_norm_batch_equals_per_layer_path():
+    """One training step with the two-launch WeightNormBatch == the per-layer weight-norm path."""
+    from flowk.marscf import MarScfFlow
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    model = MarScfFlow(4, (16, 16, 3), "mixlogcdf", 2, 1, 32, num_blocks=1).to(dev)
+    x = torch.rand(4, 3, 16, 16, device=dev) - 0.5
+    noise = torch.rand(4, 3, 16, 16, device=dev)
+    model.train()
+    with torch.no_grad():
+        model(x, noise=noise)
+    for m in model.modules():                           # dropout off so both runs are comparable
+        if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout2d)):
+            m.p = 0.0
+        if hasattr(m, "drop_prob"):
+            m.drop_prob = 0.0
+
+    def grads(use_batch):
+        model.zero_grad(set_to_none=True)
+        if use_batch:
+            _, nll, _ = model(x, noise=noise)           # MarScfFlow.normal_flow refreshes the batch
+            assert model._wn_batch is not None and len(model._wn_batch.modules) > 4
+        else:
+            d = x[0].numel()
+            z = x + noise / 256.0
+            ld = x.new_full((4,), float(-math.log(256.0) * d))
+            _, obj = model.flow(z, logdet=ld, reverse=False)   # FlowNet directly: no refresh -> per-layer path
+            nll = -obj / (math.log(2.0) * d)
+        nll.mean().backward()
+        return nll.detach().clone(), [p.grad.clone() for p in model.parameters()]
+
+    nll_a, ga = grads(True)
+    nll_b, gb = grads(False)
+    assert torch.equal(nll_a, nll_b)                    # same operands -> the forward is bit-identical
+    for a, b in zip(ga, gb):                            # (a few torch backward ops use atomics: compare to fp32 round-off)
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-9
