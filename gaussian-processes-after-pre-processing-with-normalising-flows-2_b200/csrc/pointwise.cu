@@ -290,7 +290,7 @@ extern "C" int flowk_weight_norm_operands_batched(const flowk_wn_job* jobs_devic
   if (njobs == 0) return FLOWK_OK;
   if (!jobs_device) return FLOWK_ERR_ARG;
   wn_norm_batched_kernel<<<dim3((max_rows + 3) / 4, njobs), 128, 0, stream>>>(jobs_device);
-  wn_operands_batched_kernel<<<dim3(12, njobs), 256, 0, stream>>>(jobs_device);
+  wn_operands_batched_kernel<<<dim3(96, njobs), 256, 0, stream>>>(jobs_device);
   return launch_status();
 }
 
@@ -335,18 +335,27 @@ __device__ __forceinline__ size_t ln_addr(bool nchw, long long m, int c, int C, 
   return ((size_t)b * C + c) * HW + (size_t)(m - b * HW);
 }
 
-// tile[c * 33 + p]
+// tile[c * 33 + p].  NCHW: a thread keeps its pixel (p = tid & 31) and walks the channels, so the (image, offset)
+// split of the pixel index - an integer division - is done once per thread, not once per element.
 template <typename F>
 __device__ __forceinline__ void ln_tile_io(bool nchw, long long m0, long long M, int C, int HW, F f) {
   if (nchw) {
-    for (int i = threadIdx.x; i < C * kLnPix; i += kLnThreads) {
-      const int c = i >> 5, p = i & 31;
-      if (m0 + p < M) f(c, p, ln_addr(true, m0 + p, c, C, HW));
+    const int p = threadIdx.x & 31;
+    const long long m = m0 + p;
+    if (m < M) {
+      const long long b = m / HW;
+      const size_t base = (size_t)b * C * HW + (size_t)(m - b * HW);
+#pragma unroll 4
+      for (int c = threadIdx.x >> 5; c < C; c += kLnThreads / 32) f(c, p, base + (size_t)c * HW);
     }
   } else {
-    for (int i = threadIdx.x; i < C * kLnPix; i += kLnThreads) {
-      const int p = i / C, c = i - p * C;
-      if (m0 + p < M) f(c, p, (size_t)(m0 + p) * C + c);
+    const unsigned total = (unsigned)C * kLnPix, uc = (unsigned)C;
+    const size_t base = (size_t)m0 * C;
+    const unsigned limit = (M - m0 >= kLnPix) ? total : (unsigned)(M - m0) * uc;      // rows past M are skipped
+#pragma unroll 4
+    for (unsigned i = threadIdx.x; i < limit; i += kLnThreads) {
+      const unsigned p = i / uc, c = i - p * uc;
+      f((int)c, (int)p, base + i);                       // row-major: element i of the tile is at base + i
     }
   }
 }
@@ -506,15 +515,28 @@ namespace flowk {
 
 constexpr int kSumChunks = 64;
 
-__global__ void channel_sum_nchw_kernel(const float* __restrict__ x, float* __restrict__ part, int B, int C, int HW) {
-  // one CTA per (channel, chunk of samples)
+__global__ void __launch_bounds__(256) channel_sum_nchw_kernel(const float* __restrict__ x, float* __restrict__ part, int B,
+                                                              int C, int HW) {
+  // one CTA per (channel, chunk of samples); the chunk's B' x HW values are B' contiguous runs of HW floats
   __shared__ float red[8];
   const int c = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
   const int b0 = (int)((long long)B * chunk / chunks), b1 = (int)((long long)B * (chunk + 1) / chunks);
   float acc = 0.f;
-  for (int b = b0; b < b1; ++b) {
-    const float* p = x + ((size_t)b * C + c) * HW;
-    for (int i = threadIdx.x; i < HW; i += 256) acc += p[i];
+  if ((HW & 3) == 0) {
+    const int hw4 = HW >> 2, total = (b1 - b0) * hw4;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int b = b0 + i / hw4, j = i - (i / hw4) * hw4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * C + c) * HW) + j);
+      a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
+    }
+    acc = (a4.x + a4.y) + (a4.z + a4.w);
+  } else {
+    for (int b = b0; b < b1; ++b) {
+      const float* p = x + ((size_t)b * C + c) * HW;
+      for (int i = threadIdx.x; i < HW; i += 256) acc += p[i];
+    }
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -565,7 +587,7 @@ extern "C" int flowk_channel_sum(const float* x, float* out, void* workspace, lo
   int chunks;
   if (inner > 1) {
     chunks = (int)(outer < kSumChunks ? outer : kSumChunks);
-    while (chunks > 1 && (long long)chunks * C > 148 * 16) chunks >>= 1;
+    while (chunks > 1 && (long long)chunks * C > 148 * 6) chunks >>= 1;
     channel_sum_nchw_kernel<<<dim3(C, chunks), 256, 0, stream>>>(x, part, (int)outer, C, (int)inner);
   } else {
     chunks = (int)(outer / 64 < 1 ? 1 : (outer / 64 > kSumChunks ? kSumChunks : outer / 64));

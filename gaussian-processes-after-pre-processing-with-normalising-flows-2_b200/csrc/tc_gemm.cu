@@ -642,26 +642,38 @@ static bool make_map_w(CUtensorMap* map, const float* base, int N, int Ktot, int
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// split-K finish: out = sum_s partial[s][m][n] + bias[n], as fp32 rows [M, N] or NCHW [B, N, HW]; slices in index order
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
-                                     float* __restrict__ out_f32, float* __restrict__ out_nchw, int M, int N, int HW,
-                                     int splits) {
+// split-K finish: out = sum_s partial[s][m][n] + bias[n], as fp32 rows [M, N] or NCHW [B, N, HW]; slices in index order.
+// 32 x 32 (m, n) tiles: the partial rows are read coalesced along n, transposed through shared memory and written
+// coalesced along the pixels of the NCHW destination (or straight back as rows).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                            float* __restrict__ out_f32, float* __restrict__ out_nchw,
+                                                            int M, int N, int HW, int splits) {
+  __shared__ float tile[32][33];
   griddep_wait();
-  const long long total = (long long)M * N;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long m, n;
-    if (out_nchw) {                      // thread order follows the NCHW output: (b, n, hw)
-      const long long b = i / ((long long)N * HW), r = i - b * (long long)N * HW;
-      n = r / HW;
-      m = b * HW + (r - n * HW);
-    } else {
-      m = i / N;
-      n = i - m * N;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const size_t slice = (size_t)M * N;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int m = m0 + ty + 8 * r, n = n0 + tx;
+    float acc = 0.f;
+    if (m < M && n < N) {
+      const float* q = partial + (size_t)m * N + n;
+      acc = bias ? bias[n] : 0.f;
+      for (int s = 0; s < splits; ++s) acc += q[s * slice];
+      if (out_f32) out_f32[(size_t)m * N + n] = acc;
     }
-    float acc = bias ? bias[n] : 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * M + m) * N + n];
-    if (out_nchw) out_nchw[i] = acc;
-    else out_f32[i] = acc;
+    tile[ty + 8 * r][tx] = acc;
+  }
+  if (!out_nchw) return;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int n = n0 + ty + 8 * r, m = m0 + tx;
+    if (m < M && n < N) {
+      const int b = m / HW, hw = m - b * HW;
+      out_nchw[((size_t)b * N + n) * HW + hw] = tile[tx][ty + 8 * r];
+    }
   }
 }
 
@@ -872,9 +884,7 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
     FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_BIAS, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));
   }
   if (p.ksplit > 1) {
-    const long long total = (long long)p.M * N;
-    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    FLOWK_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, (const float*)a->splitk_ws, a->bias,
+    FLOWK_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3((p.M + 31) / 32, (N + 31) / 32), dim3(256), 0, stream, (const float*)a->splitk_ws, a->bias,
                              a->out_mask == OUT_F32 ? a->out_f32 : (float*)nullptr,
                              a->out_mask == OUT_NCHW ? a->out_nchw : (float*)nullptr, p.M, N, p.HW, p.ksplit));
   }
