@@ -10,42 +10,76 @@ namespace flowk {
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 __device__ __forceinline__ float elu_grad(float x) { return x > 0.f ? 1.f : expf(x); }
 
-__global__ void concat_elu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long outer, int C,
-                                      long long inner) {
-  const long long per = (long long)C * inner, total = outer * per;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long o = i / per, r = i - o * per;
-    const float v = x[i];
-    y[o * 2 * per + r] = elu_f(v);
-    y[o * 2 * per + per + r] = elu_f(-v);
+// Index type I: unsigned when the tensor has < 2^31 elements (one 32-bit division per VEC elements instead of a 64-bit
+// one per element - the division, not the memory system, bounded the first version); VEC = 4 when C*inner % 4 == 0.
+template <typename I, int VEC>
+__global__ void concat_elu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, I total_v, I per_v) {
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total_v; i += (I)gridDim.x * blockDim.x) {
+    const I o = i / per_v, r = i - o * per_v;
+    const size_t src = (size_t)i * VEC, dst = ((size_t)o * 2 * per_v + r) * VEC, half = (size_t)per_v * VEC;
+    if (VEC == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(x + src);
+      *reinterpret_cast<float4*>(y + dst) = make_float4(elu_f(v.x), elu_f(v.y), elu_f(v.z), elu_f(v.w));
+      *reinterpret_cast<float4*>(y + dst + half) = make_float4(elu_f(-v.x), elu_f(-v.y), elu_f(-v.z), elu_f(-v.w));
+    } else {
+      const float v = x[src];
+      y[dst] = elu_f(v);
+      y[dst + half] = elu_f(-v);
+    }
   }
 }
+template <typename I, int VEC>
 __global__ void concat_elu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
-                                      long long outer, int C, long long inner) {
-  const long long per = (long long)C * inner, total = outer * per;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long o = i / per, r = i - o * per;
-    const float v = x[i];
-    gx[i] = gy[o * 2 * per + r] * elu_grad(v) - gy[o * 2 * per + per + r] * elu_grad(-v);
+                                      I total_v, I per_v) {
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total_v; i += (I)gridDim.x * blockDim.x) {
+    const I o = i / per_v, r = i - o * per_v;
+    const size_t src = (size_t)i * VEC, dst = ((size_t)o * 2 * per_v + r) * VEC, half = (size_t)per_v * VEC;
+    if (VEC == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(x + src);
+      const float4 g1 = *reinterpret_cast<const float4*>(gy + dst), g2 = *reinterpret_cast<const float4*>(gy + dst + half);
+      *reinterpret_cast<float4*>(gx + src) =
+          make_float4(g1.x * elu_grad(v.x) - g2.x * elu_grad(-v.x), g1.y * elu_grad(v.y) - g2.y * elu_grad(-v.y),
+                      g1.z * elu_grad(v.z) - g2.z * elu_grad(-v.z), g1.w * elu_grad(v.w) - g2.w * elu_grad(-v.w));
+    } else {
+      const float v = x[src];
+      gx[src] = gy[dst] * elu_grad(v) - gy[dst + half] * elu_grad(-v);
+    }
   }
 }
-__global__ void glu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long outer, int C, long long inner) {
-  const long long per = (long long)C * inner, total = outer * per;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long o = i / per, r = i - o * per;
-    const float a = x[o * 2 * per + r], b = x[o * 2 * per + per + r];
-    y[i] = a / (1.f + expf(-b));
+__device__ __forceinline__ float sigmoid_f(float b) { return 1.f / (1.f + expf(-b)); }
+template <typename I, int VEC>
+__global__ void glu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, I total_v, I per_v) {
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total_v; i += (I)gridDim.x * blockDim.x) {
+    const I o = i / per_v, r = i - o * per_v;
+    const size_t dst = (size_t)i * VEC, src = ((size_t)o * 2 * per_v + r) * VEC, half = (size_t)per_v * VEC;
+    if (VEC == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(x + src), b = *reinterpret_cast<const float4*>(x + src + half);
+      *reinterpret_cast<float4*>(y + dst) =
+          make_float4(a.x * sigmoid_f(b.x), a.y * sigmoid_f(b.y), a.z * sigmoid_f(b.z), a.w * sigmoid_f(b.w));
+    } else {
+      y[dst] = x[src] * sigmoid_f(x[src + half]);
+    }
   }
 }
-__global__ void glu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
-                               long long outer, int C, long long inner) {
-  const long long per = (long long)C * inner, total = outer * per;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long o = i / per, r = i - o * per;
-    const float a = x[o * 2 * per + r], b = x[o * 2 * per + per + r], g = gy[i];
-    const float s = 1.f / (1.f + expf(-b));
-    gx[o * 2 * per + r] = g * s;
-    gx[o * 2 * per + per + r] = g * a * s * (1.f - s);
+template <typename I, int VEC>
+__global__ void glu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx, I total_v,
+                               I per_v) {
+  for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total_v; i += (I)gridDim.x * blockDim.x) {
+    const I o = i / per_v, r = i - o * per_v;
+    const size_t dst = (size_t)i * VEC, src = ((size_t)o * 2 * per_v + r) * VEC, half = (size_t)per_v * VEC;
+    if (VEC == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(x + src), b = *reinterpret_cast<const float4*>(x + src + half);
+      const float4 g = *reinterpret_cast<const float4*>(gy + dst);
+      const float s0 = sigmoid_f(b.x), s1 = sigmoid_f(b.y), s2 = sigmoid_f(b.z), s3 = sigmoid_f(b.w);
+      *reinterpret_cast<float4*>(gx + src) = make_float4(g.x * s0, g.y * s1, g.z * s2, g.w * s3);
+      *reinterpret_cast<float4*>(gx + src + half) =
+          make_float4(g.x * a.x * s0 * (1.f - s0), g.y * a.y * s1 * (1.f - s1), g.z * a.z * s2 * (1.f - s2),
+                      g.w * a.w * s3 * (1.f - s3));
+    } else {
+      const float a = x[src], g = gy[dst], sg = sigmoid_f(x[src + half]);
+      gx[src] = g * sg;
+      gx[src + half] = g * a * sg * (1.f - sg);
+    }
   }
 }
 
@@ -58,30 +92,44 @@ static int grid_for(long long total) {
 
 using namespace flowk;
 
-#define FLOWK_POINTWISE_ENTRY(NAME, KERNEL, ...)                                                            \
-  if (outer < 0 || C < 1 || inner < 1) return FLOWK_ERR_SHAPE;                                              \
-  if (outer == 0) return FLOWK_OK;                                                                          \
-  const long long total = outer * C * inner;                                                                \
-  KERNEL<<<grid_for(total), 256, 0, stream>>>(__VA_ARGS__, outer, C, inner);                                \
+// picks (index type, vector width) and launches KERNEL<I, VEC>(args..., total / VEC, C * inner / VEC)
+#define FLOWK_POINTWISE_ENTRY(KERNEL, ALIGNED, ...)                                                                     \
+  if (outer < 0 || C < 1 || inner < 1) return FLOWK_ERR_SHAPE;                                                          \
+  if (outer == 0) return FLOWK_OK;                                                                                      \
+  {                                                                                                                     \
+    const long long per = (long long)C * inner, total = outer * per;                                                    \
+    const bool v4 = (per % 4 == 0) && (ALIGNED);                                                                        \
+    const long long tv = v4 ? total / 4 : total, pv = v4 ? per / 4 : per;                                               \
+    const int grid = grid_for(tv);                                                                                      \
+    if (2 * total < 0x7fffffffLL) {                                                                                     \
+      if (v4) KERNEL<unsigned, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__, (unsigned)tv, (unsigned)pv);                   \
+      else KERNEL<unsigned, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__, (unsigned)tv, (unsigned)pv);                      \
+    } else {                                                                                                            \
+      if (v4) KERNEL<unsigned long long, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__, (unsigned long long)tv,              \
+                                                                      (unsigned long long)pv);                         \
+      else KERNEL<unsigned long long, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__, (unsigned long long)tv,                 \
+                                                                   (unsigned long long)pv);                            \
+    }                                                                                                                   \
+  }                                                                                                                     \
   return launch_status();
 
 extern "C" int flowk_concat_elu_fwd(const float* x, float* y, long long outer, int C, long long inner, flowk_stream_t stream) {
   if (outer > 0 && (!x || !y)) return FLOWK_ERR_ARG;
-  FLOWK_POINTWISE_ENTRY(concat_elu_fwd, concat_elu_fwd_kernel, x, y)
+  FLOWK_POINTWISE_ENTRY(concat_elu_fwd_kernel, aligned16(x) && aligned16(y), x, y)
 }
 extern "C" int flowk_concat_elu_bwd(const float* x, const float* gy, float* gx, long long outer, int C, long long inner,
                                     flowk_stream_t stream) {
   if (outer > 0 && (!x || !gy || !gx)) return FLOWK_ERR_ARG;
-  FLOWK_POINTWISE_ENTRY(concat_elu_bwd, concat_elu_bwd_kernel, x, gy, gx)
+  FLOWK_POINTWISE_ENTRY(concat_elu_bwd_kernel, aligned16(x) && aligned16(gy) && aligned16(gx), x, gy, gx)
 }
 extern "C" int flowk_glu_fwd(const float* x, float* y, long long outer, int C, long long inner, flowk_stream_t stream) {
   if (outer > 0 && (!x || !y)) return FLOWK_ERR_ARG;
-  FLOWK_POINTWISE_ENTRY(glu_fwd, glu_fwd_kernel, x, y)
+  FLOWK_POINTWISE_ENTRY(glu_fwd_kernel, aligned16(x) && aligned16(y), x, y)
 }
 extern "C" int flowk_glu_bwd(const float* x, const float* gy, float* gx, long long outer, int C, long long inner,
                              flowk_stream_t stream) {
   if (outer > 0 && (!x || !gy || !gx)) return FLOWK_ERR_ARG;
-  FLOWK_POINTWISE_ENTRY(glu_bwd, glu_bwd_kernel, x, gy, gx)
+  FLOWK_POINTWISE_ENTRY(glu_bwd_kernel, aligned16(x) && aligned16(gy) && aligned16(gx), x, gy, gx)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -242,24 +290,24 @@ __global__ void wn_norm_batched_kernel(const flowk_wn_job* __restrict__ jobs) {
 }
 
 __global__ void wn_operands_batched_kernel(const flowk_wn_job* __restrict__ jobs) {
+  // 32-bit index math throughout (a weight tensor has far fewer than 2^31 elements)
   const flowk_wn_job j = jobs[blockIdx.y];
-  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int N = j.N, cin = j.cin, taps = j.taps, cin_pad = j.cin_pad, n_pad = j.n_pad;
+  const unsigned stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned N = j.N, cin = j.cin, taps = j.taps, cin_pad = j.cin_pad, n_pad = j.n_pad;
   if (j.w) {
-    const long long total = (long long)N * cin * taps, per = (long long)cin * taps;
-    for (long long i = t0; i < total; i += stride) {
-      const int n = (int)(i / per);
+    const unsigned total = N * cin * taps, per = cin * taps;
+    for (unsigned i = t0; i < total; i += stride) {
+      const unsigned n = i / per;
       j.w[i] = j.v[i] * (j.g[n] / j.norm[n]);
     }
   }
   if (j.fwd_hi) {
-    const long long total = (long long)N * taps * cin_pad;
-    for (long long i = t0; i < total; i += stride) {
-      const int c = (int)(i % cin_pad);
-      const int t = (int)((i / cin_pad) % taps);
-      const int n = (int)(i / ((long long)cin_pad * taps));
+    const unsigned total = N * taps * cin_pad, row = taps * cin_pad;
+    for (unsigned i = t0; i < total; i += stride) {
+      const unsigned n = i / row, r = i - n * row;
+      const unsigned t = r / cin_pad, c = r - t * cin_pad;
       float val = 0.f;
-      if (c < cin) val = j.v[((size_t)n * cin + c) * taps + t] * (j.g[n] / j.norm[n]);
+      if (c < cin) val = j.v[(n * cin + c) * taps + t] * (j.g[n] / j.norm[n]);
       float hi, lo;
       split_tf32_rna(val, hi, lo);
       j.fwd_hi[i] = hi;
@@ -267,13 +315,12 @@ __global__ void wn_operands_batched_kernel(const flowk_wn_job* __restrict__ jobs
     }
   }
   if (j.dg_hi) {
-    const long long total = (long long)cin * taps * n_pad;
-    for (long long i = t0; i < total; i += stride) {
-      const int n = (int)(i % n_pad);
-      const int t = (int)((i / n_pad) % taps);
-      const int c = (int)(i / ((long long)n_pad * taps));
+    const unsigned total = cin * taps * n_pad, row = taps * n_pad;
+    for (unsigned i = t0; i < total; i += stride) {
+      const unsigned c = i / row, r = i - c * row;
+      const unsigned t = r / n_pad, n = r - t * n_pad;
       float val = 0.f;
-      if (n < N) val = j.v[((size_t)n * cin + c) * taps + (taps - 1 - t)] * (j.g[n] / j.norm[n]);
+      if (n < N) val = j.v[(n * cin + c) * taps + (taps - 1 - t)] * (j.g[n] / j.norm[n]);
       float hi, lo;
       split_tf32_rna(val, hi, lo);
       j.dg_hi[i] = hi;

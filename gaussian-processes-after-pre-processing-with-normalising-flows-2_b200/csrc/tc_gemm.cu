@@ -588,21 +588,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 // elementwise helpers around the GEMMs
 // --------------------------------------------------------------------------------------------------
 // NCHW slice -> NHWC hi/lo operand, channel dim zero-padded to c_pad (conditioner input, mixlogcdf_nn.py:66)
-__global__ void nchw_to_nhwc_hilo_kernel(const float* __restrict__ x, long long batch_stride, int c, int hw, int c_pad,
-                                         float* __restrict__ hi, float* __restrict__ lo, long long total) {
+__global__ void __launch_bounds__(256) nchw_to_nhwc_hilo_kernel(const float* __restrict__ x, long long batch_stride, int c,
+                                                               int hw, int c_pad, float* __restrict__ hi,
+                                                               float* __restrict__ lo) {
+  // 32 pixels x 32 channels per CTA, transposed through shared memory: reads coalesced along the pixels of the NCHW
+  // source, writes coalesced along the channels of the NHWC operand pair.  grid = (pixel tiles, channel tiles, B)
+  __shared__ float tile[32][33];
   griddep_launch();
   griddep_wait();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c_pad);
-    const long long m = i / c_pad;
-    const int p = (int)(m % hw);
-    const long long b = m / hw;
-    const float v = ch < c ? x[b * batch_stride + (long long)ch * hw + p] : 0.f;
-    float h, l;
-    split_tf32(v, h, l);
-    hi[i] = h;
-    lo[i] = l;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = x + (size_t)blockIdx.z * batch_stride;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ch = c0 + ty + 8 * r, p = p0 + tx;
+    tile[ty + 8 * r][tx] = (ch < c && p < hw) ? __ldg(src + (size_t)ch * hw + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int p = p0 + ty + 8 * r, ch = c0 + tx;
+    if (p < hw && ch < c_pad) {
+      float h, l;
+      split_tf32(tile[tx][ty + 8 * r], h, l);
+      const size_t o = ((size_t)blockIdx.z * hw + p) * c_pad + ch;
+      hi[o] = h;
+      lo[o] = l;
+    }
   }
 }
 
@@ -896,9 +908,9 @@ extern "C" int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, i
   if (B < 0 || C < 1 || HW < 1 || C_pad < C) return FLOWK_ERR_SHAPE;
   if (B == 0) return FLOWK_OK;
   if (!x || !hi || !lo) return FLOWK_ERR_ARG;
-  const long long total = (long long)B * HW * C_pad;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  FLOWK_CUDA_OK(launch_pdl(nchw_to_nhwc_hilo_kernel, dim3(blocks), dim3(256), 0, stream, x, batch_stride, C, HW, C_pad, hi, lo, total));
+  if (B > 65535) return FLOWK_ERR_SHAPE;
+  FLOWK_CUDA_OK(launch_pdl(nchw_to_nhwc_hilo_kernel, dim3((HW + 31) / 32, (C_pad + 31) / 32, B), dim3(256), 0, stream, x,
+                           batch_stride, C, HW, C_pad, hi, lo));
   return launch_status();
 }
 
