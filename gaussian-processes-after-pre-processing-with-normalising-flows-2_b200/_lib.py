@@ -63,6 +63,7 @@ SIGNATURES = {
     "flowk_shift_columns": ([_fp, _fp, _fp, ctypes.c_longlong, _i, _st], _i),
     "flowk_weight_norm_bwd_partials": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _st], _i),
     "flowk_conv_gemm_splitk_slices": ([_fp], _i),
+    "flowk_adamax_step": ([_fp, _i, _fp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _st], _i),
     "flowk_glu_bwd": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
 }
 
@@ -81,6 +82,11 @@ class WnJob(ctypes.Structure):
     """Mirror of `flowk_wn_job` (include/flowk.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("v", "g", "norm", "w", "fwd_hi", "fwd_lo", "dg_hi", "dg_lo")] + \
                [(n, ctypes.c_int) for n in ("N", "cin", "taps", "cin_pad", "n_pad", "reserved")]
+
+
+class AdamaxChunk(ctypes.Structure):
+    """Mirror of `flowk_adamax_chunk` (include/flowk.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("p", "g", "m", "u")] + [("n", ctypes.c_longlong)]
 
 
 PRE_BIAS, PRE_GLU_RES_LN = 0, 1

@@ -151,16 +151,14 @@ class GatedAttn(nn.Module):
         seq, heads, d = h * w, self.num_heads, c // self.num_heads
         t = x.reshape(b, seq, c) + self._pos_enc(seq, c, x.device)
         proj = self.in_proj(t)
-        # in_proj output order is (k | v | q): memory = first 2C, query = last C (mixlogcdf_nn.py:136-139)
-        k, v, q = proj[..., :c], proj[..., c:2 * c], proj[..., 2 * c:]
-
-        def heads_first(m):
-            return m.reshape(b, seq, heads, d).permute(0, 2, 1, 3)
-
-        q = heads_first(q) * (d ** -0.5)
-        weights = torch.softmax(q @ heads_first(k).transpose(-1, -2), dim=-1)
+        # in_proj output order is (k | v | q): memory = first 2C, query = last C (mixlogcdf_nn.py:136-139).
+        # ONE strided copy puts all three head-first, [3, B, heads, seq, d] contiguous: the batched matmuls then need
+        # no further layout copies and the backward is a single permute-copy instead of slice-gradient fills.
+        kvq = proj.view(b, seq, 3, heads, d).permute(2, 0, 3, 1, 4).contiguous()
+        k, v, q = kvq[0], kvq[1], kvq[2] * (d ** -0.5)
+        weights = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
         weights = F.dropout(weights, self.drop_prob, self.training)
-        att = (weights @ heads_first(v)).permute(0, 2, 1, 3).reshape(b, h, w, c)
+        att = (weights @ v).permute(0, 2, 1, 3).reshape(b, h, w, c)
         return _glu(self.gate(att), -1)
 
 

@@ -1,0 +1,103 @@
+"""`FusedAdamax`: torch.optim.Adamax (the reference's optimizer, marscf_main.py:302: lr 1e-4, betas (0.9, 0.999), eps 1e-8,
+no weight decay) as ONE libflowk launch over all parameter tensors - one pass over HBM instead of ~10 multi-tensor
+passes (7.2 ms -> 0.4 ms for the 44.5 M parameters of cfg2).  State (`exp_avg`, `exp_inf`, `step`) and `state_dict()` keep
+torch's layout, so optimizer checkpoints interchange with `torch.optim.Adamax`.
+
+The learning rate and bias correction reach the kernel through a device scalar (`clr = lr / (1 - beta1^step)`) that
+`step()` refreshes on the host side, so the update can be captured in a CUDA graph: call `prepare_step()` before each
+replay of a graph that captured `apply()`.
+"""
+import torch
+
+from . import _lib, tc
+
+CHUNK = 16384
+
+
+class FusedAdamax(torch.optim.Optimizer):
+    def __init__(self, params, lr=2e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._table = None
+        self._key = None
+        self._clr = None
+        self._steps = 0
+
+    # ------------------------------------------------------------------ state
+    def _ensure_state(self):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = torch.tensor(0.0)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_inf"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+
+    def _build(self):
+        """Device table of (p, g, exp_avg, exp_inf, n) pieces, one per <= CHUNK elements; one table per param group."""
+        tables, key = [], []
+        for group in self.param_groups:
+            chunks = []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
+                st = self.state[p]
+                ptrs = (p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_inf"].data_ptr())
+                key.append(ptrs)
+                n = p.numel()
+                for off in range(0, n, CHUNK):
+                    cnt = min(CHUNK, n - off)
+                    chunks.append(_lib.AdamaxChunk(*(q + 4 * off for q in ptrs), cnt))
+            arr = (_lib.AdamaxChunk * len(chunks))(*chunks)
+            dev = group["params"][0].device
+            tables.append((torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev) if chunks else None, len(chunks)))
+        self._table, self._key = tables, key
+        if self._clr is None:
+            dev = self.param_groups[0]["params"][0].device
+            self._clr = torch.zeros(len(self.param_groups), device=dev, dtype=torch.float32)
+
+    def _current_key(self):
+        key = []
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is not None:
+                    st = self.state[p]
+                    key.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_inf"].data_ptr()))
+        return key
+
+    # ------------------------------------------------------------------ stepping
+    def prepare_step(self):
+        """Host side of one step: advance the step count and refresh the device scalar lr / (1 - beta1^t)."""
+        self._ensure_state()
+        if self._table is None or self._current_key() != self._key:
+            self._build()
+        self._steps += 1
+        vals = []
+        for group in self.param_groups:
+            lr = float(group["lr"])
+            vals.append(lr / (1.0 - group["betas"][0] ** self._steps))
+            for p in group["params"]:
+                if p in self.state and self.state[p]:
+                    self.state[p]["step"] += 1
+        self._clr.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=True)
+
+    def apply(self):
+        """Device side: one launch per param group (capturable)."""
+        for gi, group in enumerate(self.param_groups):
+            table, n = self._table[gi]
+            if n:
+                b1, b2 = group["betas"]
+                _lib.call("flowk_adamax_step", table.data_ptr(), n, self._clr[gi:].data_ptr(), float(b1), float(b2),
+                          float(group["eps"]), tc._stream())
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.prepare_step()
+        self.apply()
+        return loss

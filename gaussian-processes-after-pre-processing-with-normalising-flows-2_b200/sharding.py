@@ -133,8 +133,16 @@ class ShardedTrainer:
         on_cuda = next(model.parameters()).is_cuda
         self.use_graph = on_cuda if use_graph is None else (use_graph and on_cuda)
         self.base_lr, self.warm_up = lr, warm_up
-        if self.use_graph:
+        self.fused = False
+        if on_cuda:
+            # one-launch Adamax over all parameter tensors (flowk.optim); the learning rate reaches the kernel through
+            # a device scalar refreshed on the host, so the same update is captured when use_graph is on
+            from .optim import FusedAdamax
             torch.backends.cudnn.benchmark = True      # fixed shapes: let cuDNN pick its fastest fp32 algorithms (-6 %)
+            self.opt = FusedAdamax(model.parameters(), lr=lr)
+            self.sched = None
+            self.fused = True
+        elif self.use_graph:
             self.lr_t = torch.tensor(lr, device=next(model.parameters()).device)
             self.opt = torch.optim.Adamax(model.parameters(), lr=self.lr_t, capturable=True, foreach=True)
             self.sched = None
@@ -154,6 +162,9 @@ class ShardedTrainer:
         if self.sched is not None:
             self.sched.last_epoch = self.global_step - 1
             self.sched.step()
+        elif self.fused:
+            for group in self.opt.param_groups:
+                group["lr"] = self.base_lr * min(1., self.global_step / self.warm_up)
         else:
             self.lr_t.fill_(self.base_lr * min(1., self.global_step / self.warm_up))
 
@@ -178,8 +189,13 @@ class ShardedTrainer:
             _, nll, _ = self.model(static_x)
             loss = nll.mean()
             loss.backward()
-        with torch.cuda.graph(up, stream=side):
-            self.opt.step()
+        if self.fused:
+            self.opt.prepare_step()              # host side (step count, lr scalar); the graph holds only the kernel
+            with torch.cuda.graph(up, stream=side):
+                self.opt.apply()
+        else:
+            with torch.cuda.graph(up, stream=side):
+                self.opt.step()
         self._graphs = (fb, up, static_x, loss.detach())
 
     def step(self, x_local):
@@ -193,6 +209,10 @@ class ShardedTrainer:
             static_x.copy_(x_local, non_blocking=True)
             fb.replay()
             self.buckets.reduce_all()
+            if self.fused and not getattr(self, "_first_replay_done", False):
+                self._first_replay_done = True   # prepare_step() already ran for this step inside _capture
+            elif self.fused:
+                self.opt.prepare_step()
             up.replay()
         self.global_step += self.global_batch or x_local.shape[0] * self.world
         self._set_lr()

@@ -262,6 +262,20 @@ int flowk_weight_norm_bwd_partials(const float* v, const float* g, const float* 
                                    float* gg, int N, int cin, int taps, int splits, int transposed,
                                    flowk_stream_t stream);
 
+/* Adamax step (torch.optim.Adamax semantics, weight_decay = 0; the reference's optimizer, marscf_main.py:302) over every
+ * parameter tensor of a model in one launch / one HBM pass.  `chunks_device`: DEVICE array, each tensor cut into pieces
+ * (the caller chooses the size, e.g. 16 Ki elements), one CTA per piece; p, m (exp_avg), u (exp_inf) are updated in
+ * place from g.  clr_device: device scalar lr / (1 - beta1^step), refreshed by the host before every (graph) launch. */
+typedef struct flowk_adamax_chunk {
+  float* p;
+  const float* g;
+  float* m;
+  float* u;
+  long long n;
+} flowk_adamax_chunk;
+int flowk_adamax_step(const flowk_adamax_chunk* chunks_device, int nchunks, const float* clr_device, float beta1,
+                      float beta2, float eps, flowk_stream_t stream);
+
 /* Self-attention core of GatedAttn (mixlogcdf_nn.py:134-147,154-173), inference: qkv = in_proj rows [B*HW, 3C] in the
  * reference's (k | v | q) column order; out_hi/out_lo [B*HW, C] = softmax(q k^T / sqrt(C/heads)) v as an operand pair.
  * C/heads in {8,16,24,32,40,64}; HW <= 256 or a multiple of 256. */

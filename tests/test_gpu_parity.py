@@ -7,6 +7,8 @@ Tolerance (BASELINE.json north_star): z and logdet within 1e-4 relative in fp32,
 """
 import math
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -623,3 +625,41 @@ def test_odd_batch_sizes_through_tensor_core_path(F, coupling, hidden, B):
             conditioner_tc.ENABLED = True
     parity(z_tc, z_ref.cpu(), what="z")
     assert float((nll_tc - nll_ref).abs().max()) < 1e-3
+
+
+@pytest.mark.gpu
+def test_fused_adamax_matches_torch_adamax():
+    """flowk.optim.FusedAdamax (one launch over all tensors) == torch.optim.Adamax over several steps, incl. a changing
+    learning rate, odd tensor sizes (scalar tail / unaligned views) and state_dict interchange."""
+    from flowk.optim import FusedAdamax
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(12)
+    shapes = [(96, 192, 3, 3), (7,), (3, 5), (40000,), (1, 1, 1), (96,)]
+    flat = torch.zeros(sum(int(np.prod(s)) for s in shapes), device=dev)         # gradients as unaligned views of one buffer
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    off = 0
+    for p in pa:
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    oa, ob = FusedAdamax(pa, lr=1e-2), torch.optim.Adamax(pb, lr=1e-2)
+    for it in range(6):
+        lr = 1e-2 * (it + 1) / 6
+        for grp in list(oa.param_groups) + list(ob.param_groups):
+            grp["lr"] = lr
+        for p, q in zip(pa, pb):
+            gr = torch.randn(p.shape, generator=g).to(dev) * (10.0 ** (it - 3))
+            p.grad.copy_(gr)
+            q.grad = gr.clone()
+        oa.step()
+        ob.step()
+    for p, q in zip(pa, pb):
+        assert float((p - q).abs().max()) <= 2e-6 * float(q.abs().max()) + 1e-7
+    sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        assert set(sa[k].keys()) == set(sb[k].keys()) == {"step", "exp_avg", "exp_inf"}
+        assert float(sa[k]["step"]) == float(sb[k]["step"]) == 6.0
+        torch.testing.assert_close(sa[k]["exp_inf"], sb[k]["exp_inf"], rtol=1e-6, atol=1e-12)
+    ob2 = torch.optim.Adamax(pb, lr=1e-2)
+    ob2.load_state_dict(oa.state_dict())                     # torch's optimizer accepts the fused optimizer's checkpoint
