@@ -121,6 +121,8 @@ class GatedConv(nn.Module):
 class GatedAttn(nn.Module):
     """Gated multi-head self-attention over the H*W positions of an NHWC tensor (mixlogcdf_nn.py:105-224)."""
 
+    _instances = 0
+
     def __init__(self, d_model, num_heads=4, drop_prob=0.):
         super().__init__()
         self.d_model = d_model
@@ -129,6 +131,8 @@ class GatedAttn(nn.Module):
         self.in_proj = _WNLinear(d_model, 3 * d_model, bias=False)
         self.gate = _WNLinear(d_model, 2 * d_model)
         self._pos = {}
+        GatedAttn._instances += 1
+        self._salt = GatedAttn._instances          # keys this layer's dropout masks (flowk training attention kernels)
 
     @staticmethod
     def get_pos_enc(seq_len, num_channels, device):
@@ -151,6 +155,11 @@ class GatedAttn(nn.Module):
         seq, heads, d = h * w, self.num_heads, c // self.num_heads
         t = x.reshape(b, seq, c) + self._pos_enc(seq, c, x.device)
         proj = self.in_proj(t)
+        from .. import tc_autograd
+        if torch.is_grad_enabled() and tc_autograd.attention_train_supported(proj, heads):
+            # fused forward / backward with in-kernel dropout: nothing of size seq x seq touches HBM
+            att = tc_autograd.attention_core(proj, heads, self.drop_prob if self.training else 0.0, self._salt)
+            return _glu(self.gate(att.view(b, h, w, c)), -1)
         # in_proj output order is (k | v | q): memory = first 2C, query = last C (mixlogcdf_nn.py:136-139).
         # ONE strided copy puts all three head-first, [3, B, heads, seq, d] contiguous: the batched matmuls then need
         # no further layout copies and the backward is a single permute-copy instead of slice-gradient fills.

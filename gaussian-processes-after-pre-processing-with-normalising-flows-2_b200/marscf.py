@@ -249,6 +249,8 @@ class MarScfFlow(nn.Module):
         d = x.size(1) * x.size(2) * x.size(3)
         if self.training and torch.is_grad_enabled() and x.is_cuda:
             self._weight_norm_batch().refresh()         # every weight-normed layer's GEMM operands in two launches
+            from . import tc_autograd
+            tc_autograd.advance_dropout_seed(x.device)  # fresh attention-dropout masks (also on every graph replay)
         if noise is None:
             noise = torch.rand_like(x)
         z = x + noise * (1. / 256.)

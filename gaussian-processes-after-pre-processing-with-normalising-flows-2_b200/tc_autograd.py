@@ -496,6 +496,78 @@ def add_layernorm(a, b, norm, in_nchw, out_nchw):
     return _AddLayerNorm.apply(a, b, norm.weight, norm.bias, norm.eps, in_nchw, out_nchw)
 
 
+_DROPOUT_SEED = {}
+
+
+def dropout_seed(device):
+    """Per-device scalar the attention-dropout masks are keyed on; `advance_dropout_seed` bumps it once per training
+    step ON THE DEVICE, so a captured CUDA graph draws fresh masks at every replay.  (The backward pass re-reads it: run
+    backward before the next training forward.)"""
+    t = _DROPOUT_SEED.get(device)
+    if t is None:
+        t = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(device)
+        _DROPOUT_SEED[device] = t
+    return t
+
+
+def advance_dropout_seed(device):
+    dropout_seed(device).add_(1)
+
+
+def attention_train_supported(qkv, heads):
+    if not (ENABLED and ATTENTION_TC and qkv.is_cuda and qkv.dtype == torch.float32 and qkv.dim() == 3):
+        return False
+    b, s, c3 = qkv.shape
+    c = c3 // 3
+    return c3 % 3 == 0 and c % heads == 0 and c // heads in (8, 16, 24, 32, 40) and s % 8 == 0 and \
+        b * heads * s * s < 2 ** 32 - 1
+
+
+ATTENTION_TC = True      # training attention core (softmax(q k^T) v with dropout, forward + backward) on the flowk kernels
+
+
+class _AttentionCore(torch.autograd.Function):
+    """att = dropout(softmax(q k^T / sqrt(d))) v per (image, head); qkv [B, S, 3C] rows in (k | v | q) order -> [B, S, C]."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, p_drop, salt):
+        qkv = qkv.contiguous()
+        b, s, c3 = qkv.shape
+        c = c3 // 3
+        out = torch.empty(b, s, c, device=qkv.device, dtype=torch.float32)
+        lse = torch.empty(b * heads, s, device=qkv.device, dtype=torch.float32)
+        seed = dropout_seed(qkv.device)
+        _lib.call("flowk_attention_train_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), seed.data_ptr(), salt,
+                  float(p_drop), b, s, c, heads, tc._stream())
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.cfg = (heads, float(p_drop), salt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        heads, p_drop, salt = ctx.cfg
+        b, s, c3 = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse)
+        seed = dropout_seed(qkv.device)
+        _lib.call("flowk_attention_train_bwd", qkv.data_ptr(), out.data_ptr(), dout.contiguous().data_ptr(), lse.data_ptr(),
+                  delta.data_ptr(), dqkv.data_ptr(), seed.data_ptr(), salt, p_drop, b, s, c3 // 3, heads, tc._stream())
+        return dqkv, None, None, None
+
+
+def attention_core(qkv, heads, p_drop, salt):
+    return _AttentionCore.apply(qkv, heads, p_drop, salt)
+
+
+def attention_dropout_mask(device, salt, p_drop, pairs, seq):
+    """The multipliers (0 or 1/(1-p)) the kernels apply, [pairs, seq, seq] - test helper."""
+    mask = torch.empty(pairs, seq, seq, device=device, dtype=torch.float32)
+    _lib.call("flowk_attention_dropout_mask", dropout_seed(device).data_ptr(), salt, float(p_drop), pairs, seq,
+              mask.data_ptr(), tc._stream())
+    return mask
+
+
 def pointwise_ok(x):
     return ENABLED and x.is_cuda and x.dtype == torch.float32
 

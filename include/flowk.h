@@ -262,6 +262,21 @@ int flowk_weight_norm_bwd_partials(const float* v, const float* g, const float* 
                                    float* gg, int N, int cin, int taps, int splits, int transposed,
                                    flowk_stream_t stream);
 
+/* Training-time attention core with attention-weight dropout (mixlogcdf_nn.py:134-147 with :143's F.dropout): forward and
+ * backward.  qkv / dqkv rows [B*HW, 3C] in (k | v | q) order; out / dout rows [B*HW, C]; lse [B*heads, HW] (row
+ * log-sum-exp, written by the forward); delta_ws [B*heads, HW] scratch.  The dropout mask is a counter-based hash of
+ * (*seed_device, salt, image*head, query, key): the backward regenerates it, nothing of size HW x HW touches HBM.
+ * seed_device: device scalar the caller advances once per training step (so a captured graph draws fresh masks on each
+ * replay); salt: per-layer constant.  HW % 8 == 0, C / heads in {8, 16, 24, 32, 40}, B*heads*HW*HW < 2^32.
+ * flowk_attention_dropout_mask materialises the multipliers (0 or 1/(1-p)) [B*heads, HW, HW] - for tests. */
+int flowk_attention_train_fwd(const float* qkv, float* out, float* lse, const unsigned* seed_device, unsigned salt,
+                              float p_drop, int B, int HW, int C, int heads, flowk_stream_t stream);
+int flowk_attention_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* delta_ws,
+                              float* dqkv, const unsigned* seed_device, unsigned salt, float p_drop, int B, int HW, int C,
+                              int heads, flowk_stream_t stream);
+int flowk_attention_dropout_mask(const unsigned* seed_device, unsigned salt, float p_drop, int pairs, int HW, float* mask,
+                                 flowk_stream_t stream);
+
 /* Adamax step (torch.optim.Adamax semantics, weight_decay = 0; the reference's optimizer, marscf_main.py:302) over every
  * parameter tensor of a model in one launch / one HBM pass.  `chunks_device`: DEVICE array, each tensor cut into pieces
  * (the caller chooses the size, e.g. 16 Ki elements), one CTA per piece; p, m (exp_avg), u (exp_inf) are updated in

@@ -18,6 +18,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_sh
     step(); torch.cuda.synchronize()
 # CPU-side ops sorted by the device time of the kernels they launched
 ka = prof.key_averages(group_by_input_shape=True)
-rows = sorted(ka, key=lambda e: -e.self_device_time_total)[:45]
+rows = [e for e in ka if e.key.startswith("aten::") or e.key.startswith("_") or "Backward" in e.key]
+rows = sorted(rows, key=lambda e: -e.device_time_total)[:60]
 for e in rows:
-    print("%8.2f ms n=%5d  %-40s %s" % (e.self_device_time_total/1e3, e.count, e.key[:40], str(e.input_shapes)[:110]))
+    print("%8.2f ms n=%5d  %-40s %s" % (e.device_time_total/1e3, e.count, e.key[:40], str(e.input_shapes)[:110]))

@@ -494,3 +494,36 @@ def test_weight_norm_batch_equals_per_layer_path():
     assert torch.equal(nll_a, nll_b)                    # same operands -> the forward is bit-identical
     for a, b in zip(ga, gb):                            # (a few torch backward ops use atomics: compare to fp32 round-off)
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-9
+
+
+@pytest.mark.parametrize("B,S,C,heads,p", [(2, 16, 32, 4, 0.0), (3, 64, 96, 4, 0.2), (2, 256, 96, 4, 0.2), (1, 136, 160, 4, 0.3),
+                                           (2, 32, 64, 8, 0.5)])
+def test_training_attention_fwd_bwd_match_fp64(B, S, C, heads, p):
+    """dropout(softmax(q k^T / sqrt d)) v and its gradients against fp64 autograd using the kernels' own dropout mask."""
+    from flowk import tc_autograd
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(23)
+    qkv = torch.randn(B, S, 3 * C, generator=g).to(dev).requires_grad_()
+    dout = torch.randn(B, S, C, generator=g).to(dev)
+    salt, d = 7, C // heads
+    out = tc_autograd.attention_core(qkv, heads, p, salt)
+    out.backward(dout)
+    mask = tc_autograd.attention_dropout_mask(dev, salt, p, B * heads, S).double().view(B, heads, S, S)
+    if p > 0:
+        keep = float((mask > 0).double().mean())
+        assert abs(keep - (1 - p)) < 0.02 and abs(float(mask.max()) - 1 / (1 - p)) < 1e-6
+    else:
+        assert torch.all(mask == 1)
+    x = qkv.detach().double().requires_grad_()
+    k, v, q = x[..., :C], x[..., C:2 * C], x[..., 2 * C:]
+    hf = lambda m: m.reshape(B, S, heads, d).permute(0, 2, 1, 3)          # noqa: E731
+    w = torch.softmax((hf(q) * d ** -0.5) @ hf(k).transpose(-1, -2), dim=-1) * mask
+    ref = (w @ hf(v)).permute(0, 2, 1, 3).reshape(B, S, C)
+    ref.backward(dout.double())
+    assert rel_err(out.detach(), ref.detach()) < 2e-5
+    assert rel_err(qkv.grad, x.grad) < 5e-5
+    out2 = tc_autograd.attention_core(qkv.detach(), heads, p, salt)       # same seed -> same mask -> bit-identical
+    assert torch.equal(out2, out.detach())
+    tc_autograd.advance_dropout_seed(dev)
+    if p > 0:
+        assert not torch.equal(tc_autograd.attention_core(qkv.detach(), heads, p, salt), out.detach())
