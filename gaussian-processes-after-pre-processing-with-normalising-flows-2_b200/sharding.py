@@ -62,7 +62,9 @@ class GradientBuckets:
             self._seal(cur)
         self._pending = []
         self._ready = [0] * len(self.buckets)
-        self.overlap = True          # False: no all-reduce from the hooks (CUDA-graph capture), call reduce_all()
+        self.overlap = True          # False: no all-reduce from the hooks, call reduce_all() after the backward pass
+        # NCCL averages inside the collective; gloo (CPU tests) sums and the mean is taken by a division afterwards
+        self._avg = self.world > 1 and dist.get_backend() == "nccl"
         self._bucket_of = {}
         for bi, (_, ps) in enumerate(self.buckets):
             for p in ps:
@@ -83,18 +85,22 @@ class GradientBuckets:
         if self._ready[bi] == len(self.buckets[bi][1]):
             self._launch(bi)
 
+    def _all_reduce(self, flat):
+        return dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, async_op=True)
+
     def _launch(self, bi):
         if self.world > 1 and self.overlap:
-            self._pending.append(dist.all_reduce(self.buckets[bi][0], async_op=True))
+            self._pending.append(self._all_reduce(self.buckets[bi][0]))
 
     def reduce_all(self):
         """All-reduce every bucket now (used after a CUDA-graph replay of forward + backward) and average."""
         if self.world > 1:
-            handles = [dist.all_reduce(flat, async_op=True) for flat, _ in self.buckets]
+            handles = [self._all_reduce(flat) for flat, _ in self.buckets]
             for h in handles:
                 h.wait()
-            for flat, _ in self.buckets:
-                flat.div_(self.world)
+            if not self._avg:
+                for flat, _ in self.buckets:
+                    flat.div_(self.world)
 
     def zero(self):
         for flat, _ in self.buckets:
@@ -105,11 +111,11 @@ class GradientBuckets:
         """Wait for the outstanding all-reduces and turn sums into means."""
         for bi, n in enumerate(self._ready):       # parameters that got no gradient this step
             if n != len(self.buckets[bi][1]) and self.world > 1:
-                self._pending.append(dist.all_reduce(self.buckets[bi][0], async_op=True))
+                self._pending.append(self._all_reduce(self.buckets[bi][0]))
         for h in self._pending:
             h.wait()
         self._pending = []
-        if self.world > 1:
+        if self.world > 1 and not self._avg:
             for flat, _ in self.buckets:
                 flat.div_(self.world)
 
@@ -133,6 +139,7 @@ class ShardedTrainer:
         on_cuda = next(model.parameters()).is_cuda
         self.use_graph = on_cuda if use_graph is None else (use_graph and on_cuda)
         self.base_lr, self.warm_up = lr, warm_up
+        self.graph_allreduce = False
         self.fused = False
         if on_cuda:
             # one-launch Adamax over all parameter tensors (flowk.optim); the learning rate reaches the kernel through
@@ -178,7 +185,11 @@ class ShardedTrainer:
         return loss.detach()
 
     def _capture(self, x_local):
-        self.buckets.overlap = False
+        # NCCL collectives are capturable: with FLOWK_GRAPH_ALLREDUCE=1 (default) the bucket all-reduces fired by the
+        # gradient hooks become nodes of the forward+backward graph, on NCCL's stream, overlapped with the rest of the
+        # backward pass; =0 keeps them outside (one reduce_all() between the two graphs).
+        self.graph_allreduce = self.world > 1 and os.environ.get("FLOWK_GRAPH_ALLREDUCE", "1") != "0"
+        self.buckets.overlap = self.graph_allreduce
         static_x = x_local.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -189,6 +200,9 @@ class ShardedTrainer:
             _, nll, _ = self.model(static_x)
             loss = nll.mean()
             loss.backward()
+            if self.graph_allreduce:
+                self.buckets.finish()
+        self.buckets.overlap = False
         if self.fused:
             self.opt.prepare_step()              # host side (step count, lr scalar); the graph holds only the kernel
             with torch.cuda.graph(up, stream=side):
@@ -208,7 +222,8 @@ class ShardedTrainer:
             fb, up, static_x, loss = self._graphs
             static_x.copy_(x_local, non_blocking=True)
             fb.replay()
-            self.buckets.reduce_all()
+            if not self.graph_allreduce:
+                self.buckets.reduce_all()
             if self.fused and not getattr(self, "_first_replay_done", False):
                 self._first_replay_done = True   # prepare_step() already ran for this step inside _capture
             elif self.fused:
