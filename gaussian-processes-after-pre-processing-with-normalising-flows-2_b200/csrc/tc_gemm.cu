@@ -328,7 +328,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const int n0 = n_base + j;
           if (n0 >= p.N) break;
           float v[16];
-          tmem_ld16(trow + j, v);
+          if (p.dxsplit) {                   // combine the three column-shift accumulators (see the row-major path below)
+            float vm[16], vp[16];
+            tmem_ld16(trow + j, vm);
+            tmem_ld16(trow + p.n_chunk + j, v);
+            tmem_ld16(trow + 2 * p.n_chunk + j, vp);
+            const int wcol = (slab_row0 + lane) % p.W;
+            const bool has_l = wcol > 0, has_r = wcol < p.W - 1;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float l = __shfl_up_sync(0xffffffffu, vm[i], 1), r = __shfl_down_sync(0xffffffffu, vp[i], 1);
+              v[i] += (has_l ? l : 0.f) + (has_r ? r : 0.f);
+            }
+          } else {
+            tmem_ld16(trow + j, v);
+          }
           if (!valid) continue;
           float* o = p.out_nchw + ((size_t)img * p.N + n0) * p.HW + hw;
 #pragma unroll
@@ -816,8 +830,8 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   if (stages > 6) stages = 6;
   if (stages < 1) return FLOWK_ERR_SHAPE;
   // 3x3 dx-split mode: three accumulators (one per column shift) so that an activation tile serves three taps
-  p.dxsplit = (a->taps == 9 && a->pre == PRE_BIAS && !(a->out_mask & OUT_NCHW) && W <= 32 && 32 % W == 0 &&
-               p.n_chunks == 1 && 3 * p.n_chunk <= 512 && p.ksplit == 1) ? 1 : 0;
+  p.dxsplit = (a->taps == 9 && a->pre == PRE_BIAS && W <= 32 && 32 % W == 0 && p.n_chunks == 1 && 3 * p.n_chunk <= 512 &&
+               p.ksplit == 1) ? 1 : 0;
   if (p.dxsplit) {
     p.tmem_cols = 3 * p.n_chunk <= 256 ? 256 : 512;
     if (3 * p.n_chunk <= 128) p.tmem_cols = 128;
