@@ -226,6 +226,41 @@ def _wn_backward(v, g, norm, gw):
     return gv, gg
 
 
+OVERLAP_WGRAD = True      # backward: weight/bias-gradient kernels on a side stream, concurrent with the input-gradient GEMM
+_SIDE = {}
+
+
+class _fork_wgrad:
+    """`with _fork_wgrad(device): ...` runs the body on a side stream that has waited for the current one; `join()` makes
+    the current stream wait for it.  The two gradient chains of a layer are independent, and below level 1 neither fills
+    the GPU.  (Capturable: inside a CUDA graph the fork becomes a parallel branch.)"""
+
+    def __init__(self, device):
+        self.on = OVERLAP_WGRAD
+        if self.on:
+            self.main = torch.cuda.current_stream(device)
+            side = _SIDE.get(device)
+            if side is None:
+                side = _SIDE[device] = torch.cuda.Stream(device)
+            self.side = side
+            self.ctx = torch.cuda.stream(side)
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.main)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.on:
+            self.main.wait_stream(self.side)
+
+
 class WeightNormBatch:
     """All weight-normalised conv / Linear layers of a model, normalised and turned into GEMM operands in TWO launches
     per training step (instead of two per layer).  `refresh()` fills the preallocated outputs and hands each module its
@@ -325,19 +360,22 @@ class _WNConv2d(torch.autograd.Function):
         n, _, kh, kw = v.shape
         gy = gy.contiguous()
         gx = gv = gg = gb = None
-        if ctx.needs_input_grad[0]:
+        fork = _fork_wgrad(x.device)
+        with fork:                                  # side stream: weight and bias gradients
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                partial = wgrad_partials(x.contiguous(), gy, kh * kw)
+                if partial is not None:
+                    gv, gg = _wn_backward_partials(v, g, norm, partial)
+                else:
+                    gv, gg = _wn_backward(v, g, norm, torch.nn.grad.conv2d_weight(x, v.shape, gy, padding=kh // 2))
+            if ctx.has_bias and ctx.needs_input_grad[3]:
+                gb = channel_sum(gy, True)
+        if ctx.needs_input_grad[0]:                 # main stream: input gradient
             np_ = _pad32(n)
             g_hi, g_lo = _nchw_operand(gy, np_)
             gx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
             tc.conv_gemm(g_hi, g_lo, dg[0], dg[1], b, h, ww, np_, cin, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx, split_k=True)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            partial = wgrad_partials(x.contiguous(), gy, kh * kw)
-            if partial is not None:
-                gv, gg = _wn_backward_partials(v, g, norm, partial)
-            else:
-                gv, gg = _wn_backward(v, g, norm, torch.nn.grad.conv2d_weight(x, v.shape, gy, padding=kh // 2))
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            gb = channel_sum(gy, True)
+        fork.join()
         return gx, gv, gg, gb, None
 
 
@@ -367,7 +405,17 @@ class _WNLinearFn(torch.autograd.Function):
         n, k = v.shape
         g2 = gy.reshape(-1, n).contiguous()
         gx = gv = gg = gb = None
-        if ctx.needs_input_grad[0]:
+        fork = _fork_wgrad(g2.device)
+        with fork:                                  # side stream: weight and bias gradients
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                partial = linear_wgrad_partials(x2, g2)
+                if partial is not None:
+                    gv, gg = _wn_backward_partials(v, g, norm, partial)
+                else:
+                    gv, gg = _wn_backward(v, g, norm, g2.t() @ x2)
+            if ctx.has_bias and ctx.needs_input_grad[3]:
+                gb = channel_sum(g2, False)
+        if ctx.needs_input_grad[0]:                 # main stream: input gradient
             if ctx.tc_dgrad:
                 g_hi, g_lo = tc.split_rows(g2)
                 gx = torch.empty(g2.shape[0], k, device=g2.device, dtype=torch.float32)
@@ -376,14 +424,7 @@ class _WNLinearFn(torch.autograd.Function):
                 gx = gx.view(ctx.shape)
             else:
                 gx = (g2 @ wd).view(ctx.shape)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            partial = linear_wgrad_partials(x2, g2)
-            if partial is not None:
-                gv, gg = _wn_backward_partials(v, g, norm, partial)
-            else:
-                gv, gg = _wn_backward(v, g, norm, g2.t() @ x2)
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            gb = channel_sum(g2, False)
+        fork.join()
         return gx, gv, gg, gb, None
 
 
