@@ -524,10 +524,11 @@ def train_leg(args, device, rank, world, dist):
             "warmup": 4, "global_batch": batch * world, "grad_allreduce_mb": trainer.buckets.nbytes() / 1e6,
             "loss_bits_per_dim": float(loss),
             "note": "fwd+bwd+Adamax(+NCCL all-reduce of flat gradient buckets); forward+backward and the optimizer update "
-                    "replayed as CUDA graphs; conditioner convs/linears: forward, input-gradient and conv weight-gradient "
-                    "on the flowk tcgen05 kernels (3xTF32); weight norm, concat-ELU, GLU, residual+LayerNorm and bias "
-                    "gradients as fused flowk kernels; attention core and linear weight-gradients through torch "
-                    "(fp32); flow ops through the flowk forward/backward kernels"}
+                    "replayed as CUDA graphs (the all-reduces are nodes of the backward graph); conditioner convs/linears: "
+                    "forward, input- and weight-gradients on the flowk tcgen05 kernels (3xTF32); attention core "
+                    "(with dropout) forward/backward on the flowk mma.sync kernels; weight norm, concat-ELU, GLU, "
+                    "residual+LayerNorm, bias gradients and Adamax as fused flowk kernels; flow ops through the flowk "
+                    "forward/backward kernels"}
 
 
 def main():
