@@ -741,7 +741,7 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   const int B = a->B, H = a->H, W = a->W, Cin = a->Cin, N = a->N;
   if (B < 1 || H < 1 || W < 1 || Cin < BLOCK_K || Cin % BLOCK_K || N < 8) return FLOWK_ERR_SHAPE;
   if (a->taps != 1 && a->taps != 9) return FLOWK_ERR_ARG;
-  if (!encode_fn()) return FLOWK_ERR_ARG;
+  if (!plan_only && !encode_fn()) return FLOWK_ERR_ARG;      // planning is a pure host computation
   // M tile = bt images x ht rows x W columns = 128 positions
   int wt = W, ht, bt;
   if (W > BLOCK_M || BLOCK_M % W) return FLOWK_ERR_SHAPE;

@@ -42,6 +42,60 @@ def test_argument_validation_needs_no_gpu():
         _lib.check(_lib.FLOWK_ERR_ARG, "x")
 
 
+def test_training_entry_points_validate_without_gpu():
+    """The training-path entry points (wgrad, weight norm, pointwise, attention, Adamax) reject bad shapes / null
+    pointers before any launch, and their planning queries are pure host functions."""
+    L = _lib.lib
+    one = ctypes.c_void_p(16)
+    tr = ctypes.c_int(-1)
+    # planning: level-1 3x3 layer splits K over CTAs; gy on the 128-lane side (not transposed); out_conv swaps sides
+    assert L.flowk_conv_wgrad_splits(64, 16, 16, 192, 96, 9, ctypes.byref(tr)) == 16 and tr.value == 0
+    assert L.flowk_conv_wgrad_splits(64, 16, 16, 96, 588, 9, ctypes.byref(tr)) >= 1 and tr.value == 1
+    assert L.flowk_conv_wgrad_splits(64, 4, 4, 192, 96, 9, ctypes.byref(tr)) == 0          # H*W < one k-block
+    assert L.flowk_conv_wgrad_splits(64, 16, 16, 192, 96, 4, None) == 0                    # taps must be 1 or 9
+    assert L.flowk_linear_wgrad_splits(16384, 96, 288, ctypes.byref(tr)) >= 1 and tr.value == 1
+    assert L.flowk_linear_wgrad_splits(16384, 100, 288, None) == 0                         # K % 32
+    assert L.flowk_conv_wgrad(one, None, None, one, one, None, 64, 16, 16, 192, 96, 9, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_conv_wgrad(one, one, one, one, one, None, 64, 4, 4, 192, 96, 9, None) == _lib.FLOWK_ERR_SHAPE
+    assert L.flowk_linear_wgrad(one, None, one, None, 16384, 96, 288, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_shift_columns(one, one, one, 100, 6, None) == _lib.FLOWK_ERR_SHAPE
+    assert L.flowk_weight_norm_operands(one, one, 0, 8, 9, 32, 32, one, None, None, None, None, None, None) == _lib.FLOWK_ERR_SHAPE
+    assert L.flowk_weight_norm_operands(one, None, 8, 8, 9, 32, 32, one, None, None, None, None, None, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_weight_norm_operands_batched(None, 3, 8, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_weight_norm_operands_batched(None, 0, 8, None) == _lib.FLOWK_OK
+    assert L.flowk_weight_norm_bwd_partials(one, one, one, None, one, one, 8, 8, 9, 2, 0, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_concat_elu_fwd(None, None, 0, 4, 1, None) == _lib.FLOWK_OK              # empty batch
+    assert L.flowk_concat_elu_fwd(one, one, 2, 0, 1, None) == _lib.FLOWK_ERR_SHAPE
+    assert L.flowk_glu_bwd(one, None, one, 2, 4, 1, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_add_layernorm_fwd(one, one, one, one, one, one, one, one, 48, 96, 32, 1, 0, 1e-5, None) == _lib.FLOWK_ERR_SHAPE
+    assert L.flowk_add_layernorm_fwd(one, one, None, one, one, one, one, one, 64, 96, 32, 1, 0, 1e-5, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_add_layernorm_workspace_bytes(16384, 96) == 512 * 2 * 96 * 4
+    assert L.flowk_channel_sum(one, one, None, 4, 8, 16, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_channel_sum_workspace_bytes(96) == 64 * 96 * 4
+    assert L.flowk_attention_train_fwd(one, one, one, None, 1, 0.2, 2, 12, 96, 4, None) == _lib.FLOWK_ERR_SHAPE    # HW % 8
+    assert L.flowk_attention_train_fwd(one, one, one, None, 1, 1.0, 2, 16, 96, 4, None) == _lib.FLOWK_ERR_SHAPE    # p < 1
+    assert L.flowk_attention_train_fwd(one, None, one, None, 1, 0.2, 2, 16, 96, 4, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_attention_train_bwd(one, one, one, one, None, one, None, 1, 0.2, 2, 16, 96, 4, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_attention_dropout_mask(None, 1, 0.2, 0, 16, one, None) == _lib.FLOWK_ERR_SHAPE
+    assert L.flowk_adamax_step(None, 0, None, 0.9, 0.999, 1e-8, None) == _lib.FLOWK_OK
+    assert L.flowk_adamax_step(None, 4, one, 0.9, 0.999, 1e-8, None) == _lib.FLOWK_ERR_ARG
+    # split-K planning of the conv GEMM: the level-3 out_conv input-gradient splits, a level-1 layer does not
+    def slices(B, H, W, Cin, N, taps, out_mask):
+        args = _lib.ConvGemmArgs(None, None, None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                 B, H, W, Cin, N, taps, _lib.PRE_BIAS, out_mask, None, None, None, 0, None)
+        return L.flowk_conv_gemm_splitk_slices(ctypes.addressof(args))
+    assert slices(64, 4, 4, 2368, 96, 9, _lib.OUT_NCHW) > 1
+    assert slices(64, 16, 16, 192, 96, 9, _lib.OUT_NCHW) == 1
+    assert slices(64, 4, 4, 2368, 96, 9, _lib.OUT_HILO) == 1                               # only plain fp32 destinations
+
+
+def test_structs_mirror_the_header():
+    """ctypes mirrors of the C structs have the layout the header declares (8-byte pointers, 4-byte ints)."""
+    assert ctypes.sizeof(_lib.WnJob) == 8 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.AdamaxChunk) == 4 * 8 + 8
+    assert ctypes.sizeof(_lib.ConvGemmArgs) == 15 * 8 + 8 * 4 + 3 * 8 + 8 + 8             # N2 is padded to 8 before splitk_ws
+
+
 def test_no_cpu_fallback():
     from flowk.flow_modules.common_modules import squeeze2d
     with pytest.raises((NotImplementedError, RuntimeError)):
