@@ -35,6 +35,7 @@ struct WgradParams {
   int rows;                       // 1: row-major operands [M, C] (Linear layers): MN-major tiles of [32 rows x 32 channels]
                                   //    blocks, 3-D TMA boxes (32 ch, 32 rows, blocks), transposed UMMA descriptors
   int g_tile_bytes;               // shared-memory bytes reserved for the A tile (its real rows, rounded to 8)
+  int kblk;                       // pixels per k-block: 32 (128-byte swizzle rows) or 16 (64-byte rows, H*W == 16 maps)
   int W;                          // image width: a row shift is W pixels
   int kb_per_image, total_kb;     // k-block = 32 consecutive pixels of one image
   int g_rows, x_rows;             // TMA box rows (<= 128, <= c_tile)
@@ -65,10 +66,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
   const int split = blockIdx.y, splits = gridDim.y;
   const int kb0 = (int)((long long)p.total_kb * split / splits), kb1 = (int)((long long)p.total_kb * (split + 1) / splits);
   const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
-  const int g_bytes = p.g_rows * 128, x_bytes = p.x_rows * 128;
+  const int row_bytes = p.kblk * 4;
+  const int g_bytes = p.g_rows * row_bytes, x_bytes = p.x_rows * row_bytes;
   const int x_off = p.g_tile_bytes;                      // the MMA reads 128 A rows: rows past the tile are garbage
                                                          // that only reaches accumulator rows nobody stores
-  const int lo_off = x_off + p.c_tile * 128;             // lo tiles mirror the raw ones
+  const int lo_off = x_off + p.c_tile * row_bytes;       // lo tiles mirror the raw ones
 
   if (threadIdx.x == 0) {
     failed_flag = 0;
@@ -94,7 +96,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb) {
         const int i = kb - kb0, s = i % p.stages;
         if (i >= p.stages) mbar_wait(&empty_bar[s], ((uint32_t)(i / p.stages) - 1u) & 1u, failed);
-        const int b = kb / p.kb_per_image, p0 = (kb - b * p.kb_per_image) * BLOCK_K;
+        const int b = kb / p.kb_per_image, p0 = (kb - b * p.kb_per_image) * p.kblk;
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
         mbar_expect_tx(&full_raw[s], (uint32_t)(g_bytes + x_bytes));
         const CUtensorMap* mx = dx < 0 ? &map_xm : dx > 0 ? &map_xp : &map_x;
@@ -124,12 +126,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         if (p.rows) {
           dg_hi = make_smem_desc_mn(base, 4096), dx_hi = make_smem_desc_mn(base + x_off, 4096);
           dg_lo = make_smem_desc_mn(base + lo_off, 4096), dx_lo = make_smem_desc_mn(base + lo_off + x_off, 4096);
+        } else if (p.kblk == 16) {
+          dg_hi = make_smem_desc_sw64(base), dx_hi = make_smem_desc_sw64(base + x_off);
+          dg_lo = make_smem_desc_sw64(base + lo_off), dx_lo = make_smem_desc_sw64(base + lo_off + x_off);
         } else {
           dg_hi = make_smem_desc(base), dx_hi = make_smem_desc(base + x_off);
           dg_lo = make_smem_desc(base + lo_off), dx_lo = make_smem_desc(base + lo_off + x_off);
         }
-#pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+        const int ksteps = p.kblk / UMMA_K;
+#pragma unroll 4
+        for (int k = 0; k < ksteps; ++k) {
           // K-major: 32 bytes further inside the 128-byte row; MN-major: 8 rows = 1024 bytes further
           const uint64_t ko = p.rows ? (uint64_t)(k * 1024 >> 4) : (uint64_t)(k * UMMA_K * 4 >> 4);
           if ((i | k) == 0) umma_tf32(tmem_base, dg_hi + ko, dx_hi + ko, idesc, 0u);
@@ -203,18 +209,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
 }
 
 // channel-major operand [B, C, H*W] viewed by TMA as dims (H*W, C, B, 1); box (32 pixels, rows, 1, 1)
-static bool make_map_cm(CUtensorMap* map, const float* base, int B, int C, int HW, int rows) {
+static bool make_map_cm(CUtensorMap* map, const float* base, int B, int C, int HW, int rows, int kblk = BLOCK_K) {
   cuuint64_t dims[4] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B, 1};
   cuuint64_t strides[3] = {(cuuint64_t)HW * 4, (cuuint64_t)C * HW * 4, (cuuint64_t)B * C * HW * 4};
-  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)rows, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return encode_fn() && encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box,
-                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    kblk == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct WgradPlan {
   bool ok;
+  int kblk;                      // pixels per k-block (32, or 16 for 4x4 maps)
   int swap;                      // 1: A side = x (Cin rows), B side = gy (N columns): partial[s][t][c][n]
   int a_ch, b_ch, g_tile_bytes;
   int c_tile, c_tiles, m_tiles, splits, stages, stage_bytes, tmem_cols;
@@ -222,7 +230,9 @@ struct WgradPlan {
 
 static WgradPlan plan_wgrad(int B, int H, int W, int Cin, int N, int taps) {
   WgradPlan pl = {};
-  if (B < 1 || H < 1 || W < 4 || W % 4 || (H * W) % BLOCK_K || Cin < 1 || N < 1 || (taps != 1 && taps != 9)) return pl;
+  if (B < 1 || H < 1 || W < 4 || W % 4 || (H * W) % 16 || Cin < 1 || N < 1 || (taps != 1 && taps != 9)) return pl;
+  pl.kblk = (H * W) % BLOCK_K ? 16 : BLOCK_K;
+  const int row_bytes = pl.kblk * 4;
   // a K=8 MMA costs about the same whatever its N <= 256 (measured): put the side that fills 128-row tiles with the
   // fewest MMAs on the A side
   auto tiles_of = [](int a, int b) { return ((a + BLOCK_M - 1) / BLOCK_M) * ((b + 255) / 256); };
@@ -233,15 +243,15 @@ static WgradPlan plan_wgrad(int B, int H, int W, int Cin, int N, int taps) {
   pl.c_tile = ((pl.b_ch + pl.c_tiles - 1) / pl.c_tiles + 15) / 16 * 16;
   pl.m_tiles = (pl.a_ch + BLOCK_M - 1) / BLOCK_M;
   const int a_rows = pl.a_ch < BLOCK_M ? (pl.a_ch + 7) / 8 * 8 : BLOCK_M;
-  pl.g_tile_bytes = a_rows * 128;
-  pl.stage_bytes = 2 * (pl.g_tile_bytes + pl.c_tile * 128);
+  pl.g_tile_bytes = a_rows * row_bytes;
+  pl.stage_bytes = 2 * (pl.g_tile_bytes + pl.c_tile * row_bytes);
   // the MMA always reads 128 A rows: keep (128 rows - tile) bytes of slack after the last stage inside the allocation
-  pl.stages = (225 * 1024 - (BLOCK_M * 128 - pl.g_tile_bytes)) / pl.stage_bytes;
+  pl.stages = (225 * 1024 - (BLOCK_M * row_bytes - pl.g_tile_bytes)) / pl.stage_bytes;
   if (pl.stages > WG_MAX_STAGES) pl.stages = WG_MAX_STAGES;
   if (pl.stages < 2) return pl;
   pl.tmem_cols = 32;
   while (pl.tmem_cols < pl.c_tile) pl.tmem_cols <<= 1;
-  const long long total_kb = (long long)B * H * W / 32;
+  const long long total_kb = (long long)B * H * W / pl.kblk;
   const int tiles = pl.m_tiles * taps * pl.c_tiles;
   long long s = (148 + tiles / 2) / tiles;
   if (s > total_kb / 4) s = total_kb / 4;
@@ -342,6 +352,7 @@ extern "C" int flowk_linear_wgrad(const float* x, const float* gy, float* partia
   p.Cin = pl.b_ch;
   p.shift_a = pl.swap;
   p.rows = 1;
+  p.kblk = BLOCK_K;
   p.g_tile_bytes = pl.g_tile_bytes;
   p.taps = 1;
   p.W = 32;
@@ -393,7 +404,8 @@ extern "C" int flowk_conv_wgrad(const float* x, const float* x_left, const float
   p.g_tile_bytes = pl.g_tile_bytes;
   p.taps = taps;
   p.W = W;
-  p.kb_per_image = H * W / 32;
+  p.kblk = pl.kblk;
+  p.kb_per_image = H * W / pl.kblk;
   p.total_kb = B * p.kb_per_image;
   p.g_rows = pl.a_ch < BLOCK_M ? pl.a_ch : BLOCK_M;
   p.x_rows = pl.b_ch < pl.c_tile ? pl.b_ch : pl.c_tile;
@@ -407,10 +419,10 @@ extern "C" int flowk_conv_wgrad(const float* x, const float* x_left, const float
   p.status = status;
   CUtensorMap mg, mx, mxm, mxp;
   const int gy_rows = pl.swap ? p.x_rows : p.g_rows, xx_rows = pl.swap ? p.g_rows : p.x_rows;
-  if (!make_map_cm(&mg, gy, B, N, H * W, gy_rows) || !make_map_cm(&mx, x, B, Cin, H * W, xx_rows) ||
-      !make_map_cm(&mxm, x_left, B, Cin, H * W, xx_rows) || !make_map_cm(&mxp, x_right, B, Cin, H * W, xx_rows))
+  if (!make_map_cm(&mg, gy, B, N, H * W, gy_rows, pl.kblk) || !make_map_cm(&mx, x, B, Cin, H * W, xx_rows, pl.kblk) ||
+      !make_map_cm(&mxm, x_left, B, Cin, H * W, xx_rows, pl.kblk) || !make_map_cm(&mxp, x_right, B, Cin, H * W, xx_rows, pl.kblk))
     return FLOWK_ERR_ARG;
-  const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + (BLOCK_M * 128 - pl.g_tile_bytes);
+  const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + (BLOCK_M * pl.kblk * 4 - pl.g_tile_bytes);
   if (smem > g_wgrad_smem_attr) {
     FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_wgrad_smem_attr = smem;

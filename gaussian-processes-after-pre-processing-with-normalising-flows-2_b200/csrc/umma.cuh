@@ -135,6 +135,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
   return d;
 }
+// K-major, 64-byte swizzle (rows of 16 fp32): 8-row groups of 512 B.  Used when a k-block can only be 16 elements long
+// (weight gradients of 4x4 feature maps: 16 pixels per image).
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                       // SWIZZLE_64B
+  return d;
+}
 // MN-major tf32 operand (the contraction index is the ROW of the tile, 32 channels = 128 B are contiguous): tiles of
 // [32 rows x 128 B] per 32-channel block, loaded by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and described with the
 // matching UMMA layout type 1 (SWIZZLE_128B_BASE32B): LBO = bytes between channel blocks, SBO = 512 B between groups of

@@ -51,12 +51,13 @@ def test_training_entry_points_validate_without_gpu():
     # planning: level-1 3x3 layer splits K over CTAs; gy on the 128-lane side (not transposed); out_conv swaps sides
     assert L.flowk_conv_wgrad_splits(64, 16, 16, 192, 96, 9, ctypes.byref(tr)) == 16 and tr.value == 0
     assert L.flowk_conv_wgrad_splits(64, 16, 16, 96, 588, 9, ctypes.byref(tr)) >= 1 and tr.value == 1
-    assert L.flowk_conv_wgrad_splits(64, 4, 4, 192, 96, 9, ctypes.byref(tr)) == 0          # H*W < one k-block
+    assert L.flowk_conv_wgrad_splits(64, 4, 4, 192, 96, 9, ctypes.byref(tr)) >= 1          # 4x4 maps: 16-pixel k-blocks
+    assert L.flowk_conv_wgrad_splits(64, 2, 4, 192, 96, 9, ctypes.byref(tr)) == 0          # H*W % 16
     assert L.flowk_conv_wgrad_splits(64, 16, 16, 192, 96, 4, None) == 0                    # taps must be 1 or 9
     assert L.flowk_linear_wgrad_splits(16384, 96, 288, ctypes.byref(tr)) >= 1 and tr.value == 1
     assert L.flowk_linear_wgrad_splits(16384, 100, 288, None) == 0                         # K % 32
     assert L.flowk_conv_wgrad(one, None, None, one, one, None, 64, 16, 16, 192, 96, 9, None) == _lib.FLOWK_ERR_ARG
-    assert L.flowk_conv_wgrad(one, one, one, one, one, None, 64, 4, 4, 192, 96, 9, None) == _lib.FLOWK_ERR_SHAPE
+    assert L.flowk_conv_wgrad(one, one, one, one, one, None, 64, 2, 4, 192, 96, 9, None) == _lib.FLOWK_ERR_SHAPE
     assert L.flowk_linear_wgrad(one, None, one, None, 16384, 96, 288, None) == _lib.FLOWK_ERR_ARG
     assert L.flowk_shift_columns(one, one, one, 100, 6, None) == _lib.FLOWK_ERR_SHAPE
     assert L.flowk_weight_norm_operands(one, one, 0, 8, 9, 32, 32, one, None, None, None, None, None, None) == _lib.FLOWK_ERR_SHAPE

@@ -389,7 +389,8 @@ def test_add_layernorm_matches_torch_autograd(in_nchw, out_nchw):
 
 
 @pytest.mark.parametrize("b,cin,n,k,h,w", [(2, 32, 32, 1, 8, 16), (4, 24, 40, 3, 16, 16), (8, 192, 96, 3, 8, 8),
-                                           (3, 96, 588, 3, 8, 8), (2, 320, 160, 3, 8, 8), (1, 96, 288, 1, 64, 32)])
+                                           (3, 96, 588, 3, 8, 8), (2, 320, 160, 3, 8, 8), (1, 96, 288, 1, 64, 32),
+                                           (64, 192, 96, 3, 4, 4), (6, 96, 2352, 3, 4, 4), (8, 192, 192, 1, 4, 4)])
 def test_conv_wgrad_tcgen05_matches_fp64(b, cin, n, k, h, w):
     from flowk import tc_autograd
     dev = torch.device("cuda:0")
