@@ -403,10 +403,21 @@ def run_flowk(args):
             _, n, us, (gb, gh, gw, cin, nn, taps, pre) = top
             flops = 2.0 * gb * gh * gw * nn * taps * cin
             ach = flops / (us * 1e-6) / 1e12
+            gemm_traffic = None            # dram bytes of this launch from the committed ncu --set full capture
+            prof = os.path.join(ROOT, "profiles", "r1_conv_gemm_ncu_summary.json")
+            if os.path.exists(prof) and (gb, gh, gw, cin, nn, taps, pre) == (64, 16, 16, 192, 96, 9, 0):
+                try:
+                    with open(prof) as f:
+                        first = json.load(f)["launches"][0]
+                    unit = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+                    gemm_traffic = sum(float(first[k].split()[0]) * unit[first[k].split()[1]]
+                                       for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                except (KeyError, ValueError, IndexError):
+                    gemm_traffic = None
             roofline = {
                 "bound": "tensor", "kernel": "flowk_conv_gemm %s Cin=%d N=%d @%dx%d B=%d" % (
                     "3x3" if taps == 9 else "1x1", cin, nn, gh, gw, gb),
-                "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+                "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": gemm_traffic,
                 "flops_per_launch": flops, "us_per_launch": us, "launches_timed": n, "peak_source": tf_src,
                 "note": "algorithmic flops 2*M*N*K of the fp32 convolution; the kernel runs 3 TF32 tensor-core passes "
                         "(3xTF32 split for the 1e-4 fp32 parity budget) at half the bf16 rate, i.e. its own ceiling is "
