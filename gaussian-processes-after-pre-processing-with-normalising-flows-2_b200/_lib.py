@@ -64,7 +64,7 @@ SIGNATURES = {
     "flowk_weight_norm_bwd_partials": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _st], _i),
     "flowk_conv_gemm_splitk_slices": ([_fp], _i),
     "flowk_attention_train_fwd": ([_fp, _fp, _fp, _fp, ctypes.c_uint, ctypes.c_float, _i, _i, _i, _i, _st], _i),
-    "flowk_attention_train_bwd": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, ctypes.c_uint, ctypes.c_float, _i, _i, _i, _i, _st], _i),
+    "flowk_attention_train_bwd": ([_i, _fp, _fp, _fp, _fp, _fp, _fp, ctypes.c_uint, ctypes.c_float, _i, _i, _i, _i, _st], _i),
     "flowk_attention_dropout_mask": ([_fp, ctypes.c_uint, ctypes.c_float, _i, _i, _fp, _st], _i),
     "flowk_adamax_step": ([_fp, _i, _fp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _st], _i),
     "flowk_glu_bwd": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),

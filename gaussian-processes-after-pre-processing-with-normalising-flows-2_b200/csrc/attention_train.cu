@@ -5,7 +5,8 @@
 //     dV = Pd^T dO;  dPd = dO V^T;  delta_i = dO_i . O_i;  dS = P * (dPd * M - delta_i);  dQ = dS K / sqrt(d);  dK = dS^T q'
 // Nothing of size seq x seq touches HBM: the forward stores the row log-sum-exp, the backward recomputes S = q' K^T
 // and regenerates the dropout mask from a counter-based hash of (seed, image*head, query, key).  Two backward kernels,
-// no atomics: one owns 16 queries per warp (dQ, also writes delta), one owns 16 keys per warp (dK, dV) -> deterministic.
+// no atomics: one owns 16 queries per warp (dQ), one owns 16 keys per warp (dK, dV) -> deterministic; they share no
+// intermediate (each computes delta itself), so they may run concurrently on two streams.
 // Rows of qkv [M, 3C] are (k | v | q) (:136-139); dqkv has the same layout.
 #include "common.cuh"
 
@@ -154,12 +155,12 @@ __global__ void __launch_bounds__(256) fwd_kernel(const float* __restrict__ qkv,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward, query side: delta_i = dO_i . O_i (written for the key-side kernel), dQ = scale * dS K.  a warp = 16 queries
+// backward, query side: delta_i = dO_i . O_i, dQ = scale * dS K.  a warp = 16 queries
 // ---------------------------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(256) bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
                                                      const float* __restrict__ dout, const float* __restrict__ lse,
-                                                     float* __restrict__ delta, float* __restrict__ dqkv,
+                                                     float* __restrict__ dqkv,
                                                      const unsigned* __restrict__ seed_dev, unsigned salt, uint32_t thresh,
                                                      float inv_keep, int S, int C, int heads, float scale) {
   extern __shared__ __align__(16) uint32_t smem_u[];
@@ -193,10 +194,6 @@ __global__ void __launch_bounds__(256) bwd_dq_kernel(const float* __restrict__ q
     }
     d_lo += __shfl_xor_sync(0xffffffffu, d_lo, 1); d_lo += __shfl_xor_sync(0xffffffffu, d_lo, 2);
     d_hi += __shfl_xor_sync(0xffffffffu, d_hi, 1); d_hi += __shfl_xor_sync(0xffffffffu, d_hi, 2);
-    if (t == 0) {
-      if (ok_lo) delta[(size_t)pair * S + q0 + g] = d_lo;
-      if (ok_hi) delta[(size_t)pair * S + q0 + g + 8] = d_hi;
-    }
   }
   const float L_lo = ok_lo ? __ldg(lse + (size_t)pair * S + r_lo) : 0.f, L_hi = ok_hi ? __ldg(lse + (size_t)pair * S + r_hi) : 0.f;
   float dq[KS][4];
@@ -238,11 +235,12 @@ __global__ void __launch_bounds__(256) bwd_dq_kernel(const float* __restrict__ q
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward, key side: dV = Pd^T dO, dK = dS^T q'.  a warp = 16 keys; queries (q', dO, lse, delta) stream through smem
+// backward, key side: dV = Pd^T dO, dK = dS^T q'.  a warp = 16 keys; queries (q', dO, lse, delta) stream through smem.
+// Independent of the query-side kernel (delta is recomputed here), so the two can run on different streams.
 // ---------------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256) bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
-                                                      const float* __restrict__ lse, const float* __restrict__ delta,
+__global__ void __launch_bounds__(256) bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ out,
+                                                      const float* __restrict__ dout, const float* __restrict__ lse,
                                                       float* __restrict__ dqkv, const unsigned* __restrict__ seed_dev,
                                                       unsigned salt, uint32_t thresh, float inv_keep, int S, int C, int heads,
                                                       float scale) {
@@ -273,9 +271,17 @@ __global__ void __launch_bounds__(256) bwd_dkv_kernel(const float* __restrict__ 
     __syncthreads();
     stage_rows<D>(Qh, Ql, base + (size_t)qt0 * row_stride + 2 * C, row_stride, q_here, q_here, scale);
     stage_rows<D>(Gh, Gl, dout + (size_t)(b * S + qt0) * C + h * D, (size_t)C, q_here, q_here, 1.f);
-    for (int i = threadIdx.x; i < q_here; i += blockDim.x) {
+    for (int i = threadIdx.x; i < q_here; i += blockDim.x) {          // row log-sum-exp and delta_i = dO_i . O_i
       Ls[i] = __ldg(lse + (size_t)pair * S + qt0 + i);
-      Ds[i] = __ldg(delta + (size_t)pair * S + qt0 + i);
+      const float4* po = reinterpret_cast<const float4*>(out + (size_t)(b * S + qt0 + i) * C + h * D);
+      const float4* pg = reinterpret_cast<const float4*>(dout + (size_t)(b * S + qt0 + i) * C + h * D);
+      float acc = 0.f;
+#pragma unroll
+      for (int v4 = 0; v4 < D / 4; ++v4) {
+        const float4 o4 = __ldg(po + v4), g4 = __ldg(pg + v4);
+        acc += o4.x * g4.x + o4.y * g4.y + o4.z * g4.z + o4.w * g4.w;
+      }
+      Ds[i] = acc;
     }
     __syncthreads();
     for (int q0 = 0; q0 < q_here; q0 += 8) {
@@ -365,16 +371,20 @@ static int run_fwd(const float* qkv, float* out, float* lse, const unsigned* see
   return launch_status();
 }
 template <int D>
-static int run_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* delta, float* dqkv,
+static int run_bwd(int which, const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv,
                    const unsigned* seed, unsigned salt, float p, int B, int S, int C, int heads, cudaStream_t st) {
   Launch l;
   if (!plan(B, S, C, heads, p, D, &l)) return FLOWK_ERR_SHAPE;
-  FLOWK_CUDA_OK(cudaFuncSetAttribute(bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
-  FLOWK_CUDA_OK(cudaFuncSetAttribute(bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
-  bwd_dq_kernel<D><<<l.grid, l.block, l.smem, st>>>(qkv, out, dout, lse, delta, dqkv, seed, salt, l.thresh, l.inv_keep, S, C,
-                                                    heads, l.scale);
-  bwd_dkv_kernel<D><<<l.grid, l.block, l.smem, st>>>(qkv, dout, lse, delta, dqkv, seed, salt, l.thresh, l.inv_keep, S, C, heads,
-                                                     l.scale);
+  if (which & 1) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
+    bwd_dq_kernel<D><<<l.grid, l.block, l.smem, st>>>(qkv, out, dout, lse, dqkv, seed, salt, l.thresh, l.inv_keep, S, C, heads,
+                                                      l.scale);
+  }
+  if (which & 2) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
+    bwd_dkv_kernel<D><<<l.grid, l.block, l.smem, st>>>(qkv, out, dout, lse, dqkv, seed, salt, l.thresh, l.inv_keep, S, C, heads,
+                                                       l.scale);
+  }
   return launch_status();
 }
 
@@ -399,18 +409,20 @@ extern "C" int flowk_attention_train_fwd(const float* qkv, float* out, float* ls
   }
 }
 
-extern "C" int flowk_attention_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse,
-                                         float* delta_ws, float* dqkv, const unsigned* seed_device, unsigned salt, float p_drop,
-                                         int B, int HW, int C, int heads, flowk_stream_t stream) {
+// which: 1 = query side (dq columns of dqkv), 2 = key side (dk, dv columns), 3 = both on `stream`
+extern "C" int flowk_attention_train_bwd(int which, const float* qkv, const float* out, const float* dout, const float* lse,
+                                         float* dqkv, const unsigned* seed_device, unsigned salt, float p_drop, int B, int HW,
+                                         int C, int heads, flowk_stream_t stream) {
   if (B == 0) return FLOWK_OK;
-  if (!qkv || !out || !dout || !lse || !delta_ws || !dqkv) return FLOWK_ERR_ARG;
+  if (which < 1 || which > 3) return FLOWK_ERR_ARG;
+  if (!qkv || !out || !dout || !lse || !dqkv) return FLOWK_ERR_ARG;
   if (heads < 1 || C % heads) return FLOWK_ERR_SHAPE;
   switch (C / heads) {
-    case 8: return run_bwd<8>(qkv, out, dout, lse, delta_ws, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
-    case 16: return run_bwd<16>(qkv, out, dout, lse, delta_ws, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
-    case 24: return run_bwd<24>(qkv, out, dout, lse, delta_ws, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
-    case 32: return run_bwd<32>(qkv, out, dout, lse, delta_ws, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
-    case 40: return run_bwd<40>(qkv, out, dout, lse, delta_ws, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
+    case 8: return run_bwd<8>(which, qkv, out, dout, lse, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
+    case 16: return run_bwd<16>(which, qkv, out, dout, lse, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
+    case 24: return run_bwd<24>(which, qkv, out, dout, lse, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
+    case 32: return run_bwd<32>(which, qkv, out, dout, lse, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
+    case 40: return run_bwd<40>(which, qkv, out, dout, lse, dqkv, seed_device, salt, p_drop, B, HW, C, heads, stream);
     default: return FLOWK_ERR_SHAPE;
   }
 }

@@ -564,6 +564,9 @@ def attention_train_supported(qkv, heads):
         b * heads * s * s < 2 ** 32 - 1
 
 
+# the two attention backward kernels are independent and may run on two streams; measured: no gain (62.2 vs 61-63 ms/step,
+# both already fill the GPU at level 1), so they stay on one stream unless FLOWK_ATTN_FORK=1
+ATTENTION_BWD_FORK = __import__("os").environ.get("FLOWK_ATTN_FORK", "0") == "1"
 ATTENTION_TC = True      # training attention core (softmax(q k^T) v with dropout, forward + backward) on the flowk kernels
 
 
@@ -590,10 +593,16 @@ class _AttentionCore(torch.autograd.Function):
         heads, p_drop, salt = ctx.cfg
         b, s, c3 = qkv.shape
         dqkv = torch.empty_like(qkv)
-        delta = torch.empty_like(lse)
+        dout = dout.contiguous()
         seed = dropout_seed(qkv.device)
-        _lib.call("flowk_attention_train_bwd", qkv.data_ptr(), out.data_ptr(), dout.contiguous().data_ptr(), lse.data_ptr(),
-                  delta.data_ptr(), dqkv.data_ptr(), seed.data_ptr(), salt, p_drop, b, s, c3 // 3, heads, tc._stream())
+        args = (qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), seed.data_ptr(), salt, p_drop,
+                b, s, c3 // 3, heads)
+        fork = _fork_wgrad(qkv.device)
+        fork.on = fork.on and ATTENTION_BWD_FORK
+        with fork:                                  # side stream: key side (dk, dv columns)
+            _lib.call("flowk_attention_train_bwd", 2, *args, tc._stream())
+        _lib.call("flowk_attention_train_bwd", 1, *args, tc._stream())       # main stream: query side (dq columns)
+        fork.join()
         return dqkv, None, None, None
 
 

@@ -264,14 +264,15 @@ int flowk_weight_norm_bwd_partials(const float* v, const float* g, const float* 
 
 /* Training-time attention core with attention-weight dropout (mixlogcdf_nn.py:134-147 with :143's F.dropout): forward and
  * backward.  qkv / dqkv rows [B*HW, 3C] in (k | v | q) order; out / dout rows [B*HW, C]; lse [B*heads, HW] (row
- * log-sum-exp, written by the forward); delta_ws [B*heads, HW] scratch.  The dropout mask is a counter-based hash of
+ * log-sum-exp, written by the forward).  The backward is two independent kernels selected by `which`: 1 = query side
+ * (writes the q columns of dqkv), 2 = key side (k and v columns), 3 = both; 1 and 2 may run on different streams.  The dropout mask is a counter-based hash of
  * (*seed_device, salt, image*head, query, key): the backward regenerates it, nothing of size HW x HW touches HBM.
  * seed_device: device scalar the caller advances once per training step (so a captured graph draws fresh masks on each
  * replay); salt: per-layer constant.  HW % 8 == 0, C / heads in {8, 16, 24, 32, 40}, B*heads*HW*HW < 2^32.
  * flowk_attention_dropout_mask materialises the multipliers (0 or 1/(1-p)) [B*heads, HW, HW] - for tests. */
 int flowk_attention_train_fwd(const float* qkv, float* out, float* lse, const unsigned* seed_device, unsigned salt,
                               float p_drop, int B, int HW, int C, int heads, flowk_stream_t stream);
-int flowk_attention_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* delta_ws,
+int flowk_attention_train_bwd(int which, const float* qkv, const float* out, const float* dout, const float* lse,
                               float* dqkv, const unsigned* seed_device, unsigned salt, float p_drop, int B, int HW, int C,
                               int heads, flowk_stream_t stream);
 int flowk_attention_dropout_mask(const unsigned* seed_device, unsigned salt, float p_drop, int pairs, int HW, float* mask,

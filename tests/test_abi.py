@@ -76,7 +76,8 @@ def test_training_entry_points_validate_without_gpu():
     assert L.flowk_attention_train_fwd(one, one, one, None, 1, 0.2, 2, 12, 96, 4, None) == _lib.FLOWK_ERR_SHAPE    # HW % 8
     assert L.flowk_attention_train_fwd(one, one, one, None, 1, 1.0, 2, 16, 96, 4, None) == _lib.FLOWK_ERR_SHAPE    # p < 1
     assert L.flowk_attention_train_fwd(one, None, one, None, 1, 0.2, 2, 16, 96, 4, None) == _lib.FLOWK_ERR_ARG
-    assert L.flowk_attention_train_bwd(one, one, one, one, None, one, None, 1, 0.2, 2, 16, 96, 4, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_attention_train_bwd(3, one, one, one, one, None, None, 1, 0.2, 2, 16, 96, 4, None) == _lib.FLOWK_ERR_ARG
+    assert L.flowk_attention_train_bwd(4, one, one, one, one, one, None, 1, 0.2, 2, 16, 96, 4, None) == _lib.FLOWK_ERR_ARG
     assert L.flowk_attention_dropout_mask(None, 1, 0.2, 0, 16, one, None) == _lib.FLOWK_ERR_SHAPE
     assert L.flowk_adamax_step(None, 0, None, 0.9, 0.999, 1e-8, None) == _lib.FLOWK_OK
     assert L.flowk_adamax_step(None, 4, one, 0.9, 0.999, 1e-8, None) == _lib.FLOWK_ERR_ARG
