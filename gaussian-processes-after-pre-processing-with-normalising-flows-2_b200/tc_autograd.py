@@ -1,13 +1,20 @@
-"""Differentiable convolution / linear layers on the tcgen05 GEMM kernel, for the TRAINING path of the conditioners.
+"""Training path of the MixLogCDF conditioner on libflowk: `autograd.Function`s whose forward AND backward are C-ABI calls.
 
-The training forward keeps torch's module graph (dropout, autograd), but its dense contractions - forward and
-input-gradient (dgrad) of every conv / Linear - run through `flowk_conv_gemm` (3xTF32, fp32-accurate) instead of
-cuDNN / cuBLAS fp32 SIMT kernels; the weight gradient stays a library call (`torch.nn.grad.conv2d_weight` / matmul).
+The training forward keeps torch's module graph (so dropout semantics, autograd and the reference's module tree stay), but
+every kernel between the flow-level ops is ours:
 
-    conv2d(x, w, b, padding)   x NCHW fp32  ->  NHWC (hi, lo) operand (one elementwise kernel)  ->  GEMM  ->  NCHW fp32
-    linear(x, w, b)            x [.., K] rows ->  (hi, lo) operand                               ->  GEMM  ->  rows
+    wn_conv2d / wn_linear    weight norm + operand construction (batched over the model: `WeightNormBatch`), forward GEMM,
+                             input-gradient GEMM (taps flipped, weight transposed), weight-gradient GEMM (tcgen05 split-K:
+                             `flowk_conv_wgrad` on NCHW operands, `flowk_linear_wgrad` on row-major MN-major operands),
+                             weight-norm backward fused with the split-K reduction, bias gradient
+    concat_elu / glu         one pass each way
+    add_layernorm            residual + LayerNorm + the block's NCHW<->NHWC permutes, forward / backward
+    attention_core           softmax(q k^T / sqrt d) with weight dropout times v: flash-style forward + two backward kernels,
+                             dropout mask regenerated from a counter-based hash (`advance_dropout_seed` once per step)
 
-dgrad of a 3x3 "same" conv is the same implicit GEMM on dL/dy with the taps flipped and the weight transposed.
+All of them are fp32-accurate (3xTF32 split on the tensor cores) and deterministic (no atomics).  `conv2d` / `linear`
+(without weight norm) are the plain building blocks, used by tests.  Unsupported shapes fall back to the torch layers in
+`flow_modules/` - never to a CPU path.
 """
 import ctypes
 
@@ -163,7 +170,7 @@ def _wn_operands(v, g, cin_pad, n_pad, want_w=False, want_dg=True):
 
 
 WGRAD_LINEAR_TC = True    # Linear weight gradients on the tcgen05 kernel, row-major operands as MN-major tiles
-WGRAD_TC = True      # weight gradients on the tcgen05 split-K kernel (else cuDNN / cuBLAS fp32)
+WGRAD_TC = True      # weight gradients on the tcgen05 split-K kernels (False: torch.nn.grad.conv2d_weight / matmul, for A/B tests)
 
 
 def wgrad_partials(x_cm, gy_cm, taps):
