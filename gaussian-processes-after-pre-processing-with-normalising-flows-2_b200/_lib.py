@@ -44,8 +44,8 @@ SIGNATURES = {
     "flowk_nchw_to_nhwc_hilo": ([_fp, ctypes.c_longlong, _i, _i, _i, _i, _fp, _fp, _st], _i),
     "flowk_split_hilo": ([_fp, _fp, _fp, ctypes.c_longlong, _st], _i),
     "flowk_attention": ([_fp, _fp, _fp, _i, _i, _i, _i, _st], _i),
-    "flowk_concat_elu_fwd": ([_fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
-    "flowk_concat_elu_bwd": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
+    "flowk_concat_elu_fwd": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
+    "flowk_concat_elu_bwd": ([_fp, _fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
     "flowk_glu_fwd": ([_fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
     "flowk_weight_norm_operands": ([_fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _st], _i),
     "flowk_weight_norm_operands_batched": ([_fp, _i, _i, _st], _i),

@@ -12,37 +12,55 @@ __device__ __forceinline__ float elu_grad(float x) { return x > 0.f ? 1.f : expf
 
 // Index type I: unsigned when the tensor has < 2^31 elements (one 32-bit division per VEC elements instead of a 64-bit
 // one per element - the division, not the memory system, bounded the first version); VEC = 4 when C*inner % 4 == 0.
+// `mask` (nullable, [outer, 2C]): feature dropout applied to the OUTPUT channels (nn.Dropout2d right after concat_elu in
+// GatedConv, mixlogcdf_nn.py:251-256): y[o, c', :] *= mask[o, c'].  With VEC = 4 the host guarantees inner % 4 == 0.
 template <typename I, int VEC>
-__global__ void concat_elu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, I total_v, I per_v) {
+__global__ void concat_elu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mask,
+                                      unsigned long long inner, I total_v, I per_v) {
+  const I inner_i = (I)inner, C = (I)(per_v * VEC / inner_i);
   for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total_v; i += (I)gridDim.x * blockDim.x) {
     const I o = i / per_v, r = i - o * per_v;
     const size_t src = (size_t)i * VEC, dst = ((size_t)o * 2 * per_v + r) * VEC, half = (size_t)per_v * VEC;
+    float m1 = 1.f, m2 = 1.f;
+    if (mask) {
+      const I c = (r * VEC) / inner_i;
+      m1 = mask[(size_t)o * 2 * C + c];
+      m2 = mask[(size_t)o * 2 * C + C + c];
+    }
     if (VEC == 4) {
       const float4 v = *reinterpret_cast<const float4*>(x + src);
-      *reinterpret_cast<float4*>(y + dst) = make_float4(elu_f(v.x), elu_f(v.y), elu_f(v.z), elu_f(v.w));
-      *reinterpret_cast<float4*>(y + dst + half) = make_float4(elu_f(-v.x), elu_f(-v.y), elu_f(-v.z), elu_f(-v.w));
+      *reinterpret_cast<float4*>(y + dst) = make_float4(m1 * elu_f(v.x), m1 * elu_f(v.y), m1 * elu_f(v.z), m1 * elu_f(v.w));
+      *reinterpret_cast<float4*>(y + dst + half) =
+          make_float4(m2 * elu_f(-v.x), m2 * elu_f(-v.y), m2 * elu_f(-v.z), m2 * elu_f(-v.w));
     } else {
       const float v = x[src];
-      y[dst] = elu_f(v);
-      y[dst + half] = elu_f(-v);
+      y[dst] = m1 * elu_f(v);
+      y[dst + half] = m2 * elu_f(-v);
     }
   }
 }
 template <typename I, int VEC>
 __global__ void concat_elu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
-                                      I total_v, I per_v) {
+                                      const float* __restrict__ mask, unsigned long long inner, I total_v, I per_v) {
+  const I inner_i = (I)inner, C = (I)(per_v * VEC / inner_i);
   for (I i = blockIdx.x * (I)blockDim.x + threadIdx.x; i < total_v; i += (I)gridDim.x * blockDim.x) {
     const I o = i / per_v, r = i - o * per_v;
     const size_t src = (size_t)i * VEC, dst = ((size_t)o * 2 * per_v + r) * VEC, half = (size_t)per_v * VEC;
+    float m1 = 1.f, m2 = 1.f;
+    if (mask) {
+      const I c = (r * VEC) / inner_i;
+      m1 = mask[(size_t)o * 2 * C + c];
+      m2 = mask[(size_t)o * 2 * C + C + c];
+    }
     if (VEC == 4) {
       const float4 v = *reinterpret_cast<const float4*>(x + src);
       const float4 g1 = *reinterpret_cast<const float4*>(gy + dst), g2 = *reinterpret_cast<const float4*>(gy + dst + half);
       *reinterpret_cast<float4*>(gx + src) =
-          make_float4(g1.x * elu_grad(v.x) - g2.x * elu_grad(-v.x), g1.y * elu_grad(v.y) - g2.y * elu_grad(-v.y),
-                      g1.z * elu_grad(v.z) - g2.z * elu_grad(-v.z), g1.w * elu_grad(v.w) - g2.w * elu_grad(-v.w));
+          make_float4(m1 * g1.x * elu_grad(v.x) - m2 * g2.x * elu_grad(-v.x), m1 * g1.y * elu_grad(v.y) - m2 * g2.y * elu_grad(-v.y),
+                      m1 * g1.z * elu_grad(v.z) - m2 * g2.z * elu_grad(-v.z), m1 * g1.w * elu_grad(v.w) - m2 * g2.w * elu_grad(-v.w));
     } else {
       const float v = x[src];
-      gx[src] = gy[dst] * elu_grad(v) - gy[dst + half] * elu_grad(-v);
+      gx[src] = m1 * gy[dst] * elu_grad(v) - m2 * gy[dst + half] * elu_grad(-v);
     }
   }
 }
@@ -113,14 +131,17 @@ using namespace flowk;
   }                                                                                                                     \
   return launch_status();
 
-extern "C" int flowk_concat_elu_fwd(const float* x, float* y, long long outer, int C, long long inner, flowk_stream_t stream) {
-  if (outer > 0 && (!x || !y)) return FLOWK_ERR_ARG;
-  FLOWK_POINTWISE_ENTRY(concat_elu_fwd_kernel, aligned16(x) && aligned16(y), x, y)
-}
-extern "C" int flowk_concat_elu_bwd(const float* x, const float* gy, float* gx, long long outer, int C, long long inner,
+extern "C" int flowk_concat_elu_fwd(const float* x, float* y, const float* mask, long long outer, int C, long long inner,
                                     flowk_stream_t stream) {
+  if (outer > 0 && (!x || !y)) return FLOWK_ERR_ARG;
+  FLOWK_POINTWISE_ENTRY(concat_elu_fwd_kernel, aligned16(x) && aligned16(y) && (!mask || inner % 4 == 0), x, y, mask,
+                        (unsigned long long)inner)
+}
+extern "C" int flowk_concat_elu_bwd(const float* x, const float* gy, float* gx, const float* mask, long long outer, int C,
+                                    long long inner, flowk_stream_t stream) {
   if (outer > 0 && (!x || !gy || !gx)) return FLOWK_ERR_ARG;
-  FLOWK_POINTWISE_ENTRY(concat_elu_bwd_kernel, aligned16(x) && aligned16(gy) && aligned16(gx), x, gy, gx)
+  FLOWK_POINTWISE_ENTRY(concat_elu_bwd_kernel, aligned16(x) && aligned16(gy) && aligned16(gx) && (!mask || inner % 4 == 0), x,
+                        gy, gx, mask, (unsigned long long)inner)
 }
 extern "C" int flowk_glu_fwd(const float* x, float* y, long long outer, int C, long long inner, flowk_stream_t stream) {
   if (outer > 0 && (!x || !y)) return FLOWK_ERR_ARG;

@@ -114,7 +114,15 @@ class GatedConv(nn.Module):
         x = self.conv(self.nlin(x))
         if aux is not None:
             x = x + self.aux_conv(self.nlin(aux))
-        x = self.gate(self.drop(self.nlin(x)))
+        from .. import tc_autograd
+        if tc_autograd.pointwise_ok(x) and torch.is_grad_enabled() and tc_autograd.FOLD_DROPOUT:
+            # concat_elu with the feature dropout that follows it folded in (one kernel each way)
+            mask = None
+            if self.training and self.drop.p > 0:
+                mask = tc_autograd.feature_dropout_mask(x, 2 * x.shape[1], self.drop.p)
+            x = self.gate(tc_autograd.concat_elu(x, 1, mask))
+        else:
+            x = self.gate(self.drop(self.nlin(x)))
         return _glu(x, 1)
 
 

@@ -458,25 +458,25 @@ def _oci(x, dim):
 
 class _ConcatElu(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, dim):
+    def forward(ctx, x, dim, mask):
         x = x.contiguous()
         outer, c, inner = _oci(x, dim)
         shape = list(x.shape)
         shape[dim] = 2 * c
         y = torch.empty(shape, device=x.device, dtype=torch.float32)
-        _lib.call("flowk_concat_elu_fwd", x.data_ptr(), y.data_ptr(), outer, c, inner, tc._stream())
-        ctx.save_for_backward(x)
+        _lib.call("flowk_concat_elu_fwd", x.data_ptr(), y.data_ptr(), tc._p(mask), outer, c, inner, tc._stream())
+        ctx.save_for_backward(x, mask)
         ctx.dim = dim
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        (x,) = ctx.saved_tensors
+        x, mask = ctx.saved_tensors
         outer, c, inner = _oci(x, ctx.dim)
         gx = torch.empty_like(x)
-        _lib.call("flowk_concat_elu_bwd", x.data_ptr(), gy.contiguous().data_ptr(), gx.data_ptr(), outer, c, inner,
+        _lib.call("flowk_concat_elu_bwd", x.data_ptr(), gy.contiguous().data_ptr(), gx.data_ptr(), tc._p(mask), outer, c, inner,
                   tc._stream())
-        return gx, None
+        return gx, None, None
 
 
 class _Glu(torch.autograd.Function):
@@ -574,6 +574,7 @@ def attention_train_supported(qkv, heads):
 # the two attention backward kernels are independent and may run on two streams; measured: no gain (62.2 vs 61-63 ms/step,
 # both already fill the GPU at level 1), so they stay on one stream unless FLOWK_ATTN_FORK=1
 ATTENTION_BWD_FORK = __import__("os").environ.get("FLOWK_ATTN_FORK", "0") == "1"
+FOLD_DROPOUT = __import__("os").environ.get("FLOWK_FOLD_DROPOUT", "1") != "0"   # Dropout2d folded into concat_elu
 ATTENTION_TC = True      # training attention core (softmax(q k^T) v with dropout, forward + backward) on the flowk kernels
 
 
@@ -629,8 +630,14 @@ def pointwise_ok(x):
     return ENABLED and x.is_cuda and x.dtype == torch.float32
 
 
-def concat_elu(x, dim=1):
-    return _ConcatElu.apply(x, dim)
+def concat_elu(x, dim=1, mask=None):
+    """elu(cat(x, -x)) along `dim`; `mask` [outer, 2C] (fp32, 0 or 1/(1-p)) folds the following feature dropout in."""
+    return _ConcatElu.apply(x, dim, mask)
+
+
+def feature_dropout_mask(x, channels, p):
+    """nn.Dropout2d's mask for a [B, channels, H, W] tensor as a [B, channels] multiplier (0 or 1/(1-p))."""
+    return torch.empty(x.shape[0], channels, device=x.device, dtype=torch.float32).bernoulli_(1.0 - p).div_(1.0 - p)
 
 
 def glu(x, dim):

@@ -184,11 +184,14 @@ int flowk_split_hilo(const float* x, float* hi, float* lo, long long n, flowk_st
 /* Fused pointwise layers of the Flow++ conditioner (training path), tensors viewed as [outer, channels, inner]
  * (inner = H*W for NCHW / dim 1, inner = 1 for NHWC / last dim):
  *   concat_elu: x [outer, C, inner] -> y [outer, 2C, inner] = elu(cat(x, -x))        mixlogcdf_nn.py:8-10
+ *               optional mask [outer, 2C]: per-(sample, output channel) multiplier = the nn.Dropout2d that follows
+ *               concat_elu in GatedConv (mixlogcdf_nn.py:251-256), folded in (0 or 1/(1-p); nullable)
  *   glu:        x [outer, 2C, inner] -> y [outer, C, inner] = x[:, :C] * sigmoid(x[:, C:])   mixlogcdf_nn.py:149-151,257-258
  * and their backward passes (gx from x and gy). */
-int flowk_concat_elu_fwd(const float* x, float* y, long long outer, int C, long long inner, flowk_stream_t stream);
-int flowk_concat_elu_bwd(const float* x, const float* gy, float* gx, long long outer, int C, long long inner,
+int flowk_concat_elu_fwd(const float* x, float* y, const float* mask, long long outer, int C, long long inner,
                          flowk_stream_t stream);
+int flowk_concat_elu_bwd(const float* x, const float* gy, float* gx, const float* mask, long long outer, int C,
+                         long long inner, flowk_stream_t stream);
 int flowk_glu_fwd(const float* x, float* y, long long outer, int C, long long inner, flowk_stream_t stream);
 int flowk_glu_bwd(const float* x, const float* gy, float* gx, long long outer, int C, long long inner,
                   flowk_stream_t stream);

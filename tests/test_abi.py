@@ -65,8 +65,8 @@ def test_training_entry_points_validate_without_gpu():
     assert L.flowk_weight_norm_operands_batched(None, 3, 8, None) == _lib.FLOWK_ERR_ARG
     assert L.flowk_weight_norm_operands_batched(None, 0, 8, None) == _lib.FLOWK_OK
     assert L.flowk_weight_norm_bwd_partials(one, one, one, None, one, one, 8, 8, 9, 2, 0, None) == _lib.FLOWK_ERR_ARG
-    assert L.flowk_concat_elu_fwd(None, None, 0, 4, 1, None) == _lib.FLOWK_OK              # empty batch
-    assert L.flowk_concat_elu_fwd(one, one, 2, 0, 1, None) == _lib.FLOWK_ERR_SHAPE
+    assert L.flowk_concat_elu_fwd(None, None, None, 0, 4, 1, None) == _lib.FLOWK_OK        # empty batch
+    assert L.flowk_concat_elu_fwd(one, one, None, 2, 0, 1, None) == _lib.FLOWK_ERR_SHAPE
     assert L.flowk_glu_bwd(one, None, one, 2, 4, 1, None) == _lib.FLOWK_ERR_ARG
     assert L.flowk_add_layernorm_fwd(one, one, one, one, one, one, one, one, 48, 96, 32, 1, 0, 1e-5, None) == _lib.FLOWK_ERR_SHAPE
     assert L.flowk_add_layernorm_fwd(one, one, None, one, one, one, one, one, 64, 96, 32, 1, 0, 1e-5, None) == _lib.FLOWK_ERR_ARG

@@ -302,11 +302,17 @@ def test_fused_pointwise_layers_match_torch_autograd():
     g = torch.Generator(device="cpu").manual_seed(9)
     for shape, dim in (((3, 8, 4, 5), 1), ((2, 4, 4, 12), -1), ((64, 96, 16, 16), 1)):
         x = torch.randn(shape, generator=g).to(dev).requires_grad_()
-        y = tc_autograd.concat_elu(x, dim)
+        mask = None
+        if dim == 1:                                    # feature dropout folded in (GatedConv's Dropout2d)
+            mask = tc_autograd.feature_dropout_mask(x, 2 * x.shape[1], 0.3)
+            assert all(v == 0.0 or abs(v - 1.0 / 0.7) < 1e-6 for v in mask.unique().tolist())
+        y = tc_autograd.concat_elu(x, dim, mask)
         gy = torch.randn(y.shape, generator=g).to(dev)
         y.backward(gy)
         x64 = x.detach().double().requires_grad_()
         y64 = F.elu(torch.cat((x64, -x64), dim=dim))
+        if mask is not None:
+            y64 = y64 * mask.double().view(mask.shape[0], mask.shape[1], 1, 1)
         y64.backward(gy.double())
         assert rel_err(y, y64.detach()) < 1e-6 and rel_err(x.grad, x64.grad) < 1e-6
         x2 = torch.randn(y.shape, generator=g).to(dev).requires_grad_()
