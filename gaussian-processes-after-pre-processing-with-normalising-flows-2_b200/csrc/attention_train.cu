@@ -271,17 +271,24 @@ __global__ void __launch_bounds__(256) bwd_dkv_kernel(const float* __restrict__ 
     __syncthreads();
     stage_rows<D>(Qh, Ql, base + (size_t)qt0 * row_stride + 2 * C, row_stride, q_here, q_here, scale);
     stage_rows<D>(Gh, Gl, dout + (size_t)(b * S + qt0) * C + h * D, (size_t)C, q_here, q_here, 1.f);
-    for (int i = threadIdx.x; i < q_here; i += blockDim.x) {          // row log-sum-exp and delta_i = dO_i . O_i
-      Ls[i] = __ldg(lse + (size_t)pair * S + qt0 + i);
-      const float4* po = reinterpret_cast<const float4*>(out + (size_t)(b * S + qt0 + i) * C + h * D);
-      const float4* pg = reinterpret_cast<const float4*>(dout + (size_t)(b * S + qt0 + i) * C + h * D);
+    for (int i = threadIdx.x; i < q_here; i += blockDim.x) Ls[i] = __ldg(lse + (size_t)pair * S + qt0 + i);
+    // delta_i = dO_i . O_i: eight lanes per row (D / 4 <= 10 float4 per row, so lanes 0..7 take one or two each), reduced
+    // with shuffles in a fixed order - coalesced row reads, deterministic
+    for (int i0 = 0; i0 < q_here * 8; i0 += blockDim.x) {
+      const int i = i0 + threadIdx.x, row = i >> 3, part = i & 7;
       float acc = 0.f;
-#pragma unroll
-      for (int v4 = 0; v4 < D / 4; ++v4) {
-        const float4 o4 = __ldg(po + v4), g4 = __ldg(pg + v4);
-        acc += o4.x * g4.x + o4.y * g4.y + o4.z * g4.z + o4.w * g4.w;
+      if (row < q_here) {
+        const float4* po = reinterpret_cast<const float4*>(out + (size_t)(b * S + qt0 + row) * C + h * D);
+        const float4* pg = reinterpret_cast<const float4*>(dout + (size_t)(b * S + qt0 + row) * C + h * D);
+        for (int v4 = part; v4 < D / 4; v4 += 8) {
+          const float4 o4 = __ldg(po + v4), g4 = __ldg(pg + v4);
+          acc += o4.x * g4.x + o4.y * g4.y + o4.z * g4.z + o4.w * g4.w;
+        }
       }
-      Ds[i] = acc;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (part == 0 && row < q_here) Ds[row] = acc;
     }
     __syncthreads();
     for (int q0 = 0; q0 < q_here; q0 += 8) {
