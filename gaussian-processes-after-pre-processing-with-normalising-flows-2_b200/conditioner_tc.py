@@ -14,7 +14,7 @@ re-laid-out, hi/lo-split weights are cached per parameter version.
 """
 import torch
 
-from . import _lib, tc
+from . import tc
 
 ENABLED = True      # set False to force the torch/cuDNN conditioner (used by tests to A/B the two paths)
 CHAIN = False       # gate -> in_proj fused into one launch (works, tested; measured no faster than two PDL launches: the
