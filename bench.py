@@ -19,7 +19,6 @@ batch 64 per GPU (BASELINE.json configs[1]).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
-import math
 import os
 import sys
 import threading

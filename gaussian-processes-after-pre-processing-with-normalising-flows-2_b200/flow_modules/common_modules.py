@@ -8,8 +8,6 @@ Differences a caller can observe:
     the CPU, common_modules.py:108-110) and caches W / W^-1 per parameter version in no-grad mode;
   * Actnormlayer's "is it initialised yet" test syncs with the host only until it has been seen true.
 """
-import math
-
 import numpy as np
 import scipy.linalg
 import torch

@@ -20,7 +20,6 @@ Every arithmetic module (Actnormlayer, InvertibleConv1x1, AffineCoupling, MixLog
 SqueezeLayer, Split2dMsC, TupleFlip, log_dist.*) is the reference's code, unmodified.
 """
 import json
-import math
 import os
 import sys
 import warnings

@@ -6,7 +6,7 @@ import os
 import pytest
 import torch
 
-import flowk
+import flowk  # noqa: F401  (registers the package alias)
 from flowk import driver
 
 

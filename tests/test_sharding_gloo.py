@@ -3,7 +3,6 @@ process on the full batch, replicas stay bit-identical, bits/dim mean reduces co
 import os
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -4,7 +4,7 @@ in the `gpu` variant."""
 import pytest
 import torch
 
-import flowk
+import flowk  # noqa: F401  (registers the package alias)
 from flowk.flow_modules.transformer import Transformer_attn
 from oracle import flow_oracle as O
 
