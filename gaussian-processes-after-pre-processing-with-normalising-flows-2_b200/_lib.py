@@ -130,6 +130,31 @@ def _load():
 
 
 lib = _load()
+
+# Weights generation: raw-pointer writers (the fused Adamax kernel, CUDA-graph replays of an update, `.data` copies in
+# broadcasts and the ActNorm init) change parameters WITHOUT touching torch's per-tensor version counter, so every
+# derived-weight cache in the package keys on (GENERATION, data_ptr, _version) and those writers bump GENERATION.
+GENERATION = 0
+
+
+def bump_generation():
+    global GENERATION
+    GENERATION += 1
+
+
+def check_device(t, what="flowk"):
+    """Kernels are enqueued on the CURRENT device's current stream: a tensor that lives on another GPU would be
+    touched from the wrong context.  Fail loudly instead (use torch.cuda.set_device / `with torch.cuda.device(...)`)."""
+    import torch
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError("%s: tensor lives on %s but the current CUDA device is cuda:%d; select the tensor's device "
+                           "first (torch.cuda.set_device or `with torch.cuda.device(t.device)`)"
+                           % (what, t.device, torch.cuda.current_device()))
+
+
+def param_key(params):
+    return (GENERATION,) + tuple((p.data_ptr(), p._version) for p in params)
+
 LAUNCHES = 0          # number of kernel-launching C-ABI calls made by this process
 TIMING = None         # set to a dict to record a CUDA-event pair around every call: name -> [(start, end, int args)]
 

@@ -14,7 +14,7 @@ re-laid-out, hi/lo-split weights are cached per parameter version.
 """
 import torch
 
-from . import tc
+from . import _lib, tc
 
 ENABLED = True      # set False to force the torch/cuDNN conditioner (used by tests to A/B the two paths)
 CHAIN = False       # gate -> in_proj fused into one launch (works, tested; measured no faster than two PDL launches: the
@@ -40,7 +40,7 @@ class _Cache:
         self.value = None
 
     def get(self, params, build):
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = _lib.param_key(params)
         if key != self.key:
             with torch.no_grad():
                 self.value = build()

@@ -17,13 +17,17 @@ def _images(item):
     return item[0] if isinstance(item, (tuple, list)) else item
 
 
-def test_model(model, test_loader, device=None):
+def test_model(model, test_loader, device=None, reference_mode=False):
     """Mean bits/dim over the loader (marscf_main.py:233-246); every rank evaluates its shard of each batch and the
-    (sum, count) pair is all-reduced once at the end."""
+    (sum, count) pair is all-reduced once at the end.
+
+    The reference never calls `.eval()`: its test NLL is computed with the conditioner dropout ACTIVE (train mode under
+    no_grad).  `reference_mode=True` reproduces that; the default evaluates in eval mode (deterministic, and it lets
+    the tcgen05 inference conditioner run) - a documented deviation."""
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
     total = None
     was_training = model.training
-    model.eval()
+    model.train(bool(reference_mode))
     with torch.no_grad():
         for item in test_loader:
             x = _images(item)
@@ -88,6 +92,13 @@ def fit(model, train_loader, test_loader, epochs, checkpoint_path=None, lr=1e-4,
             if device is not None:
                 x = x.to(device, non_blocking=True)
             if trainer is None:
+                # Replica sync before the first step: run the ActNorm data-dependent init (first TRAINING forward,
+                # common_modules.py:141-151) on this rank's shard, then copy rank 0's parameters and buffers to every
+                # rank - the initial weights (InvConv draws from each process's numpy RNG) and the init statistics
+                # (the reference's DataParallel keeps replica 0's, marscf_main.py:326).
+                with torch.no_grad():
+                    model(sharding.shard_batch(x, rank, world), reverse=False)
+                sharding.broadcast_module(model)
                 trainer = sharding.ShardedTrainer(model, lr=lr, warm_up=warm_up, global_batch=x.shape[0],
                                                   use_graph=use_graph)
             last = float(trainer.step(sharding.shard_batch(x, rank, world)))

@@ -13,7 +13,7 @@ import scipy.linalg
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import _lib, ops
 from .misc import cpd_sum
 
 
@@ -80,6 +80,7 @@ class Actnormlayer(nn.Module):
             self.bias.data.copy_(bias.view_as(self.bias))
             self.logs.data.copy_(logs.view_as(self.logs))
             self.is_initialized += 1.
+        _lib.bump_generation()        # `.data` writes skip the version counter
 
     def maybe_initialize(self, x):
         """The reference tests `if not self.is_initialized` every call (a host sync); here the
@@ -157,7 +158,7 @@ class InvertibleConv1x1(nn.Module):
         track = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if track:
             return self._build(reverse)
-        key = (bool(reverse),) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (bool(reverse),) + _lib.param_key(params)
         hit = self._cache.get(bool(reverse))
         if hit is None or hit[0] != key:
             with torch.no_grad():

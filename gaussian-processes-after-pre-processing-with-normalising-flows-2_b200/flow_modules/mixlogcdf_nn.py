@@ -13,6 +13,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import _lib
+
 
 def concat_elu(x, dim=1):
     from .. import tc_autograd
@@ -48,7 +50,7 @@ class _WeightNormed(nn.Module):
         v, g = self.weight_v, self.weight_g
         track = torch.is_grad_enabled() and (v.requires_grad or g.requires_grad)
         if not track:
-            key = (v.data_ptr(), v._version, g.data_ptr(), g._version)
+            key = _lib.param_key((v, g))
             if self._cache is not None and self._cache[0] == key:
                 return self._cache[1]
         norm = v.reshape(v.shape[0], -1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
@@ -129,8 +131,6 @@ class GatedConv(nn.Module):
 class GatedAttn(nn.Module):
     """Gated multi-head self-attention over the H*W positions of an NHWC tensor (mixlogcdf_nn.py:105-224)."""
 
-    _instances = 0
-
     def __init__(self, d_model, num_heads=4, drop_prob=0.):
         super().__init__()
         self.d_model = d_model
@@ -139,8 +139,8 @@ class GatedAttn(nn.Module):
         self.in_proj = _WNLinear(d_model, 3 * d_model, bias=False)
         self.gate = _WNLinear(d_model, 2 * d_model)
         self._pos = {}
-        GatedAttn._instances += 1
-        self._salt = GatedAttn._instances          # keys this layer's dropout masks (flowk training attention kernels)
+        self._salt = 1                             # keys this layer's dropout masks (flowk training attention kernels):
+                                                   # its index inside the owning NN / model (see assign_dropout_salts)
 
     @staticmethod
     def get_pos_enc(seq_len, num_channels, device):
@@ -177,6 +177,13 @@ class GatedAttn(nn.Module):
         weights = F.dropout(weights, self.drop_prob, self.training)
         att = (weights @ v).permute(0, 2, 1, 3).reshape(b, h, w, c)
         return _glu(self.gate(att), -1)
+
+
+def assign_dropout_salts(root):
+    """Number the GatedAttn layers of `root` 1..n in module order: a layer's dropout stream depends on its position in
+    the model, not on how many other models the process built before."""
+    for i, m in enumerate(m for m in root.modules() if isinstance(m, GatedAttn)):
+        m._salt = i + 1
 
 
 class ConvAttnBlock(nn.Module):
@@ -238,6 +245,7 @@ class NN(nn.Module):
                                         for _ in range(num_blocks)])
         self.out_conv = WNConv2d(num_channels, in_channels * (2 + 3 * self.k), kernel_size=3, padding=1)
         self.rescale = _WNRescale(in_channels)
+        assign_dropout_salts(self)
 
     def forward_raw(self, x, aux=None):
         """Un-split out_conv output [B,(2+3K)c,H,W].  In inference mode (eval, autograd off) on supported shapes

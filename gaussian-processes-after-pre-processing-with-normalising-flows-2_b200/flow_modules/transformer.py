@@ -20,6 +20,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import _lib
+
 
 def _patches(x, p):
     b, c, h, w = x.shape
@@ -62,7 +64,7 @@ class Transformer_attn(nn.Module):
         """G = sum_i Wq_i^T Wk_i as a [C, C, 1, 1] conv weight (cached outside autograd)."""
         ws = (self.convq1, self.convk1, self.convq2, self.convk2, self.convq3, self.convk3)
         track = torch.is_grad_enabled() and any(w.requires_grad for w in ws)
-        key = tuple((w.data_ptr(), w._version) for w in ws)
+        key = _lib.param_key(ws)
         if not track and self._g is not None and self._g[0] == key:
             return self._g[1]
         g = sum(q[:, :, 0, 0].t() @ k[:, :, 0, 0] for q, k in zip(ws[0::2], ws[1::2]))

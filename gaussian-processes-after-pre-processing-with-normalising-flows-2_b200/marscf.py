@@ -16,7 +16,7 @@ import math
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .flow_modules.affine_coupling import AffineCoupling
 from .flow_modules.common_modules import (Actnormlayer, GaussianDiag, InvertibleConv1x1, Split2dMsC, SqueezeLayer,
                                           TupleFlip, _batch_ldj, fold_actnorm_invconv, squeeze2d)
@@ -49,7 +49,7 @@ class FlowStep(nn.Module):
         params = (an.bias, an.logs) + tuple(ic._params())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return fold_actnorm_invconv(an, ic, hw, reverse)
-        key = (hw, bool(reverse)) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (hw, bool(reverse)) + _lib.param_key(params)
         hit = self._fold_cache.get(bool(reverse))
         if hit is None or hit[0] != key:
             with torch.no_grad():
@@ -237,6 +237,8 @@ class MarScfFlow(nn.Module):
                             coupling_type=coupling_type, prior=prior, num_blocks=num_blocks,
                             fuse_squeeze=fuse_squeeze, attn=attn)
         self.batch_size = batch_size
+        from .flow_modules.mixlogcdf_nn import assign_dropout_salts
+        assign_dropout_salts(self)
 
     def forward(self, x=None, z=None, eps_std=None, reverse=False, noise=None):
         if not reverse:

@@ -34,6 +34,7 @@ def _workspace(dev: torch.device, batch: int) -> Tensor:
 def _f32c(t: Tensor, what: str) -> Tensor:
     if t.dtype != torch.float32:
         raise TypeError("%s: flowk kernels are float32 (got %s)" % (what, t.dtype))
+    _lib.check_device(t, what)
     return t.contiguous()
 
 

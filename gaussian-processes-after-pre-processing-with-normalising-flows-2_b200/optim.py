@@ -91,6 +91,7 @@ class FusedAdamax(torch.optim.Optimizer):
                 b1, b2 = group["betas"]
                 _lib.call("flowk_adamax_step", table.data_ptr(), n, self._clr[gi:].data_ptr(), float(b1), float(b2),
                           float(group["eps"]), tc._stream())
+        _lib.bump_generation()        # the kernel writes through raw pointers: torch's version counters do not move
 
     @torch.no_grad()
     def step(self, closure=None):

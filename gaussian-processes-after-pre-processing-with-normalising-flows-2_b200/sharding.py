@@ -28,9 +28,12 @@ def init_distributed(backend=None):
 
 
 def shard_batch(x, rank, world):
-    """Rank r takes samples [r*B/G, (r+1)*B/G) (the reference scatters on dim 0 the same way)."""
-    per = x.shape[0] // world
-    return x[rank * per:(rank + 1) * per]
+    """Rank r takes samples [ceil(r*B/G) ... ) with torch.tensor_split bounds: every sample goes to exactly one rank,
+    the first B % G ranks take one extra (the reference's DataParallel scatters dim 0 into chunks the same way)."""
+    n = x.shape[0]
+    per, rem = divmod(n, world)
+    lo = rank * per + min(rank, rem)
+    return x[lo:lo + per + (1 if rank < rem else 0)]
 
 
 def broadcast_module(module, src=0):
@@ -40,6 +43,8 @@ def broadcast_module(module, src=0):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src)
+    from . import _lib
+    _lib.bump_generation()            # `.data` writes skip the version counter: invalidate every derived-weight cache
 
 
 class GradientBuckets:
@@ -145,7 +150,6 @@ class ShardedTrainer:
             # one-launch Adamax over all parameter tensors (flowk.optim); the learning rate reaches the kernel through
             # a device scalar refreshed on the host, so the same update is captured when use_graph is on
             from .optim import FusedAdamax
-            torch.backends.cudnn.benchmark = True      # fixed shapes: let cuDNN pick its fastest fp32 algorithms (-6 %)
             self.opt = FusedAdamax(model.parameters(), lr=lr)
             self.sched = None
             self.fused = True
@@ -157,6 +161,7 @@ class ShardedTrainer:
             self.opt = torch.optim.Adamax(model.parameters(), lr=lr)
             self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s: min(1., s / warm_up))
         self.global_step = 0
+        self._lr_samples = 0           # the sample count the schedule sees (one step behind, see _set_lr)
         self.global_batch = global_batch
         self.graph_after = graph_after
         self._calls = 0
@@ -165,15 +170,18 @@ class ShardedTrainer:
             self._set_lr()             # LambdaLR's constructor applies lambda(0) = 0 to the first step, too
 
     def _set_lr(self):
-        """LambdaLR(min(1, samples_seen / warm_up)), stepped with the sample count like marscf_main.py:346-347."""
+        """LambdaLR(min(1, samples / warm_up)) stepped like marscf_main.py:345-347: `scheduler.step(global_step)` runs
+        BEFORE `global_step += batch_size`, so step k uses the sample count after step k-2 (the first two steps run
+        with lr = 0)."""
+        seen = self._lr_samples
         if self.sched is not None:
-            self.sched.last_epoch = self.global_step - 1
+            self.sched.last_epoch = seen - 1
             self.sched.step()
         elif self.fused:
             for group in self.opt.param_groups:
-                group["lr"] = self.base_lr * min(1., self.global_step / self.warm_up)
+                group["lr"] = self.base_lr * min(1., seen / self.warm_up)
         else:
-            self.lr_t.fill_(self.base_lr * min(1., self.global_step / self.warm_up))
+            self.lr_t.fill_(self.base_lr * min(1., seen / self.warm_up))
 
     def _eager_step(self, x_local):
         self.buckets.zero()
@@ -220,6 +228,14 @@ class ShardedTrainer:
             if self._graphs is None:
                 self._capture(x_local)
             fb, up, static_x, loss = self._graphs
+            if x_local.shape != static_x.shape:           # ragged last batch: the graph is shape-specialised
+                self.buckets.overlap = True               # hooks fire the all-reduces again (off while replaying graphs)
+                loss = self._eager_step(x_local)
+                self.buckets.overlap = False
+                from . import _lib
+                _lib.bump_generation()
+                self._advance(x_local)
+                return loss
             static_x.copy_(x_local, non_blocking=True)
             fb.replay()
             if not self.graph_allreduce:
@@ -229,9 +245,15 @@ class ShardedTrainer:
             elif self.fused:
                 self.opt.prepare_step()
             up.replay()
+            from . import _lib
+            _lib.bump_generation()    # a graph replay updates the parameters without touching their version counters
+        self._advance(x_local)
+        return loss
+
+    def _advance(self, x_local):
+        self._lr_samples = self.global_step
         self.global_step += self.global_batch or x_local.shape[0] * self.world
         self._set_lr()
-        return loss
 
 
 def mean_bits_per_dim(nll_local):

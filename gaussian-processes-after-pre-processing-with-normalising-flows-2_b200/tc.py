@@ -46,6 +46,7 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias
               w2_hi=None, w2_lo=None, out2_f32=None, n2=0, split_k=False):
     """`split_k=True` (training path: one stream, kernel latency matters) lends the kernel a workspace so that layers
     with few 128-row tiles and a long K loop are shared by several CTAs per output tile."""
+    _lib.check_device(a_hi, "conv_gemm")
     args = _lib.ConvGemmArgs(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(res), _p(gamma), _p(beta), _p(pos),
                              _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status), _p(trace),
                              B, H, W, Cin, N, taps, pre, out_mask, _p(w2_hi), _p(w2_lo), _p(out2_f32), n2, None)

@@ -49,9 +49,9 @@ def _worker(rank, world, port, out):
         ref_opt.zero_grad()
         ref(full)[1].mean().backward()
         ref_opt.step()
-        gs += 8
-        ref_sched.last_epoch = gs - 1
+        ref_sched.last_epoch = gs - 1            # scheduler.step(global_step) BEFORE the increment (marscf_main.py:346-347)
         ref_sched.step()
+        gs += 8
     err = max(float((a - b).abs().max()) for a, b in zip(model.parameters(), ref.parameters()))
     flat = torch.cat([p.detach().flatten() for p in model.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
@@ -81,6 +81,9 @@ def test_shard_batch():
     from flowk import sharding
     x = torch.arange(12).view(6, 2)
     assert torch.equal(sharding.shard_batch(x, 1, 3), x[2:4])
+    y = torch.arange(7)                          # ragged: every sample lands on exactly one rank
+    parts = [sharding.shard_batch(y, r, 3) for r in range(3)]
+    assert [len(p) for p in parts] == [3, 2, 2] and torch.equal(torch.cat(parts), y)
 
 
 def _driver_worker(rank, world, port, out):
@@ -117,7 +120,7 @@ def _driver_worker(rank, world, port, out):
         for epoch in range(2):
             for x, _ in train:
                 for grp in opt.param_groups:
-                    grp["lr"] = 0.05 * min(1.0, seen / 16)
+                    grp["lr"] = 0.05 * min(1.0, max(0, seen - 8) / 16)   # one step behind, like the reference
                 opt.zero_grad()
                 ref(x)[1].mean().backward()
                 opt.step()
