@@ -49,6 +49,12 @@ DESCRIBE = {
 METRIC = "mAR-SCF CIFAR10 MixLogCDF fwd+logdet images/s"
 
 
+def shared_config(workload, batch, world, depth):
+    """The `config` object BOTH arms print (the driver compares them): workload, batch and what one step is."""
+    return {"workload": DESCRIBE[workload], "batch_per_gpu": batch, "global_batch": batch * world,
+            "step": "one forward pass (z, log-det, bits/dim) of the whole flow stack over one batch"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -176,18 +182,18 @@ def run_reference(args):
     if rank != 0:
         return
     coupling, image, L, K, hidden, batch = WORKLOADS[args.workload]
-    sample = args.cpu_sample or (8 if coupling == "mixlogcdf" else 32)
+    sample = args.cpu_sample or batch               # the SAME batch the flowk arm steps over (cfg2: 64 images)
     sd = oracle_state(coupling, image, L, K, hidden, sample)
     ips, cores, sec = time_oracle(sd, coupling, image, L, K, sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": DESCRIBE[args.workload], "sample_images_per_step": sample,
-                   "note": "CPU oracle = port of the reference's PyTorch code path (reference is Python, "
-                           "cannot travel to the GPU box); rank 0 only"},
+        "config": shared_config(args.workload, sample, 1, 1),
+        "note": "CPU oracle = port of the reference's PyTorch code path (the reference is a Python tree that cannot "
+                "travel to the GPU box); all host cores through torch's intra-op threads; rank 0 only",
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d images per step, %d steps" % (sample, args.steps)},
+                         "sample": "%d images per step (the full batch), %d steps" % (sample, args.steps)},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -300,16 +306,26 @@ def run_flowk(args):
             nll_sum.copy_(nll.sum().reshape(1))
             dist.all_reduce(nll_sum)
 
+    lane_sums = {}
+
+    def reduce_on_lane(lane):                     # runs on the lane's stream right after its replay
+        if dist is not None:
+            buf = lane_sums.get(id(lane))
+            if buf is None:
+                buf = lane_sums[id(lane)] = torch.zeros(1, device=device)
+            buf.copy_(lane.static_nll.sum().reshape(1))
+            dist.all_reduce(buf)
+
     def resident_step(i):
         if args.depth > 1:
-            graphed.submit(pool[i % len(pool)])
+            graphed.submit(pool[i % len(pool)], after=reduce_on_lane)
             return
         _, nll = graphed.run(pool[i % len(pool)])
         reduce_bits(nll)
 
     def e2e_step(i):
         if args.depth > 1:                                    # H2D, replay and D2H all on the lane's stream
-            graphed.submit(host[i % len(host)], host_out[i % len(host_out)])
+            graphed.submit(host[i % len(host)], host_out[i % len(host_out)], after=reduce_on_lane)
             return
         _, nll = graphed.run(host[i % len(host)])             # H2D from pinned memory, then replay
         host_out[i % len(host_out)].copy_(nll, non_blocking=True)   # D2H of the per-image bits/dim
@@ -322,8 +338,6 @@ def run_flowk(args):
     def finish_steps():
         if args.depth > 1:
             graphed.drain()
-            if dist is not None:                              # one exchange for the whole run of steps
-                reduce_bits(graphed.lanes[0].static_nll)
 
     def timed(step_fn):
         for i in range(args.warmup):
@@ -452,16 +466,31 @@ def run_flowk(args):
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample, rank 0 at N=1 only ---------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample or (8 if coupling == "mixlogcdf" else 32)
+        sample = args.cpu_sample or batch
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        ips, cores, sec = time_oracle(sd, coupling, image, L, K, sample, 2, 1)
+        ips, cores, sec = time_oracle(sd, coupling, image, L, K, sample, 3, 1)
         cpu_baseline = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": "%d images per step, 2 timed steps after 1 warm-up (%.2f s/step)" % (sample, sec)}
+                        "sample": "%d images per step (the full batch), 3 timed steps after 1 warm-up (%.2f s/step)"
+                                  % (sample, sec)}
 
     # ---- training step (fwd + bwd + Adamax + gradient all-reduce), the metric's second half ---------------------------
-    train = None
+    train = train_strong = None
     if not args.no_train:
-        train = train_leg(args, device, rank, world, dist)
+        train = train_leg(args, device, rank, world, dist, "weak")
+        if world > 1 and WORKLOADS[args.workload][5] % world == 0:
+            train_strong = train_leg(args, device, rank, world, dist, "strong")
+        elif train is not None:
+            train_strong = dict(train, scaling="strong", note="N = 1: strong and weak scaling coincide")
+
+    # ---- inverse pass (sampling), every rank -------------------------------------------------------------------------
+    inverse = None
+    if not args.no_inverse:
+        inverse = inverse_leg(args, model, device, rank, world, dist)
+
+    # ---- HBM rooflines of the flow-level kernels, working set >> L2 (rank 0) ----------------------------------------------
+    roofline_flow_kernels = None
+    if rank == 0 and not args.no_large:
+        roofline_flow_kernels = elementwise_rooflines(device, hbm_peak)
 
     if rank == 0:
         ew_bytes = elementwise_bytes_per_image(coupling, image, L, K)
@@ -469,12 +498,13 @@ def run_flowk(args):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": DESCRIBE[args.workload], "batch_per_gpu": batch, "global_batch": batch * world,
-                       "batches_in_flight": args.depth,
-                       "l2": "no explicit flush: one step streams 2x178 MB of conditioner weight operands (cfg2) through "
-                             "the 126 MB L2 and rotates over 8 input batches",
-                       "prior": "standard normal (mAR ConvLSTM prior is outside the hot path)",
-                       "conditioner": "flowk tcgen05 implicit GEMMs (3xTF32) + mma.sync attention, inside the CUDA graph"},
+            "config": shared_config(args.workload, batch, world, args.depth),
+            "run": {"batches_in_flight": args.depth,
+                    "l2": "no explicit flush: one step streams the conditioner weight operands of 12 couplings (cfg2: "
+                          ">170 MB) through the 126 MB L2 and rotates over 8 input batches",
+                    "prior": "standard normal (the mAR ConvLSTM prior is a plug-in outside the north-star path)",
+                    "conditioner": "flowk tcgen05 implicit GEMMs + attention kernel, inside the CUDA graph",
+                    "bits_dim_allreduce": "every step, on the replaying stream (N > 1)"},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(host[0].numel() * 4),
                     "d2h_bytes_per_step": int(batch * 4), "ms_per_step": ms_e2e / args.steps},
             "single_stream": {"value": images / (ms_lat / 1e3), "unit": "images/s", "ms_per_step": ms_lat / args.steps,
@@ -487,6 +517,9 @@ def run_flowk(args):
             "roofline_large": roofline_large,
             "cpu_baseline": cpu_baseline,
             "train": train,
+            "train_strong": train_strong,
+            "inverse": inverse,
+            "roofline_flow_kernels": roofline_flow_kernels,
             "elementwise_bytes_per_image": ew_bytes,
             "kernels": kernels,
         }
@@ -495,13 +528,111 @@ def run_flowk(args):
         dist.destroy_process_group()
 
 
-def train_leg(args, device, rank, world, dist):
+def inverse_leg(args, model, device, rank, world, dist):
+    """Sampling throughput (the inverse pass the north star names; marscf_main.py:167-175,223-231): latents drawn from
+    N(0,1) on the device, `FlowNet.decode_latents`, NaN/clamp post-processing, all inside one CUDA graph per lane;
+    `e2e` adds the D2H copy of the images into pinned host memory.  Weak scaling: every rank samples its own batch."""
+    from flowk.graphs import GraphedSampler
+    coupling, image, L, K, hidden, batch = WORKLOADS[args.workload]
+    depth = max(1, args.depth)
+    lanes = [GraphedSampler(model, batch, image) for _ in range(depth)]
+    host_img = [torch.empty(batch, image[2], image[0], image[1], pin_memory=True) for _ in range(depth)]
+
+    def run(steps, to_host, single):
+        for i in range(steps):
+            lane = lanes[0] if single else lanes[i % depth]
+            lane.run(host_img[i % depth] if to_host else None)
+        for lane in lanes:
+            torch.cuda.current_stream().wait_stream(lane.stream)
+
+    def timed(to_host, single):
+        run(max(3, args.warmup), to_host, single)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        run(args.steps, to_host, single)
+        e.record()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        if dist is not None:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    ms_res, ms_e2e, ms_single = timed(False, False), timed(True, False), timed(False, True)
+    images = batch * world * args.steps
+    finite = bool(torch.isfinite(lanes[0].images).all())
+    return {"value": images / (ms_res / 1e3), "unit": "images/s", "ms_per_step": ms_res / args.steps,
+            "e2e": {"value": images / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(host_img[0].numel() * 4)},
+            "single_stream": {"value": images / (ms_single / 1e3), "ms_per_step": ms_single / args.steps},
+            "batches_in_flight": depth, "batch_per_gpu": batch, "flowk_launches_per_step": int(lanes[0].flowk_launches),
+            "finite": finite,
+            "note": "sampling = inverse pass of the whole stack incl. drawing the latents; MixLogCDF: register-resident "
+                    "per-element bisection (log_dist.py:43-72), affine: closed form"}
+
+
+def elementwise_rooflines(device, hbm_peak):
+    """HBM rooflines of the flow-level kernels with working sets far beyond the 126 MB L2 (SURVEY.md section 8d bytes:
+    8 B per element for the fused ActNorm∘InvConv channel mix, 12 B per element for the affine coupling)."""
+    from flowk import ops
+    out = {}
+
+    def time_us(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) * 1e3 / reps
+
+    for c, hw in ((12, 16), (24, 8), (48, 4), (96, 4)):
+        bl = min(65535, (512 << 20) // (c * hw * hw * 4))      # <= 512 MB input + as much output (grid.y = batch)
+        x = torch.randn(bl, c, hw, hw, device=device)
+        mat = torch.linalg.qr(torch.randn(c, c, device=device))[0].contiguous()
+        bias = torch.randn(c, device=device)
+        ldj = torch.zeros(bl, device=device)
+        add = torch.ones(1, device=device)
+        us = time_us(lambda: ops.channel_mix(x, mat, bias, ldj, add, False, False))
+        nbytes = 8 * x.numel()
+        out["channel_mix_C%d" % c] = {"bound": "hbm", "kernel": "flowk_channel_mix B,C,H,W=(%d, %d, %d, %d)" % (bl, c, hw, hw),
+                                      "achieved": nbytes / (us * 1e-6) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": nbytes / (us * 1e-6) / 1e9 / hbm_peak, "bytes_per_launch": nbytes,
+                                      "us_per_launch": us, "flop_per_byte": 2.0 * c * c / (8.0 * c)}
+        del x
+    bl, c, hw = 16384, 12, 16
+    x = torch.randn(bl, c, hw, hw, device=device)
+    h = torch.randn(bl, c, hw, hw, device=device)
+    ldj = torch.zeros(bl, device=device)
+    for name, rev in (("affine_fwd", False), ("affine_inv", True)):
+        us = time_us(lambda: ops.affine_coupling(x, h, ldj, rev))
+        nbytes = 12 * x.numel()
+        out[name] = {"bound": "hbm", "kernel": "flowk_affine_coupling_%s B,C,H,W=(%d, %d, %d, %d)" % (
+                         "inv" if rev else "fwd", bl, c, hw, hw),
+                     "achieved": nbytes / (us * 1e-6) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": nbytes / (us * 1e-6) / 1e9 / hbm_peak, "bytes_per_launch": nbytes, "us_per_launch": us}
+    return out
+
+
+def train_leg(args, device, rank, world, dist, scaling="weak"):
     """Training images/s on the same workload: the reference's step (marscf_main.py:331-347) with the batch sharded
     over ranks (64 images per GPU, weak scaling) and the gradients all-reduced over NCCL in flat buckets."""
     import flowk  # noqa: F401
     from flowk import sharding
     from flowk.marscf import MarScfFlow
     coupling, image, L, K, hidden, batch = WORKLOADS[args.workload]
+    if scaling == "strong":                             # the reference divides ONE global batch (marscf_main.py:290)
+        assert batch % world == 0
+        batch = batch // world
     torch.manual_seed(0)
     np.random.seed(0)
     model = MarScfFlow(batch, image, coupling, L, K, hidden).to(device)
@@ -511,7 +642,7 @@ def train_leg(args, device, rank, world, dist):
         model(xs[0])                                    # ActNorm data-dependent init on the first batch
     sharding.broadcast_module(model)
     trainer = sharding.ShardedTrainer(model, lr=1e-4, warm_up=10000, global_batch=batch * world)
-    steps = max(2, min(args.steps, args.train_steps))
+    steps = max(2, args.train_steps)
     for i in range(4):                                  # 2 eager steps, graph capture, 1 replay
         trainer.step(xs[i % len(xs)])
     if dist is not None:
@@ -531,7 +662,8 @@ def train_leg(args, device, rank, world, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     return {"value": batch * world * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
-            "warmup": 4, "global_batch": batch * world, "grad_allreduce_mb": trainer.buckets.nbytes() / 1e6,
+            "warmup": 4, "scaling": scaling, "batch_per_gpu": batch, "global_batch": batch * world,
+            "grad_allreduce_mb": trainer.buckets.nbytes() / 1e6,
             "loss_bits_per_dim": float(loss),
             "note": "fwd+bwd+Adamax(+NCCL all-reduce of flat gradient buckets); forward+backward and the optimizer update "
                     "replayed as CUDA graphs (the all-reduces are nodes of the backward graph); conditioner convs/linears: "
@@ -553,7 +685,8 @@ def main():
     ap.add_argument("--no-large", action="store_true")
     ap.add_argument("--depth", type=int, default=6, help="batches in flight (graph instances on separate streams)")
     ap.add_argument("--no-train", action="store_true")
-    ap.add_argument("--train-steps", type=int, default=5)
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--no-inverse", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "flowk" else args.warmup
     if args.impl == "reference":

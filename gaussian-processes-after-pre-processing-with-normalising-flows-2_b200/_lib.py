@@ -152,6 +152,29 @@ def check_device(t, what="flowk"):
                            % (what, t.device, torch.cuda.current_device()))
 
 
+ALLOW_LIBRARY = os.environ.get("FLOWK_ALLOW_LIBRARY", "0") == "1"
+LIBRARY_FALLBACKS = 0      # how many times a CUDA tensor was routed to cuDNN / cuBLAS / ATen instead of a flowk kernel
+
+
+def library_fallback(what, t=None):
+    """Called right before a conditioner layer would run a CUDA tensor through a library kernel (F.conv2d, F.linear,
+    bmm + softmax attention, ATen LayerNorm) because no flowk kernel takes its shape.  There is no silent multi-backend
+    dispatch: this raises unless FLOWK_ALLOW_LIBRARY=1 (or `flowk._lib.ALLOW_LIBRARY = True`) opts in.  CPU tensors pass
+    (host-side logic tests; the flow ops themselves are CUDA-only)."""
+    global LIBRARY_FALLBACKS
+    if t is not None and (not t.is_cuda or t.dtype != torch_float32()):
+        return                       # CPU tensors: host-side tests; float64: reference computations of the tests
+    if not ALLOW_LIBRARY:
+        raise RuntimeError("flowk: %s has no flowk kernel for this shape/mode and would fall back to a library kernel; "
+                           "set FLOWK_ALLOW_LIBRARY=1 to allow it" % what)
+    LIBRARY_FALLBACKS += 1
+
+
+def torch_float32():
+    import torch
+    return torch.float32
+
+
 def param_key(params):
     return (GENERATION,) + tuple((p.data_ptr(), p._version) for p in params)
 

@@ -125,6 +125,7 @@ def mixlogcdf_nn_raw(nn_module, x_id, status=None):
             if tc.attention_supported(HW, C, heads):
                 t_hi, t_lo = tc.attention(qkv, B, HW, C, heads)
             else:                                                     # odd head sizes: library matmuls
+                _lib.library_fallback("attention core (seq %d, head dim %d)" % (HW, C // heads), qkv)
                 d = C // heads
                 t = qkv.view(B, HW, 3, heads, d)
                 k, v, q = (t[:, :, i].permute(0, 2, 1, 3) for i in range(3))

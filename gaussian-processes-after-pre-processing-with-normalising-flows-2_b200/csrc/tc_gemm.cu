@@ -739,7 +739,7 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   if (!a) return FLOWK_ERR_ARG;
   if (!plan_only && (!a->a_hi || !a->a_lo || !a->w_hi || !a->w_lo)) return FLOWK_ERR_ARG;
   const int B = a->B, H = a->H, W = a->W, Cin = a->Cin, N = a->N;
-  if (B < 1 || H < 1 || W < 1 || Cin < BLOCK_K || Cin % BLOCK_K || N < 8) return FLOWK_ERR_SHAPE;
+  if (B < 1 || H < 1 || W < 1 || Cin < BLOCK_K || Cin % BLOCK_K || N < 1) return FLOWK_ERR_SHAPE;
   if (a->taps != 1 && a->taps != 9) return FLOWK_ERR_ARG;
   if (!plan_only && !encode_fn()) return FLOWK_ERR_ARG;      // planning is a pure host computation
   // M tile = bt images x ht rows x W columns = 128 positions

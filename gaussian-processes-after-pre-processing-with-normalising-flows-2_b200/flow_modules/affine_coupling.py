@@ -9,6 +9,19 @@ from .. import ops
 from .common_modules import Actnormlayer, _batch_ldj
 
 
+def _conv(x, weight, bias, stride, padding):
+    """conv2d of the conditioner: stride-1 "same" 1x1 / 3x3 convolutions of CUDA tensors run on the flowk tcgen05 GEMMs
+    (forward, input and weight gradients: flowk.tc_autograd.conv2d); anything else is a library call and needs
+    FLOWK_ALLOW_LIBRARY=1 (flowk._lib.library_fallback)."""
+    from .. import _lib, tc_autograd
+    kh, kw = weight.shape[2], weight.shape[3]
+    same = tuple(stride) == (1, 1) and tuple(padding) == (kh // 2, kw // 2) and kh == kw
+    if same and tc_autograd.conv_supported(x, weight):
+        return tc_autograd.conv2d(x, weight, bias, kh // 2)
+    _lib.library_fallback("conv %s on input %s" % (tuple(weight.shape), tuple(x.shape)), x)
+    return F.conv2d(x, weight, bias, stride, padding)
+
+
 def _same_padding(kernel_size, stride):
     if isinstance(kernel_size, int):
         kernel_size = [kernel_size, kernel_size]
@@ -42,7 +55,7 @@ class Conv2dZeros(nn.Conv2d):
 
     def forward(self, input):
         gain = torch.exp(self.logs.view(-1) * self.logscale_factor)
-        return F.conv2d(input, self.weight * gain.view(-1, 1, 1, 1), self.bias * gain, self.stride, self.padding)
+        return _conv(input, self.weight * gain.view(-1, 1, 1, 1), self.bias * gain, self.stride, self.padding)
 
 
 class Conv2d(nn.Conv2d):
@@ -65,16 +78,15 @@ class Conv2d(nn.Conv2d):
 
     def forward(self, input):
         if not self.do_actnorm:
-            return F.conv2d(input, self.weight, self.bias, self.stride, self.padding)
+            return _conv(input, self.weight, self.bias, self.stride, self.padding)
         an = self.actnorm
         if an.training and not an._seen_initialized:
-            x = F.conv2d(input, self.weight, None, self.stride, self.padding)
+            x = _conv(input, self.weight, None, self.stride, self.padding)
             x, _ = an(x, None)                     # runs the data-dependent init on the raw conv output
             return x
         # (conv(x) + b) e^{logs} == conv(x; w e^{logs}) + b e^{logs}
         gain = torch.exp(an.logs.view(-1))
-        return F.conv2d(input, self.weight * gain.view(-1, 1, 1, 1), an.bias.view(-1) * gain, self.stride,
-                        self.padding)
+        return _conv(input, self.weight * gain.view(-1, 1, 1, 1), an.bias.view(-1) * gain, self.stride, self.padding)
 
 
 class NN_net(nn.Module):

@@ -20,6 +20,7 @@ def concat_elu(x, dim=1):
     from .. import tc_autograd
     if tc_autograd.pointwise_ok(x):
         return tc_autograd.concat_elu(x, dim)          # one fused kernel each way instead of neg + cat + elu
+    _lib.library_fallback("concat_elu on %s" % x.dtype, x)
     return F.elu(torch.cat((x, -x), dim=dim))
 
 
@@ -27,6 +28,7 @@ def _glu(x, dim):
     from .. import tc_autograd
     if tc_autograd.pointwise_ok(x):
         return tc_autograd.glu(x, dim)
+    _lib.library_fallback("GLU on %s" % x.dtype, x)
     a, b = x.chunk(2, dim=dim)
     return a * torch.sigmoid(b)
 
@@ -70,9 +72,10 @@ class _WNConvCore(_WeightNormed):
         from .. import tc_autograd
         v = self.weight_v
         prepared = tc_autograd.take_prepared(self)      # always consumed: operands are valid for ONE forward after a refresh
-        if torch.is_grad_enabled() and self.padding == v.shape[2] // 2 and tc_autograd.conv_supported(x, v):
-            # training: weight norm + operands fused, forward + dgrad on tcgen05
+        if self.padding == v.shape[2] // 2 and tc_autograd.conv_supported(x, v):
+            # weight norm + operands fused, forward (+ dgrad, wgrad under autograd) on tcgen05
             return tc_autograd.wn_conv2d(x, v, self.weight_g, self.bias, prepared)
+        _lib.library_fallback("weight-normed conv %s on input %s" % (tuple(v.shape), tuple(x.shape)), x)
         return F.conv2d(x, self.normed_weight(), self.bias, padding=self.padding)
 
 
@@ -84,8 +87,9 @@ class _WNLinear(_WeightNormed):
     def forward(self, x):
         from .. import tc_autograd
         prepared = tc_autograd.take_prepared(self)
-        if torch.is_grad_enabled() and tc_autograd.linear_supported(x, self.weight_v):
+        if tc_autograd.linear_supported(x, self.weight_v):
             return tc_autograd.wn_linear(x, self.weight_v, self.weight_g, self.bias, prepared)
+        _lib.library_fallback("weight-normed linear %s on input %s" % (tuple(self.weight_v.shape), tuple(x.shape)), x)
         return F.linear(x, self.normed_weight(), self.bias)
 
 
@@ -164,13 +168,14 @@ class GatedAttn(nn.Module):
         t = x.reshape(b, seq, c) + self._pos_enc(seq, c, x.device)
         proj = self.in_proj(t)
         from .. import tc_autograd
-        if torch.is_grad_enabled() and tc_autograd.attention_train_supported(proj, heads):
+        if tc_autograd.attention_train_supported(proj, heads):
             # fused forward / backward with in-kernel dropout: nothing of size seq x seq touches HBM
             att = tc_autograd.attention_core(proj, heads, self.drop_prob if self.training else 0.0, self._salt)
             return _glu(self.gate(att.view(b, h, w, c)), -1)
         # in_proj output order is (k | v | q): memory = first 2C, query = last C (mixlogcdf_nn.py:136-139).
         # ONE strided copy puts all three head-first, [3, B, heads, seq, d] contiguous: the batched matmuls then need
         # no further layout copies and the backward is a single permute-copy instead of slice-gradient fills.
+        _lib.library_fallback("attention core (seq %d, head dim %d)" % (seq, d), x)
         kvq = proj.view(b, seq, 3, heads, d).permute(2, 0, 3, 1, 4).contiguous()
         k, v, q = kvq[0], kvq[1], kvq[2] * (d ** -0.5)
         weights = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
@@ -205,6 +210,7 @@ class ConvAttnBlock(nn.Module):
             if self.attn:
                 x = tc_autograd.add_layernorm(self.attn(x), x, self.norm_2, False, True)
             return x
+        _lib.library_fallback("residual + LayerNorm over %d channels" % x.size(1), x)
         x = self.conv(x, aux) + x
         x = self.norm_1(x.permute(0, 2, 3, 1))
         if self.attn:

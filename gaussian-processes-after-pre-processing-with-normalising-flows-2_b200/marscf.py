@@ -117,7 +117,7 @@ class StandardNormalPrior(nn.Module):
 
 class FlowNet(nn.Module):
     def __init__(self, batch_size, image_shape, hidden_channels, K, L, coupling_type, actnorm_scale=1.0,
-                 prior=None, num_blocks=10, fuse_squeeze=True, attn=False):
+                 prior=None, num_blocks=10, fuse_squeeze=True, attn=False, drop_prob=0.2):
         super().__init__()
         self.layers = nn.ModuleList()
         self.output_shapes = []
@@ -134,7 +134,7 @@ class FlowNet(nn.Module):
             for _ in range(K):
                 self.layers.append(FlowStep(H, W, C, in_channels=C, out_channels=C, hidden_channels=hidden_channels,
                                             actnorm_scale=actnorm_scale, coupling_type=coupling_type,
-                                            num_blocks=num_blocks, attn=attn))
+                                            num_blocks=num_blocks, attn=attn, drop_prob=drop_prob))
                 self.output_shapes.append([-1, C, H, W])
             if i < L - 1:
                 self.layers.append(Split2dMsC(C, i + 1))
@@ -231,11 +231,11 @@ class FlowNet(nn.Module):
 
 class MarScfFlow(nn.Module):
     def __init__(self, batch_size, image_shape, coupling_type, L, K, C, prior=None, num_blocks=10,
-                 fuse_squeeze=True, attn=False):
+                 fuse_squeeze=True, attn=False, drop_prob=0.2):
         super().__init__()
         self.flow = FlowNet(batch_size, image_shape=image_shape, hidden_channels=C, K=K, L=L,
                             coupling_type=coupling_type, prior=prior, num_blocks=num_blocks,
-                            fuse_squeeze=fuse_squeeze, attn=attn)
+                            fuse_squeeze=fuse_squeeze, attn=attn, drop_prob=drop_prob)
         self.batch_size = batch_size
         from .flow_modules.mixlogcdf_nn import assign_dropout_salts
         assign_dropout_salts(self)

@@ -29,7 +29,7 @@ def conv_supported(x, w):
     if not (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
         return False
     n, cin, kh, kw = w.shape
-    if (kh, kw) not in ((1, 1), (3, 3)) or n < 8 or cin < 8:          # both serve as the GEMM N (forward / dgrad)
+    if (kh, kw) not in ((1, 1), (3, 3)) or n < 1 or cin < 1:          # both serve as the GEMM N (forward / dgrad)
         return False
     b, _, h, ww = x.shape
     if ww > 128 or 128 % ww:
@@ -80,7 +80,14 @@ class _Conv2d(torch.autograd.Function):
             gx = torch.empty(x.shape, device=x.device, dtype=torch.float32)      # contiguous NCHW whatever x's strides
             tc.conv_gemm(g_hi, g_lo, wt_hi, wt_lo, b, h, ww, np_, cin, taps, tc.PRE_BIAS, tc.OUT_NCHW, out_nchw=gx, split_k=True)
         if ctx.needs_input_grad[1]:
-            gw = torch.nn.grad.conv2d_weight(x, w.shape, gy, padding=kh // 2)
+            partial = wgrad_partials(x.contiguous(), gy, taps)
+            if partial is not None:                      # tcgen05 split-K slices [S, taps, N, Cin] (or [S, taps, Cin, N])
+                p, transposed = partial
+                gw = p.sum(0)
+                gw = (gw.permute(2, 1, 0) if transposed else gw.permute(1, 2, 0)).reshape(n, cin, kh, kw).contiguous()
+            else:
+                _lib.library_fallback("conv weight gradient %s" % (tuple(w.shape),), x)
+                gw = torch.nn.grad.conv2d_weight(x, w.shape, gy, padding=kh // 2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = channel_sum(gy, True)
         return gx, gw, gb
@@ -130,9 +137,17 @@ class _Linear(torch.autograd.Function):
             if n % 32 == 0:
                 gx = _rows_gemm(g2, w.detach().t().contiguous(), None, k).view(ctx.shape)
             else:
+                _lib.library_fallback("linear input gradient, N=%d" % n, g2)
                 gx = (g2 @ w).view(ctx.shape)
         if ctx.needs_input_grad[1]:
-            gw = g2.t() @ x2
+            partial = linear_wgrad_partials(x2, g2)
+            if partial is not None:
+                p, transposed = partial
+                gw = p.sum(0)[0]
+                gw = gw.t().contiguous() if transposed else gw
+            else:
+                _lib.library_fallback("linear weight gradient [%d, %d]" % (n, k), g2)
+                gw = g2.t() @ x2
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = channel_sum(g2, False)
         return gx, gw, gb
@@ -286,7 +301,7 @@ class WeightNormBatch:
             return False
         n, cin = v.shape[0], v.shape[1]
         if v.dim() == 4:
-            return (v.shape[2], v.shape[3]) in ((1, 1), (3, 3)) and n >= 8 and cin >= 8
+            return (v.shape[2], v.shape[3]) in ((1, 1), (3, 3)) and n >= 1 and cin >= 1
         return n % 4 == 0 and cin % 32 == 0
 
     def _pointers(self):
@@ -374,6 +389,7 @@ class _WNConv2d(torch.autograd.Function):
                 if partial is not None:
                     gv, gg = _wn_backward_partials(v, g, norm, partial)
                 else:
+                    _lib.library_fallback("conv weight gradient %s" % (tuple(v.shape),), x)
                     gv, gg = _wn_backward(v, g, norm, torch.nn.grad.conv2d_weight(x, v.shape, gy, padding=kh // 2))
             if ctx.has_bias and ctx.needs_input_grad[3]:
                 gb = channel_sum(gy, True)
@@ -419,6 +435,7 @@ class _WNLinearFn(torch.autograd.Function):
                 if partial is not None:
                     gv, gg = _wn_backward_partials(v, g, norm, partial)
                 else:
+                    _lib.library_fallback("linear weight gradient [%d, %d]" % (n, k), g2)
                     gv, gg = _wn_backward(v, g, norm, g2.t() @ x2)
             if ctx.has_bias and ctx.needs_input_grad[3]:
                 gb = channel_sum(g2, False)
@@ -430,6 +447,7 @@ class _WNLinearFn(torch.autograd.Function):
                              out_f32=gx, split_k=True)
                 gx = gx.view(ctx.shape)
             else:
+                _lib.library_fallback("linear input gradient, N=%d" % n, g2)
                 gx = (g2 @ wd).view(ctx.shape)
         fork.join()
         return gx, gv, gg, gb, None

@@ -44,6 +44,28 @@ class Golden(dict):
                     self[k] = t
 
 
+@pytest.fixture
+def allow_library():
+    """Tests on nets narrower than the kernels take (hidden width 8 / 16: attention head dim < 8, Linear K < 32) opt in
+    to the library layers explicitly; everything else must run on flowk kernels only (`no_library`)."""
+    from flowk import _lib
+    old = _lib.ALLOW_LIBRARY
+    _lib.ALLOW_LIBRARY = True
+    yield _lib
+    _lib.ALLOW_LIBRARY = old
+
+
+@pytest.fixture
+def no_library():
+    """Asserts that the test body never routed a CUDA tensor to cuDNN / cuBLAS / ATen conditioner layers."""
+    from flowk import _lib
+    old, before = _lib.ALLOW_LIBRARY, _lib.LIBRARY_FALLBACKS
+    _lib.ALLOW_LIBRARY = False
+    yield _lib
+    _lib.ALLOW_LIBRARY = old
+    assert _lib.LIBRARY_FALLBACKS == before
+
+
 @pytest.fixture(scope="session")
 def golden():
     cache = {}

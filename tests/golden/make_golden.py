@@ -336,13 +336,23 @@ def gen_transformer_attn():
 
 
 if __name__ == "__main__":
-    gen_transformer_attn()
-    gen_mar_prior()
-    gen_squeeze()
-    gen_actnorm()
-    gen_invconv()
-    gen_affine()
-    gen_mixlogcdf_elementwise()
-    gen_mixlogcdf_coupling()
-    gen_flownet("flownet_affine", "affine", (16, 16, 3), 3, 2, 8, 0, 2, 21)
-    gen_flownet("flownet_mixlogcdf", "mixlogcdf", (8, 8, 3), 2, 1, 8, 1, 2, 22)
+    only = set(sys.argv[1:])          # `make_golden.py wide` regenerates only the width-32 nets below
+
+    def want(tag):
+        return not only or tag in only
+    if want("base"):
+        gen_transformer_attn()
+        gen_mar_prior()
+        gen_squeeze()
+        gen_actnorm()
+        gen_invconv()
+        gen_affine()
+        gen_mixlogcdf_elementwise()
+        gen_mixlogcdf_coupling()
+        gen_flownet("flownet_affine", "affine", (16, 16, 3), 3, 2, 8, 0, 2, 21)
+        gen_flownet("flownet_mixlogcdf", "mixlogcdf", (8, 8, 3), 2, 1, 8, 1, 2, 22)
+    if want("wide"):
+        # hidden width 32: the narrowest nets whose conditioners run ENTIRELY on the tcgen05 / flowk kernels (channel
+        # blocks of 32, attention head dim 8), so the tensor-core path is pinned to the reference's own outputs
+        gen_flownet("flownet_affine_h32", "affine", (16, 16, 3), 2, 2, 32, 0, 2, 23)
+        gen_flownet("flownet_mixlogcdf_h32", "mixlogcdf", (16, 16, 3), 2, 1, 32, 1, 2, 24)

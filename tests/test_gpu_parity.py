@@ -142,7 +142,7 @@ def test_invconv_golden(F, golden, name):
 
 @pytest.mark.parametrize("C,H,W,B", [(12, 16, 16, 64), (24, 8, 8, 64), (48, 4, 4, 64), (96, 4, 4, 8), (4, 14, 14, 5),
                                      (20, 3, 5, 3), (12, 64, 64, 40)])
-def test_fused_actnorm_invconv_vs_oracle(F, C, H, W, B):
+def test_fused_actnorm_invconv_vs_oracle(F, allow_library, C, H, W, B):
     import numpy as np
     np.random.seed(C)
     gen = torch.Generator().manual_seed(C * 7 + H)
@@ -307,7 +307,7 @@ def test_mixlogcdf_tail_elements_use_log_domain(F):
     parity(l, ref_l, what="tail ldj")
 
 
-def test_mixlogcdf_coupling_with_conditioner_golden(F, golden):
+def test_mixlogcdf_coupling_with_conditioner_golden(F, golden, allow_library):
     g = golden("mixlogcdf_coupling")
     m = F.mc.MixLogCDFCoupling(12, 16, 2, 32, 0.2).to(dev())
     m.load_state_dict({k[len("coupling."):]: v for k, v in g.sd.items()})
@@ -347,8 +347,28 @@ def build_from_golden(F, g, fuse):
 
 @pytest.mark.parametrize("name", ["flownet_affine", "flownet_mixlogcdf"])
 @pytest.mark.parametrize("fuse", [True, False])
-def test_flownet_golden(F, golden, name, fuse):
-    g = golden(name)
+def test_flownet_golden(F, golden, allow_library, name, fuse):
+    """Width-8 nets: narrower than the kernels' channel blocks, so Linear / attention layers opt in to the library."""
+    _flownet_golden(F, golden(name), fuse)
+
+
+@pytest.mark.parametrize("name", ["flownet_affine_h32", "flownet_mixlogcdf_h32"])
+def test_flownet_golden_tensor_core(F, golden, no_library, name):
+    """Width-32 nets from the reference's own modules: every conditioner layer runs on the tcgen05 / flowk kernels
+    (`no_library` fails the test on any cuDNN / cuBLAS / ATen conditioner layer), pinned to the REFERENCE outputs."""
+    from flowk import _lib
+    _lib.TIMING = {}
+    try:
+        _flownet_golden(F, golden(name), True)
+        names = set(_lib.TIMING)
+    finally:
+        _lib.TIMING = None
+    assert "flowk_conv_gemm" in names, names
+    if "mixlogcdf" in name:
+        assert "flowk_attention" in names and "flowk_mixlogcdf_fwd" in names, names
+
+
+def _flownet_golden(F, g, fuse):
     model = build_from_golden(F, g, fuse)
     x, noise = g["x"].to(dev()), g["noise"].to(dev())
     with torch.no_grad():
@@ -447,7 +467,7 @@ def test_mixlogcdf_backward_vs_oracle(F, flip):
     parity(ld_.grad, l0.grad, what="dldj")
 
 
-def test_flowstep_backward_vs_oracle(F, golden):
+def test_flowstep_backward_vs_oracle(F, golden, allow_library):
     """Gradients w.r.t. every parameter of a small affine FlowNet, against autograd through the oracle."""
     g = golden("flownet_affine")
     model = build_from_golden(F, g, True)
@@ -476,7 +496,7 @@ def test_flowstep_backward_vs_oracle(F, golden):
     assert checked > 20
 
 
-def test_cfg2_architecture_vs_oracle(F):
+def test_cfg2_architecture_vs_oracle(F, no_library):
     """The BASELINE cfg2 architecture (MixLogCDF, L=3, K=4, C=96, 10 blocks) at a small batch: the whole GPU stack
     (tcgen05 conditioners + fused flow kernels) against the CPU oracle with the same weights."""
     import numpy as np
@@ -530,9 +550,10 @@ def test_marscf_with_mar_prior(F):
     assert "flow.c_prior.prior_list.0.prior_lstm.lstm.weight_ih_l0" in keys
 
 
-def test_mixlogcdf_flownet_backward_vs_oracle(F, golden):
-    """Training gradients of a small MixLogCDF FlowNet (conditioner through torch autograd, flow ops through the flowk
-    forward/backward kernels) against float64 autograd through the oracle, for every parameter."""
+def test_mixlogcdf_flownet_backward_vs_oracle(F, golden, allow_library):
+    """Training gradients of a small (width-8) MixLogCDF FlowNet against float64 autograd through the oracle, for every
+    parameter: convs and pointwise layers on the flowk forward/backward kernels, the width-8 Linear / attention layers
+    on the library (see test_cfg2_training_gradients_vs_oracle for the all-flowk full-width step)."""
     g = golden("flownet_mixlogcdf")
     model = build_from_golden(F, g, True)
     m = g.meta
@@ -600,7 +621,7 @@ def test_graphed_training_step_matches_eager(F):
 
 @pytest.mark.parametrize("coupling,hidden,B", [("mixlogcdf", 96, 5), ("mixlogcdf", 32, 1), ("affine", 64, 3),
                                                ("affine", 256, 130)])
-def test_odd_batch_sizes_through_tensor_core_path(F, coupling, hidden, B):
+def test_odd_batch_sizes_through_tensor_core_path(F, no_library, coupling, hidden, B):
     """Batches that do not fill the 128-row GEMM tiles (TMA zero-fills the missing images, the epilogues mask the rows):
     the tcgen05 conditioner path must agree with the torch/cuDNN path on the same module."""
     import numpy as np
@@ -663,3 +684,165 @@ def test_fused_adamax_matches_torch_adamax():
         torch.testing.assert_close(sa[k]["exp_inf"], sb[k]["exp_inf"], rtol=1e-6, atol=1e-12)
     ob2 = torch.optim.Adamax(pb, lr=1e-2)
     ob2.load_state_dict(oa.state_dict())                     # torch's optimizer accepts the fused optimizer's checkpoint
+
+
+# ---------------------------------------------------------------------------------------------
+# every BASELINE.json config at its real width: tcgen05 conditioners + fused flow kernels vs the CPU oracle
+# ---------------------------------------------------------------------------------------------
+BASELINE_CONFIGS = {
+    # name: (coupling, image HWC, L, K, hidden, batch, check inverse against the oracle)
+    "cfg1": ("affine", (32, 32, 3), 3, 4, 64, 32, True),
+    "cfg2": ("mixlogcdf", (32, 32, 3), 3, 4, 96, 64, False),
+    "cfg3": ("affine", (32, 32, 3), 3, 4, 256, 128, True),
+    "cfg4": ("mixlogcdf", (32, 32, 3), 3, 4, 160, 8, False),
+    "cfg5": ("affine", (64, 64, 3), 4, 4, 256, 8, True),
+}
+
+
+def _initialised_model(F, coupling, image, L, K, hidden, B, seed, **kw):
+    import numpy as np
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    model = F.marscf.MarScfFlow(B, image, coupling, L, K, hidden, **kw).to(dev())
+    gen = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(B, image[2], image[0], image[1], generator=gen) - 0.5
+    noise = torch.rand(B, image[2], image[0], image[1], generator=gen)
+    model.train()
+    with torch.no_grad():
+        model(x.to(dev()), noise=noise.to(dev()))            # ActNorm data-dependent init (first training batch)
+        for p in model.parameters():                         # move the zero-initialised output convs off zero
+            p.add_((torch.randn(p.shape, generator=gen) * 0.02).to(p.device))
+    return model, x, noise
+
+
+@pytest.mark.parametrize("cfg", sorted(BASELINE_CONFIGS))
+def test_baseline_config_vs_oracle(F, no_library, cfg):
+    """Forward (z, every factored-out z2, logdet, bits/dim) of each BASELINE.json config at its REAL width and batch
+    through the tensor-core path, against the CPU oracle with the same weights; the affine configs (cfg1, cfg3, cfg5:
+    "inverse sampling") also check the inverse pass against the oracle's, the MixLogCDF ones the round trip (their
+    bisection is pinned to the oracle in test_mixture_functions_golden / test_mixlogcdf_elementwise_vs_oracle)."""
+    from flowk import _lib
+    coupling, image, L, K, hidden, B, inverse = BASELINE_CONFIGS[cfg]
+    model, x, noise = _initialised_model(F, coupling, image, L, K, hidden, B, seed=100 + sorted(BASELINE_CONFIGS).index(cfg))
+    model.eval()
+    d = x[0].numel()
+    _lib.TIMING = {}
+    try:
+        with torch.no_grad():
+            z, nll, _ = model(x.to(dev()), noise=noise.to(dev()))
+            zf, outs, ld = model.flow.encode_latents((x + noise / 256.0).to(dev()), torch.zeros(B, device=dev()))
+            xr, ldr = model.flow.decode_latents(zf, outs, with_logdet=True)
+        torch.cuda.synchronize()
+        names = set(_lib.TIMING)
+    finally:
+        _lib.TIMING = None
+    assert "flowk_conv_gemm" in names, names                   # the tcgen05 conditioner ran
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    z_ref, outs_ref, ld_ref, nll_ref = O.normal_flow(sd, x, noise, L, K, coupling)
+    parity(z, z_ref, what=cfg + " z")
+    for i, (a, b) in enumerate(zip(outs, outs_ref)):
+        parity(a, b, what=cfg + " z2_%d" % i)
+    parity(ld, ld_ref - float(-math.log(256.0) * d), what=cfg + " logdet")
+    assert float((nll.cpu() - nll_ref).abs().max()) < 1e-3, cfg
+    if inverse:
+        xr_ref, ldr_ref = O.flownet_decode(sd, z_ref, outs_ref, L, K, coupling)
+        parity(xr, xr_ref, what=cfg + " inverse x")
+        parity(ldr, ldr_ref, what=cfg + " inverse logdet")
+    else:
+        parity(xr, x + noise / 256.0, rel=2e-3, what=cfg + " round trip")
+        assert float((ld + ldr).abs().max()) < 2e-3 * max(1.0, float(ld.abs().max()))
+
+
+def test_cfg2_training_gradients_vs_oracle(F, no_library):
+    """A cfg2-shaped TRAINING step (MixLogCDF, C=96, all three level shapes 16x16 / 8x8 / 4x4, 2 ConvAttnBlocks,
+    train mode with dropout p = 0) against float64 autograd through the oracle, for every parameter.  Exercises the
+    batched weight norm, `wn_conv2d` / `wn_linear` forward + dgrad + tcgen05 wgrad, `attention_train_*`,
+    `add_layernorm`, concat-ELU / GLU and the flow kernels' backward passes; `no_library` proves none of it fell back."""
+    from flowk import _lib
+    coupling, image, L, K, hidden, B = "mixlogcdf", (32, 32, 3), 3, 1, 96, 8
+    model, x, noise = _initialised_model(F, coupling, image, L, K, hidden, B, seed=77, num_blocks=2, drop_prob=0.0)
+    sd64 = {k: v.detach().cpu().double().requires_grad_(v.dtype.is_floating_point and "is_initialized" not in k and
+                                                         not k.endswith(".p") and not k.endswith("sign_s"))
+            for k, v in model.state_dict().items()}
+    sd_blocks = {k: v for k, v in sd64.items()}
+    z, outs, ldj, nll = O.normal_flow(sd_blocks, x.double(), noise.double(), L, K, coupling)
+    nll.mean().backward()
+    model.train()                                              # the real training path (dropout layers present, p = 0)
+    _lib.TIMING = {}
+    try:
+        _, nll_d, _ = model(x.to(dev()), noise=noise.to(dev()))
+        nll_d.mean().backward()
+        torch.cuda.synchronize()
+        names = set(_lib.TIMING)
+    finally:
+        _lib.TIMING = None
+    for need in ("flowk_conv_gemm", "flowk_conv_wgrad", "flowk_linear_wgrad", "flowk_attention_train_fwd",
+                 "flowk_attention_train_bwd", "flowk_add_layernorm_fwd", "flowk_add_layernorm_bwd",
+                 "flowk_weight_norm_operands_batched", "flowk_weight_norm_bwd_partials", "flowk_mixlogcdf_bwd"):
+        assert need in names, (need, sorted(names))
+    assert float((nll_d.detach().cpu() - nll.float()).abs().max()) < 1e-3
+    checked = 0
+    for name, p in model.named_parameters():
+        ref = sd64[name].grad
+        if ref is None:
+            continue
+        if name.endswith(".l") or name.endswith(".u"):
+            c = ref.shape[0]
+            ref = ref * (torch.tril(torch.ones(c, c), -1) if name.endswith(".l") else torch.triu(torch.ones(c, c), 1))
+        parity(p.grad, ref, rel=1e-3, what="grad " + name)
+        checked += 1
+    assert checked > 100
+
+
+def test_affine_training_gradients_on_tensor_cores(F, no_library):
+    """Affine NN_net training (cfg1 width, 16x16 / 8x8 / 4x4): conv forward, input and weight gradients on the flowk
+    tcgen05 kernels, ActNorm-in-conv through autograd; every parameter gradient vs float64 oracle autograd."""
+    coupling, image, L, K, hidden, B = "affine", (32, 32, 3), 3, 1, 64, 8
+    model, x, noise = _initialised_model(F, coupling, image, L, K, hidden, B, seed=78)
+    sd64 = {k: v.detach().cpu().double().requires_grad_(v.dtype.is_floating_point and "is_initialized" not in k and
+                                                         not k.endswith(".p") and not k.endswith("sign_s"))
+            for k, v in model.state_dict().items()}
+    z, outs, ldj, nll = O.normal_flow(sd64, x.double(), noise.double(), L, K, coupling)
+    nll.mean().backward()
+    model.train()
+    _, nll_d, _ = model(x.to(dev()), noise=noise.to(dev()))
+    nll_d.mean().backward()
+    checked = 0
+    for name, p in model.named_parameters():
+        ref = sd64[name].grad
+        if ref is None:
+            continue
+        if name.endswith(".l") or name.endswith(".u"):
+            c = ref.shape[0]
+            ref = ref * (torch.tril(torch.ones(c, c), -1) if name.endswith(".l") else torch.triu(torch.ones(c, c), 1))
+        parity(p.grad, ref, rel=1e-3, what="grad " + name)
+        checked += 1
+    assert checked > 20
+
+
+def test_eval_caches_follow_raw_pointer_updates(F, no_library):
+    """FusedAdamax writes parameters through raw device pointers (no torch version bump): the folded / packed /
+    weight-normed inference caches must still follow (weights generation, flowk._lib.bump_generation).  eval -> large
+    fused steps -> eval must equal a fresh model loaded from the live state dict, and differ from the first eval."""
+    from flowk.optim import FusedAdamax
+    for coupling in ("mixlogcdf", "affine"):
+        model, x, noise = _initialised_model(F, coupling, (16, 16, 3), 2, 2, 32, 4, seed=5, num_blocks=1)
+        xd, nd = x.to(dev()), noise.to(dev())
+        model.eval()
+        with torch.no_grad():
+            _, nll0, _ = model(xd, noise=nd)                    # fills every derived-weight cache
+        opt = FusedAdamax(model.parameters(), lr=0.05)
+        gen = torch.Generator().manual_seed(9)
+        for _ in range(3):
+            for p in model.parameters():
+                p.grad = torch.randn(p.shape, generator=gen).to(dev())
+            opt.step()
+        with torch.no_grad():
+            _, nll1, _ = model(xd, noise=nd)
+        clone = F.marscf.MarScfFlow(4, (16, 16, 3), coupling, 2, 2, 32, num_blocks=1).to(dev())
+        clone.load_state_dict(model.state_dict())
+        clone.eval()
+        with torch.no_grad():
+            _, nll2, _ = clone(xd, noise=nd)
+        assert float((nll1 - nll0).abs().max()) > 1e-2, "the update must change the model output"
+        assert float((nll1 - nll2).abs().max()) <= 1e-5 * max(1.0, float(nll2.abs().max())), coupling

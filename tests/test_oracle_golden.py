@@ -138,6 +138,12 @@ def test_flownet_mixlogcdf(golden):
     _flownet(golden, "flownet_mixlogcdf")
 
 
+def test_flownet_width32(golden):
+    """The width-32 nets (the fixtures the tensor-core conditioner path is pinned to on the GPU)."""
+    _flownet(golden, "flownet_affine_h32")
+    _flownet(golden, "flownet_mixlogcdf_h32")
+
+
 def test_float64_oracle_agrees_with_fp32_reference(golden):
     """The same functions in float64 are the high-precision yardstick; fp32 reference outputs
     must sit within the 1e-4 parity budget of them on these well-conditioned fixtures."""
