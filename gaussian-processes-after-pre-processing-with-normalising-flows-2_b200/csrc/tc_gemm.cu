@@ -6,9 +6,14 @@
 //   by ONE 4-D TMA box load whose coordinates carry the tap shift - out-of-bounds rows/columns are zero-filled by
 //   the TMA unit, which is the convolution's padding;
 // * weights [N, taps*Cin] K-major, 2-D TMA;
-// * tcgen05.mma kind::tf32, M=128, accumulators in TMEM.  fp32 accuracy (the 1e-4 parity budget rules out plain
-//   TF32) comes from the 3xTF32 split: every operand is stored as hi = x with the low 13 mantissa bits cleared and
-//   lo = x - hi (exact), and D += A_hi W_hi + A_lo W_hi + A_hi W_lo (dropped term ~2^-22);
+// * tcgen05.mma, M=128, accumulators in TMEM.  fp32 accuracy (the 1e-4 parity budget rules out plain TF32 / bf16)
+//   comes from a two-term operand split x = hi + lo and D += A_hi W_hi + A_lo W_hi + A_hi W_lo (dropped term ~2^-22):
+//     - F16 = false (training path: gradients need fp32's exponent range): kind::tf32, hi / lo are TF32 values in
+//       fp32 containers, 32 channels per 128-byte k-block, K = 8 per MMA;
+//     - F16 = true (inference): kind::f16, hi / lo are fp16 (11 significant bits each - exactly TF32's - so the
+//       split is as accurate, provided |x| < 65504; weights are pre-scaled by a power of two, undone by `acc_scale`):
+//       HALF the operand bytes through TMA / shared memory (the bound of these layers, 4 B per element for the pair
+//       = what ONE fp32 copy costs) and K = 16 per MMA, i.e. half the MMA instructions;
 // * warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane), warps 2..5 = epilogue,
 //   each thread owning one accumulator row (TMEM lane) - so row-wise epilogues (GLU, residual, LayerNorm over the
 //   channel dim) are thread-local;
@@ -25,7 +30,8 @@
 namespace flowk {
 namespace tc {
 
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB
+constexpr int ROW_BYTES = 128;                          // one swizzle row = one k-block of a tile row (32 tf32 / 64 fp16)
+constexpr int A_TILE_BYTES = BLOCK_M * ROW_BYTES;       // 16 KB
 constexpr int EPI_WARPS = 16;                // 4 per TMEM lane group: they split the column chunks
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_CHUNKS = 2;
@@ -62,13 +68,14 @@ struct Params {
   // operand tiles and are multiplied by a second weight matrix [n2, C] in the same CTA (gate -> in_proj fusion)
   int chain, n2, n2_chunk, n2_chunks, a3_offset, w2_offset;
   float* out2_f32;                 // [M, n2]
+  float acc_scale;                 // F16: the weights were scaled by 1 / acc_scale (a power of two)
   int ksplit;                      // > 1: blockIdx.z takes a slice of every tap's channel blocks; fp32 partial rows go to
                                    // out_f32 + z*M*N (no bias) and flowk's split-K reduce kernel finishes the layer
   int* status;                     // set to 1 if a barrier wait timed out
   long long* trace;                // optional [16] clock64 stamps of CTA (0,0): setup, first full, last mma, epi start, epi end
 };
 
-template <int PRE, int NV>      // NV: 128-column groups per lane in the LayerNorm epilogue (1: C <= 128, 2: C <= 256)
+template <int PRE, int NV, bool F16>   // NV: 128-column groups per lane in the LayerNorm epilogue (1: C <= 128, 2: C <= 256)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -77,7 +84,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A_hi | A_lo | W_hi | W_lo], then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int w_tile_bytes = p.n_chunk * p.n_chunks * BLOCK_K * 4;
+  constexpr int BK = F16 ? 64 : BLOCK_K;                 // channels per k-block (128 bytes either way)
+  const int w_tile_bytes = p.n_chunk * p.n_chunks * ROW_BYTES;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * w_tile_bytes;
   // normal mode:   full[stages], empty[stages], tmem_full
   // dx-split mode:  a_full[a_slots], a_empty[a_slots], w_full[w_slots], w_empty[w_slots], tmem_full
@@ -152,8 +160,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           mbar_wait(&empty_bar[sa], (((uint32_t)(g / p.a_slots)) & 1u) ^ 1u, failed);
           uint8_t* at = smem + (size_t)sa * 2 * A_TILE_BYTES;
           mbar_expect_tx(&full_bar[sa], 2u * A_TILE_BYTES);
-          tma_load_4d(at, &map_a_hi, &full_bar[sa], cb * BLOCK_K, 0, h0 + dyi - 1, b0);
-          tma_load_4d(at + A_TILE_BYTES, &map_a_lo, &full_bar[sa], cb * BLOCK_K, 0, h0 + dyi - 1, b0);
+          tma_load_4d(at, &map_a_hi, &full_bar[sa], cb * BK, 0, h0 + dyi - 1, b0);
+          tma_load_4d(at + A_TILE_BYTES, &map_a_lo, &full_bar[sa], cb * BK, 0, h0 + dyi - 1, b0);
           // the three taps (dy, dx=-1,0,+1) of this group: weight tiles back to back in ONE slot, so that the three
           // per-shift accumulators (adjacent TMEM column ranges) can be fed by wide MMAs
           const int sw = g % p.w_slots;
@@ -161,7 +169,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           uint8_t* wt = w_ring + (size_t)sw * 6 * w_tile_bytes;
           mbar_expect_tx(&wfull_bar[sw], 6u * (uint32_t)w_tile_bytes);
           for (int dxi = 0; dxi < 3; ++dxi) {
-            const int kcol = ((dyi * 3 + dxi) * p.kblocks_per_tap + cb) * BLOCK_K;
+            const int kcol = ((dyi * 3 + dxi) * p.kblocks_per_tap + cb) * BK;
             tma_load_2d(wt + dxi * w_tile_bytes, &map_w_hi, &wfull_bar[sw], kcol, n_base);
             tma_load_2d(wt + (3 + dxi) * w_tile_bytes, &map_w_lo, &wfull_bar[sw], kcol, n_base);
           }
@@ -175,11 +183,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const int tap = kb / kpt, cb = cb0 + kb % kpt;
         const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
         mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-        tma_load_4d(st, &map_a_hi, &full_bar[s], cb * BLOCK_K, dx, h0 + dy, b0);
-        tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[s], cb * BLOCK_K, dx, h0 + dy, b0);
-        const int kcol = (tap * p.kblocks_per_tap + cb) * BLOCK_K;   // weights are [N, taps*Cin], (tap, c) order
+        tma_load_4d(st, &map_a_hi, &full_bar[s], cb * BK, dx, h0 + dy, b0);
+        tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[s], cb * BK, dx, h0 + dy, b0);
+        const int kcol = (tap * p.kblocks_per_tap + cb) * BK;        // weights are [N, taps*Cin_pad], (tap, c) order
         for (int c = 0; c < p.n_chunks; ++c) {
-          const int chunk_bytes = p.n_chunk * BLOCK_K * 4;
+          const int chunk_bytes = p.n_chunk * ROW_BYTES;
           tma_load_2d(st + 2 * A_TILE_BYTES + c * chunk_bytes, &map_w_hi, &full_bar[s], kcol, n_base + c * p.n_chunk);
           tma_load_2d(st + 2 * A_TILE_BYTES + w_tile_bytes + c * chunk_bytes, &map_w_lo, &full_bar[s], kcol,
                       n_base + c * p.n_chunk);
@@ -189,7 +197,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         // second GEMM's weights [n2, C]: their slot lies over the (now idle) pipeline stages, so wait for the first
         // GEMM to retire; the load then hides behind the GLU/LayerNorm epilogue
         mbar_wait(tmem_full_bar, 0, failed);
-        const int w2_chunk_bytes = p.n2_chunk * BLOCK_K * 4, w2_half = w2_chunk_bytes * p.n2_chunks;
+        const int w2_chunk_bytes = p.n2_chunk * ROW_BYTES, w2_half = w2_chunk_bytes * p.n2_chunks;
         const int kb2 = (p.N >> 1) / BLOCK_K;
         for (int kb = 0; kb < kb2; ++kb) {
           mbar_wait(w2_empty_bar, ((uint32_t)kb & 1u) ^ 1u, failed);
@@ -205,7 +213,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.n_chunk);
+      const uint32_t idesc = make_idesc_t<F16>(p.n_chunk);
       if (p.dxsplit) {
         const uint32_t w_ring = smem_u32(smem + (size_t)p.a_slots * 2 * A_TILE_BYTES);
         const int groups = 3 * p.kblocks_per_tap;
@@ -215,8 +223,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         int n_mma = (n_total + 255) / 256;
         if ((n_total / n_mma) % 16 || n_total % n_mma) n_mma = 3;
         const int n_per = n_total / n_mma;
-        const uint32_t idesc_w = make_idesc(n_per);
-        const uint64_t per_units = (uint64_t)((uint32_t)(n_per * BLOCK_K * 4) >> 4);
+        const uint32_t idesc_w = make_idesc_t<F16>(n_per);
+        const uint64_t per_units = (uint64_t)((uint32_t)(n_per * ROW_BYTES) >> 4);
         for (int g = 0; g < groups; ++g) {
           const int sa = g % p.a_slots, sw = g % p.w_slots;
           mbar_wait(&full_bar[sa], ((uint32_t)(g / p.a_slots)) & 1u, failed);
@@ -229,15 +237,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const uint64_t da_hi = make_smem_desc(a_hi), da_lo = da_hi + (A_TILE_BYTES >> 4);
           const uint64_t db_hi = make_smem_desc(w_hi), db_lo = db_hi + ((3u * (uint32_t)w_tile_bytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
+          for (int k = 0; k < 4; ++k) {                               // 4 MMA k-steps of 32 bytes per 128-byte row
+            const uint64_t ko = (uint64_t)(k * 2);
             for (int q = 0; q < n_mma; ++q) {
               const uint64_t bo = ko + q * per_units;
               const uint32_t d = tmem_base + q * n_per;
-              if ((g | k) == 0) umma_tf32(d, da_hi + ko, db_hi + bo, idesc_w, 0u);
-              else umma_tf32_acc(d, da_hi + ko, db_hi + bo, idesc_w);
-              umma_tf32_acc(d, da_lo + ko, db_hi + bo, idesc_w);
-              umma_tf32_acc(d, da_hi + ko, db_lo + bo, idesc_w);
+              umma<F16>(d, da_hi + ko, db_hi + bo, idesc_w, (g | k) == 0 ? 0u : 1u);
+              umma<F16>(d, da_lo + ko, db_hi + bo, idesc_w, 1u);
+              umma<F16>(d, da_hi + ko, db_lo + bo, idesc_w, 1u);
             }
           }
           umma_commit(&wempty_bar[sw]);
@@ -255,17 +262,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint64_t da_hi0 = make_smem_desc(a_hi), da_lo0 = da_hi0 + (A_TILE_BYTES >> 4);
         const uint64_t db_hi0 = da_hi0 + (2 * A_TILE_BYTES >> 4), db_lo0 = db_hi0 + ((uint32_t)w_tile_bytes >> 4);
-        const uint64_t chunk_units = (uint64_t)((uint32_t)(p.n_chunk * BLOCK_K * 4) >> 4);
+        const uint64_t chunk_units = (uint64_t)((uint32_t)(p.n_chunk * ROW_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);       // 16-byte units inside the 128-byte swizzle row
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);                     // 16-byte units inside the 128-byte swizzle row
           for (int c = 0; c < p.n_chunks; ++c) {
             const uint64_t co = ko + c * chunk_units;
             const uint32_t d = tmem_base + c * p.n_chunk;
-            if ((kb | k) == 0) umma_tf32(d, da_hi0 + ko, db_hi0 + co, idesc, 0u);
-            else umma_tf32_acc(d, da_hi0 + ko, db_hi0 + co, idesc);
-            umma_tf32_acc(d, da_lo0 + ko, db_hi0 + co, idesc);
-            umma_tf32_acc(d, da_hi0 + ko, db_lo0 + co, idesc);
+            umma<F16>(d, da_hi0 + ko, db_hi0 + co, idesc, (kb | k) == 0 ? 0u : 1u);
+            umma<F16>(d, da_lo0 + ko, db_hi0 + co, idesc, 1u);
+            umma<F16>(d, da_hi0 + ko, db_lo0 + co, idesc, 1u);
           }
         }
         umma_commit(&empty_bar[s]);                                  // smem slot free once these MMAs retire
@@ -275,10 +281,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       if (p.chain) {
         mbar_wait(a3_full_bar, 0, failed);                           // epilogue warps have written the operand tiles
         tc_fence_after();
-        const uint32_t idesc2 = make_idesc(p.n2_chunk);
+        const uint32_t idesc2 = make_idesc(p.n2_chunk);           // (chain mode is tf32-only: checked on the host)
         const int kb2 = (p.N >> 1) / BLOCK_K;
-        const uint32_t w2_half = (uint32_t)(p.n2_chunk * BLOCK_K * 4 * p.n2_chunks);
-        const uint64_t chunk2_units = (uint64_t)((uint32_t)(p.n2_chunk * BLOCK_K * 4) >> 4);
+        const uint32_t w2_half = (uint32_t)(p.n2_chunk * ROW_BYTES * p.n2_chunks);
+        const uint64_t chunk2_units = (uint64_t)((uint32_t)(p.n2_chunk * ROW_BYTES) >> 4);
         for (int kb = 0; kb < kb2; ++kb) {
           mbar_wait(w2_full_bar, (uint32_t)kb & 1u, failed);
           tc_fence_after();
@@ -314,6 +320,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int slab_row0 = m_tile * BLOCK_M + lane_grp * 32;          // first global row of the 32-row slab
     const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const int ncols_cta = p.n_chunk * p.n_chunks;
+    const float sc = F16 ? p.acc_scale : 1.f;                        // undoes the power-of-two pre-scaling of fp16 weights
     mbar_wait(tmem_full_bar, 0, failed);
     tc_fence_after();
     if (tracing && threadIdx.x == 64) p.trace[3] = clock64();
@@ -347,7 +354,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           float* o = p.out_nchw + ((size_t)img * p.N + n0) * p.HW + hw;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (n0 + i < p.N) o[(size_t)i * p.HW] = v[i] + (p.bias ? __ldg(p.bias + n0 + i) : 0.f);
+            if (n0 + i < p.N) o[(size_t)i * p.HW] = fmaf(v[i], sc, p.bias ? __ldg(p.bias + n0 + i) : 0.f);
         }
       }
       if (p.out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_CELU | OUT_HILO_RELU)) {
@@ -380,7 +387,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias && n < p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             *reinterpret_cast<float4*>(slab + lane * pitch + j + i) =
-                make_float4(v[i] + bv.x, v[i + 1] + bv.y, v[i + 2] + bv.z, v[i + 3] + bv.w);
+                make_float4(fmaf(v[i], sc, bv.x), fmaf(v[i + 1], sc, bv.y), fmaf(v[i + 2], sc, bv.z), fmaf(v[i + 3], sc, bv.w));
           }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -398,24 +405,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const size_t o = (size_t)m * p.N + n;
             if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(out_f32 + o) = y;
             if (p.out_mask & (OUT_HILO | OUT_HILO_RELU)) {             // RELU: NN_net's activations (affine_coupling.py:77-78)
-              float h[4], l[4];
+              float t[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) split_tf32((p.out_mask & OUT_HILO_RELU) ? fmaxf(ys[i], 0.f) : ys[i], h[i], l[i]);
-              *reinterpret_cast<float4*>(p.out_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(p.out_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+              for (int i = 0; i < 4; ++i) t[i] = (p.out_mask & OUT_HILO_RELU) ? fmaxf(ys[i], 0.f) : ys[i];
+              store_hilo4<F16>(p.out_hi, p.out_lo, o, t);
             }
             if (p.out_mask & OUT_HILO_CELU) {                        // concat_elu: [elu(y) | elu(-y)], width 2N
               const size_t o2 = (size_t)m * 2 * p.N + n;
-              float h[4], l[4], h2[4], l2[4];
+              float t[4], t2[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                split_tf32(elu1(ys[i]), h[i], l[i]);
-                split_tf32(elu1(-ys[i]), h2[i], l2[i]);
+                t[i] = elu1(ys[i]);
+                t2[i] = elu1(-ys[i]);
               }
-              *reinterpret_cast<float4*>(p.out_hi + o2) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(p.out_lo + o2) = make_float4(l[0], l[1], l[2], l[3]);
-              *reinterpret_cast<float4*>(p.out_hi + o2 + p.N) = make_float4(h2[0], h2[1], h2[2], h2[3]);
-              *reinterpret_cast<float4*>(p.out_lo + o2 + p.N) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+              store_hilo4<F16>(p.out_hi, p.out_lo, o2, t);
+              store_hilo4<F16>(p.out_hi, p.out_lo, o2 + p.N, t2);
             }
           }
         }
@@ -450,8 +454,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + j + i));
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + C + j + i));
           *reinterpret_cast<float4*>(slab + lane * pitch + j + i) =
-              make_float4((a[i] + ba.x) * sigmoid_fast(b[i] + bb.x), (a[i + 1] + ba.y) * sigmoid_fast(b[i + 1] + bb.y),
-                          (a[i + 2] + ba.z) * sigmoid_fast(b[i + 2] + bb.z), (a[i + 3] + ba.w) * sigmoid_fast(b[i + 3] + bb.w));
+              make_float4(fmaf(a[i], sc, ba.x) * sigmoid_fast(fmaf(b[i], sc, bb.x)),
+                          fmaf(a[i + 1], sc, ba.y) * sigmoid_fast(fmaf(b[i + 1], sc, bb.y)),
+                          fmaf(a[i + 2], sc, ba.z) * sigmoid_fast(fmaf(b[i + 2], sc, bb.z)),
+                          fmaf(a[i + 3], sc, ba.w) * sigmoid_fast(fmaf(b[i + 3], sc, bb.w)));
         }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -527,24 +533,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const size_t o = (size_t)m * C + c4;
           if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
           if (p.out_mask & (OUT_HILO | OUT_HILO_POS)) {
-            float h[4], l[4];
+            float t[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_tf32(y[i] + pe[rr][v][i], h[i], l[i]);     // pe == 0 unless OUT_HILO_POS
-            *reinterpret_cast<float4*>(p.out_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(p.out_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+            for (int i = 0; i < 4; ++i) t[i] = y[i] + pe[rr][v][i];                      // pe == 0 unless OUT_HILO_POS
+            store_hilo4<F16>(p.out_hi, p.out_lo, o, t);
           }
           if (p.out_mask & OUT_HILO_CELU) {
             const size_t o2 = (size_t)m * 2 * C + c4;
-            float h[4], l[4], h2[4], l2[4];
+            float t[4], t2[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              split_tf32(elu1(y[i]), h[i], l[i]);
-              split_tf32(elu1(-y[i]), h2[i], l2[i]);
+              t[i] = elu1(y[i]);
+              t2[i] = elu1(-y[i]);
             }
-            *reinterpret_cast<float4*>(p.out_hi + o2) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(p.out_lo + o2) = make_float4(l[0], l[1], l[2], l[3]);
-            *reinterpret_cast<float4*>(p.out_hi + o2 + C) = make_float4(h2[0], h2[1], h2[2], h2[3]);
-            *reinterpret_cast<float4*>(p.out_lo + o2 + C) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+            store_hilo4<F16>(p.out_hi, p.out_lo, o2, t);
+            store_hilo4<F16>(p.out_hi, p.out_lo, o2 + C, t2);
           }
           if (p.chain) {
             // operand of the chained GEMM, written where the tensor core will read it: K-major tile of 128 rows x 128 B
@@ -602,6 +605,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 // elementwise helpers around the GEMMs
 // --------------------------------------------------------------------------------------------------
 // NCHW slice -> NHWC hi/lo operand, channel dim zero-padded to c_pad (conditioner input, mixlogcdf_nn.py:66)
+template <bool F16>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_hilo_kernel(const float* __restrict__ x, long long batch_stride, int c,
                                                                int hw, int c_pad, float* __restrict__ hi,
                                                                float* __restrict__ lo) {
@@ -623,47 +627,64 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_hilo_kernel(const float* __r
   for (int r = 0; r < 4; ++r) {
     const int p = p0 + ty + 8 * r, ch = c0 + tx;
     if (p < hw && ch < c_pad) {
-      float h, l;
-      split_tf32(tile[tx][ty + 8 * r], h, l);
       const size_t o = ((size_t)blockIdx.z * hw + p) * c_pad + ch;
-      hi[o] = h;
-      lo[o] = l;
+      if (F16) {
+        unsigned short h, l;
+        split_f16(tile[tx][ty + 8 * r], h, l);
+        reinterpret_cast<unsigned short*>(hi)[o] = h;
+        reinterpret_cast<unsigned short*>(lo)[o] = l;
+      } else {
+        float h, l;
+        split_tf32(tile[tx][ty + 8 * r], h, l);
+        hi[o] = h;
+        lo[o] = l;
+      }
     }
   }
 }
 
 // fp32 rows -> hi/lo operand pair (attention output -> gate GEMM)
+template <bool F16>
 __global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
-                                  long long total) {
+                                  long long total, float scale) {
   griddep_launch();
   griddep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    float h, l;
-    split_tf32(x[i], h, l);
-    hi[i] = h;
-    lo[i] = l;
+    if (F16) {
+      unsigned short h, l;
+      split_f16(x[i] * scale, h, l);
+      reinterpret_cast<unsigned short*>(hi)[i] = h;
+      reinterpret_cast<unsigned short*>(lo)[i] = l;
+    } else {
+      float h, l;
+      split_tf32(x[i], h, l);
+      hi[i] = h;
+      lo[i] = l;
+    }
   }
 }
 
 // --------------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------------
-static bool make_map_act(CUtensorMap* map, const float* base, int B, int H, int W, int C, int bt, int ht, int wt) {
+// `es` = element size: 4 (tf32 values in fp32 containers, 32 channels per box) or 2 (fp16, 64 channels per box); a box
+// that reaches past C (C not a multiple of the block) is zero-filled by the TMA unit
+static bool make_map_act(CUtensorMap* map, const float* base, int B, int H, int W, int C, int bt, int ht, int wt, int es) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)wt, (cuuint32_t)ht, (cuuint32_t)bt};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[4] = {(cuuint32_t)(ROW_BYTES / es), (cuuint32_t)wt, (cuuint32_t)ht, (cuuint32_t)bt};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  return encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+  return encode_fn()(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-static bool make_map_w(CUtensorMap* map, const float* base, int N, int Ktot, int rows) {
+static bool make_map_w(CUtensorMap* map, const float* base, int N, int Ktot, int rows, int es) {
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)N};
-  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * es};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / es), (cuuint32_t)rows};
   cuuint32_t estr[2] = {1, 1};
-  return encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  return encode_fn()(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -739,7 +760,12 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   if (!a) return FLOWK_ERR_ARG;
   if (!plan_only && (!a->a_hi || !a->a_lo || !a->w_hi || !a->w_lo)) return FLOWK_ERR_ARG;
   const int B = a->B, H = a->H, W = a->W, Cin = a->Cin, N = a->N;
-  if (B < 1 || H < 1 || W < 1 || Cin < BLOCK_K || Cin % BLOCK_K || N < 1) return FLOWK_ERR_SHAPE;
+  const bool f16 = a->operand_format == FLOWK_OPERAND_F16;
+  if (a->operand_format != FLOWK_OPERAND_TF32 && !f16) return FLOWK_ERR_ARG;
+  const int es = f16 ? 2 : 4, bk = ROW_BYTES / es;            // channels per k-block
+  if (B < 1 || H < 1 || W < 1 || N < 1) return FLOWK_ERR_SHAPE;
+  if (f16 ? (Cin < 8 || Cin % 8) : (Cin < BLOCK_K || Cin % BLOCK_K)) return FLOWK_ERR_SHAPE;   // 16-byte row pitch / whole blocks
+  if (f16 && !(a->acc_scale > 0.f)) return FLOWK_ERR_ARG;
   if (a->taps != 1 && a->taps != 9) return FLOWK_ERR_ARG;
   if (!plan_only && !encode_fn()) return FLOWK_ERR_ARG;      // planning is a pure host computation
   // M tile = bt images x ht rows x W columns = 128 positions
@@ -761,7 +787,8 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   p.W = W;
   p.H = H;
   p.taps = a->taps;
-  p.kblocks_per_tap = Cin / BLOCK_K;
+  p.kblocks_per_tap = (Cin + bk - 1) / bk;
+  p.acc_scale = f16 ? a->acc_scale : 1.f;
   p.wt = wt;
   p.ht = ht;
   p.bt = bt;
@@ -825,7 +852,7 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   }
   const int cols = p.n_chunk * p.n_chunks;
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * cols * BLOCK_K * 4;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * cols * ROW_BYTES;
   int stages = (int)((220 * 1024 - 2048) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 1) return FLOWK_ERR_SHAPE;
@@ -837,7 +864,7 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
     if (3 * p.n_chunk <= 128) p.tmem_cols = 128;
     p.a_slots = 2;
     if (const char* e = getenv("FLOWK_A_SLOTS")) p.a_slots = atoi(e);   // tuning knob
-    const int w_slot_bytes = 6 * cols * BLOCK_K * 4;            // 3 column shifts x (hi, lo)
+    const int w_slot_bytes = 6 * cols * ROW_BYTES;              // 3 column shifts x (hi, lo)
     int ws = (int)((220 * 1024 - 2048 - p.a_slots * 2 * A_TILE_BYTES) / w_slot_bytes);
     p.w_slots = ws > 4 ? 4 : ws;
     if (p.w_slots < 2) p.dxsplit = 0;
@@ -848,13 +875,14 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   if ((p.out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_POS | OUT_HILO_CELU | OUT_HILO_RELU)) && (N & 3)) return FLOWK_ERR_SHAPE;
   while (stages > 1 && (size_t)stages * stage_bytes + 2048 > 227 * 1024) --stages;
   size_t region = (size_t)stages * stage_bytes;
-  if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 6 * cols * BLOCK_K * 4;
+  if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 6 * cols * ROW_BYTES;
   if (epi_bytes > region) region = (epi_bytes + 1023) / 1024 * 1024;
   if (region + 2048 > 227 * 1024) return FLOWK_ERR_SHAPE;
   // chained second GEMM (gate -> in_proj): needs both accumulators in TMEM and the operand / weight tiles in smem
   p.chain = 0;
   if (a->w2_hi && a->w2_lo && a->out2_f32 && a->N2 > 0) {
     const int C = N / 2, n2 = a->N2;
+    if (f16) return FLOWK_ERR_ARG;                           // the chained second GEMM exists for tf32 operands only
     if (a->pre != PRE_GLU_RES_LN || p.n_chunks != 1 || C % BLOCK_K || n2 % 16 || N + n2 > 512) return FLOWK_ERR_SHAPE;
     p.n2 = n2;
     p.n2_chunks = n2 <= 256 ? 1 : 2;
@@ -876,12 +904,12 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   const size_t smem_bytes = region + 1024 + 256;
 
   alignas(64) CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo;
-  const int Ktot = a->taps * Cin;
-  if (!make_map_act(&ma_hi, a->a_hi, B, H, W, Cin, bt, ht, wt) || !make_map_act(&ma_lo, a->a_lo, B, H, W, Cin, bt, ht, wt) ||
-      !make_map_w(&mw_hi, a->w_hi, N, Ktot, p.n_chunk) || !make_map_w(&mw_lo, a->w_lo, N, Ktot, p.n_chunk))
+  const int Ktot = a->taps * p.kblocks_per_tap * bk;          // weights: every tap padded to whole k-blocks
+  if (!make_map_act(&ma_hi, a->a_hi, B, H, W, Cin, bt, ht, wt, es) || !make_map_act(&ma_lo, a->a_lo, B, H, W, Cin, bt, ht, wt, es) ||
+      !make_map_w(&mw_hi, a->w_hi, N, Ktot, p.n_chunk, es) || !make_map_w(&mw_lo, a->w_lo, N, Ktot, p.n_chunk, es))
     return FLOWK_ERR_ARG;
   if (p.chain) {
-    if (!make_map_w(&mw2_hi, a->w2_hi, p.n2, N / 2, p.n2_chunk) || !make_map_w(&mw2_lo, a->w2_lo, p.n2, N / 2, p.n2_chunk))
+    if (!make_map_w(&mw2_hi, a->w2_hi, p.n2, N / 2, p.n2_chunk, 4) || !make_map_w(&mw2_lo, a->w2_lo, p.n2, N / 2, p.n2_chunk, 4))
       return FLOWK_ERR_ARG;
   } else {
     mw2_hi = mw_hi;

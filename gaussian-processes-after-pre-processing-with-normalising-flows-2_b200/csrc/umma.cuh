@@ -97,6 +97,21 @@ __device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t desc_a, 
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
       : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate): K = 16 per instruction, twice the tf32 rate per dispatch
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (F16) umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  else umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -169,6 +184,36 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+// kind::f16 descriptor: c=F32 [4,6), a=F16 (0) [7,10), b=F16 (0) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t make_idesc_t(int n) { return F16 ? make_idesc_f16(n) : make_idesc(n); }
+
+// x = hi + lo with both parts fp16 (11 significant bits each, the same as TF32, so the split is as accurate as the
+// TF32 one while |x| < 65504 and lo stays above fp16's subnormal spacing 2^-24; conversions saturate instead of
+// overflowing to inf).  Returned as raw 16-bit patterns.
+__device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) {
+  unsigned short h, l;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  float hf;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
+  hi = h;
+  lo = l;
+}
+// four consecutive elements -> 8-byte stores into the hi / lo arrays (element offset `o`, o % 4 == 0)
+__device__ __forceinline__ void store_hilo4_f16(float* out_hi, float* out_lo, size_t o, const float* v) {
+  unsigned short h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_f16(v[i], h[i], l[i]);
+  uint2 hv = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+  uint2 lv = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+  *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(out_hi) + o) = hv;
+  *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(out_lo) + o) = lv;
+}
+
 // x = hi + lo with BOTH parts exactly representable in TF32 (round-to-nearest): the tensor core merely truncates
 // its fp32 containers, which would otherwise bias every product by up to 2^-10 of the lo term.
 __device__ __forceinline__ float rna_tf32(float x) {
@@ -177,6 +222,18 @@ __device__ __forceinline__ float rna_tf32(float x) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = rna_tf32(x);
   lo = rna_tf32(x - hi);
+}
+__device__ __forceinline__ void store_hilo4_tf32(float* out_hi, float* out_lo, size_t o, const float* v) {
+  float h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_tf32(v[i], h[i], l[i]);
+  *reinterpret_cast<float4*>(out_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(out_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+}
+template <bool F16>
+__device__ __forceinline__ void store_hilo4(float* out_hi, float* out_lo, size_t o, const float* v) {
+  if (F16) store_hilo4_f16(out_hi, out_lo, o, v);
+  else store_hilo4_tf32(out_hi, out_lo, o, v);
 }
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

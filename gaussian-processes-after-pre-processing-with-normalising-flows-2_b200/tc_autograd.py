@@ -103,7 +103,19 @@ def linear_supported(x, w):
     if not (ENABLED and x.is_cuda and x.dtype == torch.float32):
         return False
     m = x.numel() // x.shape[-1]
-    return m % 128 == 0 and w.shape[0] % 4 == 0 and w.shape[1] % 32 == 0 and x.shape[-1] == w.shape[1]
+    return m % 16 == 0 and w.shape[0] % 4 == 0 and w.shape[1] % 32 == 0 and x.shape[-1] == w.shape[1]
+
+
+def _rows_as_images(m):
+    """[m, K] rows as the (B, H, W) "image" grid flowk_conv_gemm tiles over (taps = 1: positions are independent): whole
+    128-row tiles when m % 128 == 0, else images of gcd(m, 128) rows (the TMA unit zero-fills the tile's missing images)."""
+    if m % 128 == 0:
+        return m // 128, 8, 16
+    hw = 128
+    while m % hw:
+        hw //= 2
+    w = min(hw, 16)
+    return m // hw, hw // w, w
 
 
 def _rows_gemm(a, wmat, bias, n):
@@ -112,7 +124,7 @@ def _rows_gemm(a, wmat, bias, n):
     a_hi, a_lo = tc.split_rows(a.contiguous())
     w_hi, w_lo = tc.split_hilo(wmat)
     y = torch.empty(m, n, device=a.device, dtype=torch.float32)
-    tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, m // 128, 8, 16, k, n, 1, tc.PRE_BIAS, tc.OUT_F32, bias=bias, out_f32=y, split_k=True)
+    tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, *_rows_as_images(m), k, n, 1, tc.PRE_BIAS, tc.OUT_F32, bias=bias, out_f32=y, split_k=True)
     return y
 
 
@@ -416,7 +428,7 @@ class _WNLinearFn(torch.autograd.Function):
             norm, w, fwd, dg = _wn_operands(vd, gd, k, n, want_w=not tc_dgrad, want_dg=tc_dgrad)
         a_hi, a_lo = tc.split_rows(x2)
         y = torch.empty(x2.shape[0], n, device=x.device, dtype=torch.float32)
-        tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], x2.shape[0] // 128, 8, 16, k, n, 1, tc.PRE_BIAS, tc.OUT_F32,
+        tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], *_rows_as_images(x2.shape[0]), k, n, 1, tc.PRE_BIAS, tc.OUT_F32,
                      bias=None if bias is None else bias.detach().contiguous(), out_f32=y, split_k=True)
         ctx.save_for_backward(x2, vd, gd, norm, dg if tc_dgrad else w)
         ctx.tc_dgrad, ctx.has_bias, ctx.shape = tc_dgrad, bias is not None, shape
@@ -443,7 +455,7 @@ class _WNLinearFn(torch.autograd.Function):
             if ctx.tc_dgrad:
                 g_hi, g_lo = tc.split_rows(g2)
                 gx = torch.empty(g2.shape[0], k, device=g2.device, dtype=torch.float32)
-                tc.conv_gemm(g_hi, g_lo, wd[0], wd[1], g2.shape[0] // 128, 8, 16, n, k, 1, tc.PRE_BIAS, tc.OUT_F32,
+                tc.conv_gemm(g_hi, g_lo, wd[0], wd[1], *_rows_as_images(g2.shape[0]), n, k, 1, tc.PRE_BIAS, tc.OUT_F32,
                              out_f32=gx, split_k=True)
                 gx = gx.view(ctx.shape)
             else:

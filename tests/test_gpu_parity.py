@@ -178,7 +178,7 @@ def test_fused_actnorm_invconv_vs_oracle(F, allow_library, C, H, W, B):
 # ---------------------------------------------------------------------------------------------
 # affine coupling
 # ---------------------------------------------------------------------------------------------
-def test_affine_golden(F, golden):
+def test_affine_golden(F, golden, allow_library):       # 6x6 maps: no 128-row tiling
     g = golden("affine")
     m = F.ac.AffineCoupling(12, 12, 16).to(dev())
     m.load_state_dict({k[len("coupling."):]: v for k, v in g.sd.items()})
@@ -710,8 +710,9 @@ def _initialised_model(F, coupling, image, L, K, hidden, B, seed, **kw):
     model.train()
     with torch.no_grad():
         model(x.to(dev()), noise=noise.to(dev()))            # ActNorm data-dependent init (first training batch)
+        std = 0.02 if hidden <= 96 else 0.005                # wide nets: keep the (2304-term) output sums O(0.1)
         for p in model.parameters():                         # move the zero-initialised output convs off zero
-            p.add_((torch.randn(p.shape, generator=gen) * 0.02).to(p.device))
+            p.add_((torch.randn(p.shape, generator=gen) * std).to(p.device))
     return model, x, noise
 
 
@@ -831,7 +832,7 @@ def test_eval_caches_follow_raw_pointer_updates(F, no_library):
         model.eval()
         with torch.no_grad():
             _, nll0, _ = model(xd, noise=nd)                    # fills every derived-weight cache
-        opt = FusedAdamax(model.parameters(), lr=0.05)
+        opt = FusedAdamax(model.parameters(), lr=0.004)
         gen = torch.Generator().manual_seed(9)
         for _ in range(3):
             for p in model.parameters():
@@ -844,5 +845,6 @@ def test_eval_caches_follow_raw_pointer_updates(F, no_library):
         clone.eval()
         with torch.no_grad():
             _, nll2, _ = clone(xd, noise=nd)
-        assert float((nll1 - nll0).abs().max()) > 1e-2, "the update must change the model output"
+        assert torch.isfinite(nll1).all() and torch.isfinite(nll2).all()
+        assert float((nll1 - nll0).abs().max()) > 1e-3, "the update must change the model output"
         assert float((nll1 - nll2).abs().max()) <= 1e-5 * max(1.0, float(nll2.abs().max())), coupling
