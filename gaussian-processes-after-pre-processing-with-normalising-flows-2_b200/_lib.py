@@ -43,6 +43,9 @@ SIGNATURES = {
     "flowk_conv_gemm": ([ctypes.c_void_p, _st], _i),
     "flowk_nchw_to_nhwc_hilo": ([_fp, ctypes.c_longlong, _i, _i, _i, _i, _fp, _fp, _st], _i),
     "flowk_split_hilo": ([_fp, _fp, _fp, ctypes.c_longlong, _st], _i),
+    "flowk_nchw_to_nhwc_hilo_f16": ([_fp, ctypes.c_longlong, _i, _i, _i, _i, _fp, _fp, _st], _i),
+    "flowk_split_hilo_f16": ([_fp, _fp, _fp, ctypes.c_longlong, ctypes.c_float, _st], _i),
+    "flowk_attention_f16": ([_fp, _fp, _fp, _i, _i, _i, _i, _st], _i),
     "flowk_attention": ([_fp, _fp, _fp, _i, _i, _i, _i, _st], _i),
     "flowk_concat_elu_fwd": ([_fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
     "flowk_concat_elu_bwd": ([_fp, _fp, _fp, _fp, ctypes.c_longlong, _i, ctypes.c_longlong, _st], _i),
@@ -78,7 +81,7 @@ class ConvGemmArgs(ctypes.Structure):
                  "out_f32", "out_hi", "out_lo", "out_nchw", "status", "trace")] + \
                [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")] + \
                [(n, ctypes.c_void_p) for n in ("w2_hi", "w2_lo", "out2_f32")] + [("N2", ctypes.c_int)] + \
-               [("splitk_ws", ctypes.c_void_p)]
+               [("splitk_ws", ctypes.c_void_p), ("operand_format", ctypes.c_int), ("acc_scale", ctypes.c_float)]
 
 
 class WnJob(ctypes.Structure):
@@ -92,6 +95,7 @@ class AdamaxChunk(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("p", "g", "m", "u")] + [("n", ctypes.c_longlong)]
 
 
+OPERAND_TF32, OPERAND_F16 = 0, 1
 PRE_BIAS, PRE_GLU_RES_LN = 0, 1
 OUT_F32, OUT_HILO, OUT_HILO_POS, OUT_HILO_CELU, OUT_NCHW, OUT_HILO_RELU = 1, 2, 4, 8, 16, 32
 
@@ -105,6 +109,7 @@ DIMS = {
     "flowk_mixlogcdf_fwd": slice(7, 10), "flowk_mixlogcdf_inv": slice(7, 10), "flowk_mixlogcdf_bwd": slice(8, 11),
     "flowk_mixture_log_cdf": slice(5, 8), "flowk_mixture_log_pdf": slice(5, 8), "flowk_mixture_inv_cdf": slice(5, 8),
     "flowk_nchw_to_nhwc_hilo": slice(2, 6), "flowk_split_hilo": slice(3, 4), "flowk_attention": slice(3, 7),
+    "flowk_nchw_to_nhwc_hilo_f16": slice(2, 6), "flowk_split_hilo_f16": slice(3, 4), "flowk_attention_f16": slice(3, 7),
 }
 
 

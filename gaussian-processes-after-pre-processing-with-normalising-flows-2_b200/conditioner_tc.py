@@ -12,10 +12,14 @@ in_conv -> 10 x ConvAttnBlock -> out_conv) as a chain of `flowk_conv_gemm` launc
 Every nonlinearity lives in a GEMM epilogue, so a block is 4 GEMM launches + attention.  Weight-normalised,
 re-laid-out, hi/lo-split weights are cached per parameter version.
 """
+import os
+
 import torch
 
 from . import _lib, tc
 
+F16 = os.environ.get("FLOWK_F16", "1") != "0"   # operand format of the inference chain: fp16 (hi, lo) pairs (tcgen05
+                    # kind::f16: half the operand bytes, twice the MMA rate, same 22-bit accuracy) or TF32 pairs ("0")
 ENABLED = True      # set False to force the torch/cuDNN conditioner (used by tests to A/B the two paths)
 CHAIN = False       # gate -> in_proj fused into one launch (works, tested; measured no faster than two PDL launches: the
                     # second GEMM's weights cannot be prefetched for lack of shared memory) - off by default
@@ -48,11 +52,26 @@ class _Cache:
         return self.value
 
 
+def _weight_operand(w):
+    """(w_hi, w_lo, acc_scale) of a conv / linear weight in the chain's operand format."""
+    if F16:
+        return tc.conv_weight_operand_f16(w)
+    return tc.conv_weight_operand(w) + (None,)
+
+
+def _act_buf(dev, *shape):
+    return torch.empty(*shape, device=dev, dtype=torch.float16 if F16 else torch.float32)
+
+
+def _cin_pad(c):
+    return (c + 7) // 8 * 8 if F16 else (c + 31) // 32 * 32
+
+
 def _wn_operand(core):
-    """(w_hi, w_lo, bias) of a weight-normed conv / linear (`_WeightNormed`)."""
-    w_hi, w_lo = tc.conv_weight_operand(core.normed_weight())
+    """(w_hi, w_lo, bias, acc_scale) of a weight-normed conv / linear (`_WeightNormed`)."""
+    w_hi, w_lo, sc = _weight_operand(core.normed_weight())
     bias = None if core.bias is None else core.bias.detach().contiguous()
-    return w_hi, w_lo, bias
+    return w_hi, w_lo, bias, sc
 
 
 def _nn_operands(nn_module):
@@ -83,81 +102,87 @@ def mixlogcdf_nn_raw(nn_module, x_id, status=None):
     def buf(*shape):
         return torch.empty(*shape, device=dev, dtype=torch.float32)
 
-    cin0 = ops["in"][0].shape[1] // 9
-    a_hi, a_lo = tc.nchw_to_nhwc_hilo(x_id, cin0)
+    def obuf(*shape):                                  # operand (hi or lo) buffer in the chain's format
+        return _act_buf(dev, *shape)
+
+    cin0 = _cin_pad(c)
+    a_hi, a_lo = tc.nchw_to_nhwc_hilo(x_id, cin0, F16)
     x = buf(M, C)
-    nxt_hi, nxt_lo = buf(M, 2 * C), buf(M, 2 * C)
-    w_hi, w_lo, bias = ops["in"]
+    nxt_hi, nxt_lo = obuf(M, 2 * C), obuf(M, 2 * C)
+    w_hi, w_lo, bias, sc = ops["in"]
     tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, cin0, C, 9, tc.PRE_BIAS, tc.OUT_F32 | tc.OUT_HILO_CELU, bias=bias,
-                 out_f32=x, out_hi=nxt_hi, out_lo=nxt_lo, status=status)
+                 out_f32=x, out_hi=nxt_hi, out_lo=nxt_lo, status=status, acc_scale=sc)
     nblocks = len(ops["blocks"])
     for bi, blk in enumerate(ops["blocks"]):
         last = bi == nblocks - 1
         # G1: conv3x3 on concat_elu(x) -> concat_elu(. + bias)
-        c1_hi, c1_lo = buf(M, 2 * C), buf(M, 2 * C)
-        w_hi, w_lo, bias = blk["conv"]
+        c1_hi, c1_lo = obuf(M, 2 * C), obuf(M, 2 * C)
+        w_hi, w_lo, bias, sc = blk["conv"]
         tc.conv_gemm(nxt_hi, nxt_lo, w_hi, w_lo, B, H, W, 2 * C, C, 9, tc.PRE_BIAS, tc.OUT_HILO_CELU, bias=bias,
-                     out_hi=c1_hi, out_lo=c1_lo, status=status)
+                     out_hi=c1_hi, out_lo=c1_lo, status=status, acc_scale=sc)
         # G2: gate 1x1 -> GLU + x -> LayerNorm
-        w_hi, w_lo, bias = blk["gate"]
+        w_hi, w_lo, bias, sc = blk["gate"]
         x1 = buf(M, C)
         has_attn = "in_proj" in blk
         if has_attn:
             pos = nn_module.mid_convs[bi].attn._pos_enc(HW, C, dev).reshape(HW, C).contiguous()
             qkv = buf(M, 3 * C)
-            if CHAIN and tc.chain_supported(C, 3 * C):
+            if CHAIN and not F16 and tc.chain_supported(C, 3 * C):
                 # G2 + G3 in one launch: the normalised rows (+ positional encoding) go from the epilogue into swizzled
                 # shared-memory operand tiles and are multiplied by in_proj's weight in the same CTA
-                w3_hi, w3_lo, _ = blk["in_proj"]
+                w3_hi, w3_lo, _, _ = blk["in_proj"]
                 tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN, tc.OUT_F32, bias=bias,
                              res=x, gamma=blk["ln1"][0], beta=blk["ln1"][1], pos=pos, out_f32=x1, status=status,
                              w2_hi=w3_hi, w2_lo=w3_lo, out2_f32=qkv, n2=3 * C)
             else:
-                p_hi, p_lo = buf(M, C), buf(M, C)
+                p_hi, p_lo = obuf(M, C), obuf(M, C)
                 tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN,
                              tc.OUT_F32 | tc.OUT_HILO_POS, bias=bias, res=x, gamma=blk["ln1"][0], beta=blk["ln1"][1],
-                             pos=pos, out_f32=x1, out_hi=p_hi, out_lo=p_lo, status=status)
+                             pos=pos, out_f32=x1, out_hi=p_hi, out_lo=p_lo, status=status, acc_scale=sc)
                 # G3: in_proj -> (k | v | q)
-                w_hi, w_lo, _ = blk["in_proj"]
+                w_hi, w_lo, _, sc = blk["in_proj"]
                 tc.conv_gemm(p_hi, p_lo, w_hi, w_lo, B, H, W, C, 3 * C, 1, tc.PRE_BIAS, tc.OUT_F32, out_f32=qkv,
-                             status=status)
+                             status=status, acc_scale=sc)
             heads = blk["heads"]
             if tc.attention_supported(HW, C, heads):
-                t_hi, t_lo = tc.attention(qkv, B, HW, C, heads)
+                t_hi, t_lo = tc.attention(qkv, B, HW, C, heads, F16)
             else:                                                     # odd head sizes: library matmuls
                 _lib.library_fallback("attention core (seq %d, head dim %d)" % (HW, C // heads), qkv)
                 d = C // heads
                 t = qkv.view(B, HW, 3, heads, d)
                 k, v, q = (t[:, :, i].permute(0, 2, 1, 3) for i in range(3))
                 att = torch.softmax((q * (d ** -0.5)) @ k.transpose(-1, -2), dim=-1) @ v      # [B, heads, HW, d]
-                t_hi, t_lo = tc.split_rows(att.permute(0, 2, 1, 3).reshape(M, C).contiguous())
+                att = att.permute(0, 2, 1, 3).reshape(M, C).contiguous()
+                t_hi, t_lo = tc.split_rows_f16(att) if F16 else tc.split_rows(att)
             # G4: attention gate -> GLU + x1 -> LayerNorm
-            w_hi, w_lo, bias = blk["attn_gate"]
+            w_hi, w_lo, bias, sc = blk["attn_gate"]
             x2 = buf(M, C)
             if last:
-                nxt_hi, nxt_lo = buf(M, C), buf(M, C)
+                nxt_hi, nxt_lo = obuf(M, C), obuf(M, C)
             else:
-                nxt_hi, nxt_lo = buf(M, 2 * C), buf(M, 2 * C)
+                nxt_hi, nxt_lo = obuf(M, 2 * C), obuf(M, 2 * C)
             tc.conv_gemm(t_hi, t_lo, w_hi, w_lo, B, H, W, C, 2 * C, 1, tc.PRE_GLU_RES_LN,
                          tc.OUT_F32 | (tc.OUT_HILO if last else tc.OUT_HILO_CELU), bias=bias, res=x1,
-                         gamma=blk["ln2"][0], beta=blk["ln2"][1], out_f32=x2, out_hi=nxt_hi, out_lo=nxt_lo, status=status)
+                         gamma=blk["ln2"][0], beta=blk["ln2"][1], out_f32=x2, out_hi=nxt_hi, out_lo=nxt_lo, status=status,
+                         acc_scale=sc)
             x = x2
         else:
             if last:
-                nxt_hi, nxt_lo = buf(M, C), buf(M, C)
+                nxt_hi, nxt_lo = obuf(M, C), obuf(M, C)
             else:
-                nxt_hi, nxt_lo = buf(M, 2 * C), buf(M, 2 * C)
+                nxt_hi, nxt_lo = obuf(M, 2 * C), obuf(M, 2 * C)
             tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN,
                          tc.OUT_F32 | (tc.OUT_HILO if last else tc.OUT_HILO_CELU), bias=bias, res=x,
-                         gamma=blk["ln1"][0], beta=blk["ln1"][1], out_f32=x1, out_hi=nxt_hi, out_lo=nxt_lo, status=status)
+                         gamma=blk["ln1"][0], beta=blk["ln1"][1], out_f32=x1, out_hi=nxt_hi, out_lo=nxt_lo, status=status,
+                         acc_scale=sc)
             x = x1
     if nblocks == 0:                                   # out_conv takes the plain activation
-        nxt_hi, nxt_lo = tc.split_rows(x)
-    w_hi, w_lo, bias = ops["out"]
+        nxt_hi, nxt_lo = tc.split_rows_f16(x) if F16 else tc.split_rows(x)
+    w_hi, w_lo, bias, sc = ops["out"]
     n_out = w_hi.shape[0]
     raw = buf(B, n_out, H, W)
     tc.conv_gemm(nxt_hi, nxt_lo, w_hi, w_lo, B, H, W, C, n_out, 9, tc.PRE_BIAS, tc.OUT_NCHW, bias=bias, out_nchw=raw,
-                 status=status)
+                 status=status, acc_scale=sc)
     return raw
 
 
@@ -167,11 +192,11 @@ def _affine_operands(net):
     ops = []
     for conv in (net.conv1, net.conv2):
         gain = torch.exp(conv.actnorm.logs.detach().reshape(-1))
-        w_hi, w_lo = tc.conv_weight_operand(conv.weight.detach() * gain.view(-1, 1, 1, 1))
-        ops.append((w_hi, w_lo, (conv.actnorm.bias.detach().reshape(-1) * gain).contiguous()))
+        w_hi, w_lo, sc = _weight_operand(conv.weight.detach() * gain.view(-1, 1, 1, 1))
+        ops.append((w_hi, w_lo, (conv.actnorm.bias.detach().reshape(-1) * gain).contiguous(), sc))
     gain = torch.exp(net.conv3.logs.detach().reshape(-1) * net.conv3.logscale_factor)
-    w_hi, w_lo = tc.conv_weight_operand(net.conv3.weight.detach() * gain.view(-1, 1, 1, 1))
-    ops.append((w_hi, w_lo, (net.conv3.bias.detach() * gain).contiguous()))
+    w_hi, w_lo, sc = _weight_operand(net.conv3.weight.detach() * gain.view(-1, 1, 1, 1))
+    ops.append((w_hi, w_lo, (net.conv3.bias.detach() * gain).contiguous(), sc))
     return ops
 
 
@@ -194,15 +219,15 @@ def affine_nn_net(net, z1, status=None):
     def buf(*shape):
         return torch.empty(*shape, device=dev, dtype=torch.float32)
 
-    cin0 = ops[0][0].shape[1] // 9
-    a_hi, a_lo = tc.nchw_to_nhwc_hilo(z1, cin0)
-    h1_hi, h1_lo = buf(M, hidden), buf(M, hidden)
+    cin0 = _cin_pad(c)
+    a_hi, a_lo = tc.nchw_to_nhwc_hilo(z1, cin0, F16)
+    h1_hi, h1_lo = _act_buf(dev, M, hidden), _act_buf(dev, M, hidden)
     tc.conv_gemm(a_hi, a_lo, ops[0][0], ops[0][1], B, H, W, cin0, hidden, 9, tc.PRE_BIAS, tc.OUT_HILO_RELU, bias=ops[0][2],
-                 out_hi=h1_hi, out_lo=h1_lo, status=status)
-    h2_hi, h2_lo = buf(M, hidden), buf(M, hidden)
+                 out_hi=h1_hi, out_lo=h1_lo, status=status, acc_scale=ops[0][3])
+    h2_hi, h2_lo = _act_buf(dev, M, hidden), _act_buf(dev, M, hidden)
     tc.conv_gemm(h1_hi, h1_lo, ops[1][0], ops[1][1], B, H, W, hidden, hidden, 1, tc.PRE_BIAS, tc.OUT_HILO_RELU,
-                 bias=ops[1][2], out_hi=h2_hi, out_lo=h2_lo, status=status)
+                 bias=ops[1][2], out_hi=h2_hi, out_lo=h2_lo, status=status, acc_scale=ops[1][3])
     out = buf(B, n_out, H, W)
     tc.conv_gemm(h2_hi, h2_lo, ops[2][0], ops[2][1], B, H, W, hidden, n_out, 9, tc.PRE_BIAS, tc.OUT_NCHW, bias=ops[2][2],
-                 out_nchw=out, status=status)
+                 out_nchw=out, status=status, acc_scale=ops[2][3])
     return out

@@ -12,9 +12,27 @@
 
 namespace flowk {
 
+// two adjacent output columns -> the (hi, lo) operand arrays: TF32 pairs in fp32 containers, or fp16 pairs (out_f16)
+__device__ __forceinline__ void store_pair(float* out_hi, float* out_lo, size_t off, float v0, float v1, int out_f16) {
+  if (out_f16) {
+    unsigned short h0, l0, h1, l1;
+    split_f16(v0, h0, l0);
+    split_f16(v1, h1, l1);
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned short*>(out_hi) + off) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned short*>(out_lo) + off) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+  } else {
+    const float a0 = __uint_as_float((__float_as_uint(v0) + 0x1000u) & 0xffffe000u);
+    const float a1 = __uint_as_float((__float_as_uint(v1) + 0x1000u) & 0xffffe000u);
+    const float b0 = __uint_as_float((__float_as_uint(v0 - a0) + 0x1000u) & 0xffffe000u);
+    const float b1 = __uint_as_float((__float_as_uint(v1 - a1) + 0x1000u) & 0xffffe000u);
+    *reinterpret_cast<float2*>(out_hi + off) = make_float2(a0, a1);
+    *reinterpret_cast<float2*>(out_lo + off) = make_float2(b0, b1);
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(256, 2) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out_hi,
-                                                        float* __restrict__ out_lo, int HW, int C, int heads,
+                                                        float* __restrict__ out_lo, int out_f16, int HW, int C, int heads,
                                                         int pairs_total, int pairs_per_block, int q_per_block,
                                                         float scale) {
   extern __shared__ __align__(16) float sm[];                  // [pairs_per_block][2][HW][D]
@@ -95,20 +113,9 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const float* __restri
     }
   }
   const float inv = 1.0f / l;
-  float4* oh = reinterpret_cast<float4*>(out_hi + m * C + h * D);
-  float4* ol = reinterpret_cast<float4*>(out_lo + m * C + h * D);
+  const size_t o0 = (size_t)m * C + h * D;
 #pragma unroll
-  for (int i = 0; i < V4; ++i) {
-    float hi[4], lo[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float y = acc[4 * i + u] * inv;
-      hi[u] = __uint_as_float((__float_as_uint(y) + 0x1000u) & 0xffffe000u);
-      lo[u] = __uint_as_float((__float_as_uint(y - hi[u]) + 0x1000u) & 0xffffe000u);
-    }
-    oh[i] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    ol[i] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-  }
+  for (int i = 0; i < D; i += 2) store_pair(out_hi, out_lo, o0 + i, acc[i] * inv, acc[i + 1] * inv, out_f16);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -131,7 +138,7 @@ __device__ __forceinline__ void split_bits(float x, uint32_t& hi, uint32_t& lo) 
 
 template <int D, int NKB>      // NKB key blocks (of 8 keys) per softmax update
 __global__ void __launch_bounds__(256, 2) attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out_hi,
-                                                            float* __restrict__ out_lo, int HW, int C, int heads,
+                                                            float* __restrict__ out_lo, int out_f16, int HW, int C, int heads,
                                                             int pairs_total, int pairs_per_block, int warps_per_pair,
                                                             int key_tile, float scale) {
   extern __shared__ __align__(16) float sm[];                  // [pairs_per_block][Khi,Klo,Vhi,Vlo][key_tile][D + 4]
@@ -274,25 +281,13 @@ __global__ void __launch_bounds__(256, 2) attention_mma_kernel(const float* __re
 #pragma unroll
   for (int nb = 0; nb < KS; ++nb) {
     const int col = h * D + nb * 8 + 2 * t;
-    if (q_lo_ok) {
-      const size_t off = (size_t)(b * HW + q0 + g) * C + col;
-      uint32_t h0, l0, h1, l1;
-      split_bits(o[nb][0] * i_lo, h0, l0); split_bits(o[nb][1] * i_lo, h1, l1);
-      *reinterpret_cast<float2*>(out_hi + off) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
-      *reinterpret_cast<float2*>(out_lo + off) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
-    }
-    if (q_hi_ok) {
-      const size_t off = (size_t)(b * HW + q0 + g + 8) * C + col;
-      uint32_t h0, l0, h1, l1;
-      split_bits(o[nb][2] * i_hi, h0, l0); split_bits(o[nb][3] * i_hi, h1, l1);
-      *reinterpret_cast<float2*>(out_hi + off) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
-      *reinterpret_cast<float2*>(out_lo + off) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
-    }
+    if (q_lo_ok) store_pair(out_hi, out_lo, (size_t)(b * HW + q0 + g) * C + col, o[nb][0] * i_lo, o[nb][1] * i_lo, out_f16);
+    if (q_hi_ok) store_pair(out_hi, out_lo, (size_t)(b * HW + q0 + g + 8) * C + col, o[nb][2] * i_hi, o[nb][3] * i_hi, out_f16);
   }
 }
 
 template <int D>
-static int launch_attention_mma(const float* qkv, float* out_hi, float* out_lo, int B, int HW, int C, int heads,
+static int launch_attention_mma(const float* qkv, float* out_hi, float* out_lo, int out_f16, int B, int HW, int C, int heads,
                                 cudaStream_t st) {
   const int pairs = B * heads;
   // 8 warps (128 queries) per CTA and 128-key tiles: ~21 K registers and <= 57 KB of shared memory per CTA, so three
@@ -311,19 +306,19 @@ static int launch_attention_mma(const float* qkv, float* out_hi, float* out_lo, 
   if (HW % 32 == 0) {
     if (smem > 48 * 1024)
       FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FLOWK_CUDA_OK(launch_pdl(attention_mma_kernel<D, 4>, grid, dim3(threads), smem, st, qkv, out_hi, out_lo, HW, C, heads,
+    FLOWK_CUDA_OK(launch_pdl(attention_mma_kernel<D, 4>, grid, dim3(threads), smem, st, qkv, out_hi, out_lo, out_f16, HW, C, heads,
                              pairs, pairs_per_block, warps_per_pair, key_tile, scale));
   } else {
     if (smem > 48 * 1024)
       FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_mma_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FLOWK_CUDA_OK(launch_pdl(attention_mma_kernel<D, 1>, grid, dim3(threads), smem, st, qkv, out_hi, out_lo, HW, C, heads,
+    FLOWK_CUDA_OK(launch_pdl(attention_mma_kernel<D, 1>, grid, dim3(threads), smem, st, qkv, out_hi, out_lo, out_f16, HW, C, heads,
                              pairs, pairs_per_block, warps_per_pair, key_tile, scale));
   }
   return launch_status();
 }
 
 template <int D>
-static int launch_attention(const float* qkv, float* out_hi, float* out_lo, int B, int HW, int C, int heads,
+static int launch_attention(const float* qkv, float* out_hi, float* out_lo, int out_f16, int B, int HW, int C, int heads,
                             cudaStream_t st) {
   const int pairs = B * heads;
   int q_per_block = HW < 256 ? HW : 256;
@@ -335,7 +330,7 @@ static int launch_attention(const float* qkv, float* out_hi, float* out_lo, int 
     FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((pairs + pairs_per_block - 1) / pairs_per_block, (HW + q_per_block - 1) / q_per_block);
   FLOWK_CUDA_OK(launch_pdl(attention_kernel<D>, grid, dim3(q_per_block * pairs_per_block), smem, st, qkv, out_hi, out_lo,
-                           HW, C, heads, pairs, pairs_per_block, q_per_block, 1.0f / sqrtf((float)D)));
+                           out_f16, HW, C, heads, pairs, pairs_per_block, q_per_block, 1.0f / sqrtf((float)D)));
   return launch_status();
 }
 
@@ -343,8 +338,8 @@ static int launch_attention(const float* qkv, float* out_hi, float* out_lo, int 
 
 using namespace flowk;
 
-extern "C" int flowk_attention(const float* qkv, float* out_hi, float* out_lo, int B, int HW, int C, int heads,
-                               flowk_stream_t stream) {
+static int attention_impl(const float* qkv, float* out_hi, float* out_lo, int out_f16, int B, int HW, int C, int heads,
+                          flowk_stream_t stream) {
   if (B < 0 || HW < 1 || C < 1 || heads < 1 || C % heads) return FLOWK_ERR_SHAPE;
   if (B == 0) return FLOWK_OK;
   if (!qkv || !out_hi || !out_lo) return FLOWK_ERR_ARG;
@@ -353,22 +348,33 @@ extern "C" int flowk_attention(const float* qkv, float* out_hi, float* out_lo, i
   if (use_mma < 0) { const char* e = getenv("FLOWK_ATTENTION_MMA"); use_mma = (e && e[0] == '0') ? 0 : 1; }
   if (use_mma && HW % 8 == 0) {
     switch (C / heads) {
-      case 8: return launch_attention_mma<8>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-      case 16: return launch_attention_mma<16>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-      case 24: return launch_attention_mma<24>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-      case 32: return launch_attention_mma<32>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-      case 40: return launch_attention_mma<40>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-      case 64: return launch_attention_mma<64>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
+      case 8: return launch_attention_mma<8>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+      case 16: return launch_attention_mma<16>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+      case 24: return launch_attention_mma<24>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+      case 32: return launch_attention_mma<32>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+      case 40: return launch_attention_mma<40>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+      case 64: return launch_attention_mma<64>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
       default: return FLOWK_ERR_SHAPE;
     }
   }
   switch (C / heads) {
-    case 8: return launch_attention<8>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-    case 16: return launch_attention<16>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-    case 24: return launch_attention<24>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-    case 32: return launch_attention<32>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-    case 40: return launch_attention<40>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
-    case 64: return launch_attention<64>(qkv, out_hi, out_lo, B, HW, C, heads, stream);
+    case 8: return launch_attention<8>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+    case 16: return launch_attention<16>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+    case 24: return launch_attention<24>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+    case 32: return launch_attention<32>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+    case 40: return launch_attention<40>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
+    case 64: return launch_attention<64>(qkv, out_hi, out_lo, out_f16, B, HW, C, heads, stream);
     default: return FLOWK_ERR_SHAPE;
   }
+}
+
+extern "C" int flowk_attention(const float* qkv, float* out_hi, float* out_lo, int B, int HW, int C, int heads,
+                               flowk_stream_t stream) {
+  return attention_impl(qkv, out_hi, out_lo, 0, B, HW, C, heads, stream);
+}
+
+extern "C" int flowk_attention_f16(const float* qkv, void* out_hi, void* out_lo, int B, int HW, int C, int heads,
+                                   flowk_stream_t stream) {
+  if (C % 2) return FLOWK_ERR_SHAPE;
+  return attention_impl(qkv, reinterpret_cast<float*>(out_hi), reinterpret_cast<float*>(out_lo), 1, B, HW, C, heads, stream);
 }

@@ -60,6 +60,18 @@ __device__ __forceinline__ float rcp_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// x = hi + lo with both parts fp16 (11 significant bits each, the same as TF32, so the split is as accurate as the
+// TF32 one while |x| < 65504 and lo stays above fp16's subnormal spacing 2^-24; conversions saturate instead of
+// overflowing to inf).  Returned as raw 16-bit patterns.
+__device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) {
+  unsigned short h, l;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  float hf;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
+  hi = h;
+  lo = l;
+}
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

@@ -917,26 +917,27 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   }
 
   dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, n_tiles, p.ksplit);
-  static size_t smem_set[3] = {0, 0, 0};               // largest dynamic-smem opt-in requested so far, per variant
-  const int variant = a->pre == PRE_GLU_RES_LN ? (N / 2 > 128 ? 2 : 1) : 0;
-  const bool need_attr = smem_bytes > smem_set[variant];
-  if (need_attr) smem_set[variant] = smem_bytes;
+  // one launch helper per (epilogue, LayerNorm width, operand format) instantiation; each remembers the largest dynamic
+  // shared-memory opt-in it has requested
+#define FLOWK_LAUNCH_GEMM(PRE_, NV_, F16_)                                                                         \
+  do {                                                                                                              \
+    static size_t smem_set = 0;                                                                                     \
+    if (smem_bytes > smem_set) {                                                                                    \
+      FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_, NV_, F16_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem_bytes));                                                         \
+      smem_set = smem_bytes;                                                                                        \
+    }                                                                                                               \
+    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_, NV_, F16_>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, \
+                             mw_hi, mw_lo, mw2_hi, mw2_lo, p));                                                     \
+  } while (0)
   if (a->pre == PRE_GLU_RES_LN && N / 2 > 128) {
-    if (need_attr)
-    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes));
-    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 2>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));
+    if (f16) FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 2, true); else FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 2, false);
   } else if (a->pre == PRE_GLU_RES_LN) {
-    if (need_attr)
-    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes));
-    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_GLU_RES_LN, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));
+    if (f16) FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 1, true); else FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 1, false);
   } else {
-    if (need_attr)
-    FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_BIAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes));
-    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_BIAS, 1>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));
+    if (f16) FLOWK_LAUNCH_GEMM(PRE_BIAS, 1, true); else FLOWK_LAUNCH_GEMM(PRE_BIAS, 1, false);
   }
+#undef FLOWK_LAUNCH_GEMM
   if (p.ksplit > 1) {
     FLOWK_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3((p.M + 31) / 32, (N + 31) / 32), dim3(256), 0, stream, (const float*)a->splitk_ws, a->bias,
                              a->out_mask == OUT_F32 ? a->out_f32 : (float*)nullptr,
@@ -951,8 +952,19 @@ extern "C" int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, i
   if (B == 0) return FLOWK_OK;
   if (!x || !hi || !lo) return FLOWK_ERR_ARG;
   if (B > 65535) return FLOWK_ERR_SHAPE;
-  FLOWK_CUDA_OK(launch_pdl(nchw_to_nhwc_hilo_kernel, dim3((HW + 31) / 32, (C_pad + 31) / 32, B), dim3(256), 0, stream, x,
+  FLOWK_CUDA_OK(launch_pdl(nchw_to_nhwc_hilo_kernel<false>, dim3((HW + 31) / 32, (C_pad + 31) / 32, B), dim3(256), 0, stream, x,
                            batch_stride, C, HW, C_pad, hi, lo));
+  return launch_status();
+}
+
+extern "C" int flowk_nchw_to_nhwc_hilo_f16(const float* x, long long batch_stride, int B, int C, int HW, int C_pad,
+                                           void* hi, void* lo, flowk_stream_t stream) {
+  if (B < 0 || C < 1 || HW < 1 || C_pad < C || C_pad % 8) return FLOWK_ERR_SHAPE;
+  if (B == 0) return FLOWK_OK;
+  if (!x || !hi || !lo) return FLOWK_ERR_ARG;
+  if (B > 65535) return FLOWK_ERR_SHAPE;
+  FLOWK_CUDA_OK(launch_pdl(nchw_to_nhwc_hilo_kernel<true>, dim3((HW + 31) / 32, (C_pad + 31) / 32, B), dim3(256), 0, stream, x,
+                           batch_stride, C, HW, C_pad, reinterpret_cast<float*>(hi), reinterpret_cast<float*>(lo)));
   return launch_status();
 }
 
@@ -961,6 +973,16 @@ extern "C" int flowk_split_hilo(const float* x, float* hi, float* lo, long long 
   if (n == 0) return FLOWK_OK;
   if (!x || !hi || !lo) return FLOWK_ERR_ARG;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  FLOWK_CUDA_OK(launch_pdl(split_hilo_kernel, dim3(blocks), dim3(256), 0, stream, x, hi, lo, (long long)n));
+  FLOWK_CUDA_OK(launch_pdl(split_hilo_kernel<false>, dim3(blocks), dim3(256), 0, stream, x, hi, lo, (long long)n, 1.f));
+  return launch_status();
+}
+
+extern "C" int flowk_split_hilo_f16(const float* x, void* hi, void* lo, long long n, float scale, flowk_stream_t stream) {
+  if (n < 0) return FLOWK_ERR_SHAPE;
+  if (n == 0) return FLOWK_OK;
+  if (!x || !hi || !lo) return FLOWK_ERR_ARG;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  FLOWK_CUDA_OK(launch_pdl(split_hilo_kernel<true>, dim3(blocks), dim3(256), 0, stream, x, reinterpret_cast<float*>(hi),
+                           reinterpret_cast<float*>(lo), (long long)n, scale));
   return launch_status();
 }

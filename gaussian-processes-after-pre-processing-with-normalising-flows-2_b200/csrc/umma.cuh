@@ -191,18 +191,6 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
 template <bool F16>
 __device__ __forceinline__ uint32_t make_idesc_t(int n) { return F16 ? make_idesc_f16(n) : make_idesc(n); }
 
-// x = hi + lo with both parts fp16 (11 significant bits each, the same as TF32, so the split is as accurate as the
-// TF32 one while |x| < 65504 and lo stays above fp16's subnormal spacing 2^-24; conversions saturate instead of
-// overflowing to inf).  Returned as raw 16-bit patterns.
-__device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) {
-  unsigned short h, l;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
-  float hf;
-  asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
-  hi = h;
-  lo = l;
-}
 // four consecutive elements -> 8-byte stores into the hi / lo arrays (element offset `o`, o % 4 == 0)
 __device__ __forceinline__ void store_hilo4_f16(float* out_hi, float* out_lo, size_t o, const float* v) {
   unsigned short h[4], l[4];

@@ -37,19 +37,52 @@ def conv_weight_operand(w, cin_pad=None):
     return split_hilo(wk.reshape(n, kh * kw * cin_pad))
 
 
+def conv_weight_operand_f16(w):
+    """[N, Cin, kh, kw] conv weight (or [N, Cin] linear weight) -> fp16 (hi, lo) pair [N, taps * ceil64(Cin)] in (tap, c)
+    order for FLOWK_OPERAND_F16, pre-scaled by a power of two s so that max|w s| lies in [2^14, 2^15): the lo part then
+    keeps its 11 bits clear of fp16's subnormal range.  Returns (hi, lo, 1 / s); 1 / s goes to conv_gemm(acc_scale=)."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    n, cin, kh, kw = w.shape
+    cin_pad = (cin + 63) // 64 * 64
+    wk = w.permute(0, 2, 3, 1).float()
+    if cin_pad != cin:
+        wk = torch.nn.functional.pad(wk, (0, cin_pad - cin))
+    wk = wk.reshape(n, kh * kw * cin_pad).contiguous()
+    amax = float(wk.abs().max()) if wk.numel() else 0.0          # (host sync: weight preparation is cached per version)
+    import math
+    e = 14 - math.floor(math.log2(amax)) if amax > 0 and math.isfinite(amax) else 0
+    e = max(-14, min(24, e))
+    hi, lo = split_rows_f16(wk, 2.0 ** e)
+    return hi, lo, 2.0 ** (-e)
+
+
+def split_rows_f16(x, scale=1.0):
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    _lib.call("flowk_split_hilo_f16", x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), float(scale), _stream())
+    return hi, lo
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
 
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias=None, res=None, gamma=None,
               beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None, trace=None,
-              w2_hi=None, w2_lo=None, out2_f32=None, n2=0, split_k=False):
-    """`split_k=True` (training path: one stream, kernel latency matters) lends the kernel a workspace so that layers
+              w2_hi=None, w2_lo=None, out2_f32=None, n2=0, split_k=False, acc_scale=None):
+    """The operand format follows the tensors: fp32 tensors = TF32 pairs (FLOWK_OPERAND_TF32), fp16 tensors = fp16 pairs
+    (FLOWK_OPERAND_F16, inference; `acc_scale` undoes the weights' power-of-two pre-scaling).
+    `split_k=True` (training path: one stream, kernel latency matters) lends the kernel a workspace so that layers
     with few 128-row tiles and a long K loop are shared by several CTAs per output tile."""
     _lib.check_device(a_hi, "conv_gemm")
     args = _lib.ConvGemmArgs(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), _p(bias), _p(res), _p(gamma), _p(beta), _p(pos),
                              _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status), _p(trace),
-                             B, H, W, Cin, N, taps, pre, out_mask, _p(w2_hi), _p(w2_lo), _p(out2_f32), n2, None)
+                             B, H, W, Cin, N, taps, pre, out_mask, _p(w2_hi), _p(w2_lo), _p(out2_f32), n2, None,
+                             _lib.OPERAND_F16 if a_hi.dtype == torch.float16 else _lib.OPERAND_TF32,
+                             1.0 if acc_scale is None else float(acc_scale))
+    assert a_hi.dtype == a_lo.dtype == w_hi.dtype == w_lo.dtype, "operand pair formats must agree"
+    assert out_hi is None or out_hi.dtype == a_hi.dtype, "out_hi/out_lo are written in the input operand format"
     if split_k:
         slices = _lib.lib.flowk_conv_gemm_splitk_slices(ctypes.addressof(args))
         if slices > 1:
@@ -58,14 +91,14 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias
     _lib.call("flowk_conv_gemm", ctypes.addressof(args), _stream(), meta=(B, H, W, Cin, N, taps, pre))
 
 
-def nchw_to_nhwc_hilo(x, c_pad):
+def nchw_to_nhwc_hilo(x, c_pad, f16=False):
     """x: NCHW view whose (C,H,W) block is contiguous (e.g. a channel slice) -> ([B*HW, c_pad] hi, lo)."""
     b, c, h, w = x.shape
     assert x.stride(3) == 1 and x.stride(2) == w and x.stride(1) == h * w, "channel slice of a contiguous NCHW tensor"
-    hi = torch.empty(b * h * w, c_pad, device=x.device, dtype=torch.float32)
+    hi = torch.empty(b * h * w, c_pad, device=x.device, dtype=torch.float16 if f16 else torch.float32)
     lo = torch.empty_like(hi)
-    _lib.call("flowk_nchw_to_nhwc_hilo", x.data_ptr(), x.stride(0), b, c, h * w, c_pad, hi.data_ptr(), lo.data_ptr(),
-              _stream())
+    _lib.call("flowk_nchw_to_nhwc_hilo_f16" if f16 else "flowk_nchw_to_nhwc_hilo", x.data_ptr(), x.stride(0), b, c, h * w,
+              c_pad, hi.data_ptr(), lo.data_ptr(), _stream())
     return hi, lo
 
 
@@ -76,11 +109,12 @@ def split_rows(x):
     return hi, lo
 
 
-def attention(qkv, B, HW, C, heads):
+def attention(qkv, B, HW, C, heads, f16=False):
     """qkv [B*HW, 3C] (k | v | q) -> (hi, lo) [B*HW, C] of softmax(q k^T / sqrt(d)) v."""
-    hi = torch.empty(B * HW, C, device=qkv.device, dtype=torch.float32)
+    hi = torch.empty(B * HW, C, device=qkv.device, dtype=torch.float16 if f16 else torch.float32)
     lo = torch.empty_like(hi)
-    _lib.call("flowk_attention", qkv.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, HW, C, heads, _stream())
+    _lib.call("flowk_attention_f16" if f16 else "flowk_attention", qkv.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, HW, C,
+              heads, _stream())
     return hi, lo
 
 

@@ -169,7 +169,18 @@ typedef struct flowk_conv_gemm_args {
    * tile, each writing fp32 partial rows here ([slices, B*H*W, N] floats), and a second kernel adds the slices in index
    * order plus the bias into the destination.  Serves the latency of single-stream (training) steps. */
   float* splitk_ws;
+  /* Operand format of a_hi/a_lo/w_hi/w_lo and of the out_hi/out_lo the epilogue writes:
+   *   FLOWK_OPERAND_TF32 (0)  fp32 arrays holding TF32 values (tcgen05 kind::tf32, 32 channels per k-block); Cin % 32 == 0
+   *   FLOWK_OPERAND_F16  (1)  fp16 arrays (the pointers are reinterpreted; tcgen05 kind::f16, 64 channels per k-block):
+   *                           half the operand bytes, twice the MMA rate, the same 11 + 11 significant bits as the TF32
+   *                           pair.  Cin % 8 == 0; the weight rows are [taps * ceil64(Cin)] with every tap zero-padded to
+   *                           whole 64-channel blocks; weights may be pre-scaled by a power of two s (|w s| < 65504) with
+   *                           acc_scale = 1 / s applied to the accumulator before the bias.  Inference only: values
+   *                           must stay below 65504 in magnitude. */
+  int operand_format;
+  float acc_scale;
 } flowk_conv_gemm_args;
+enum { FLOWK_OPERAND_TF32 = 0, FLOWK_OPERAND_F16 = 1 };
 
 int flowk_conv_gemm(const flowk_conv_gemm_args* args, flowk_stream_t stream);
 /* Slices flowk_conv_gemm would use for `args` if args->splitk_ws were non-null (1 = no split-K); no pointer is read. */
@@ -180,6 +191,11 @@ int flowk_nchw_to_nhwc_hilo(const float* x, long long batch_stride, int B, int C
                             float* hi, float* lo, flowk_stream_t stream);
 /* fp32 array -> (hi, lo) operand pair. */
 int flowk_split_hilo(const float* x, float* hi, float* lo, long long n, flowk_stream_t stream);
+/* The same two for FLOWK_OPERAND_F16: hi / lo are fp16 arrays (C_pad % 8 == 0); split_hilo_f16 multiplies by `scale`
+ * (the power-of-two weight pre-scaling) first. */
+int flowk_nchw_to_nhwc_hilo_f16(const float* x, long long batch_stride, int B, int C, int HW, int C_pad,
+                                void* hi, void* lo, flowk_stream_t stream);
+int flowk_split_hilo_f16(const float* x, void* hi, void* lo, long long n, float scale, flowk_stream_t stream);
 
 /* Fused pointwise layers of the Flow++ conditioner (training path), tensors viewed as [outer, channels, inner]
  * (inner = H*W for NCHW / dim 1, inner = 1 for NHWC / last dim):
@@ -300,6 +316,9 @@ int flowk_adamax_step(const flowk_adamax_chunk* chunks_device, int nchunks, cons
  * C/heads in {8,16,24,32,40,64}; HW <= 256 or a multiple of 256. */
 int flowk_attention(const float* qkv, float* out_hi, float* out_lo, int B, int HW, int C, int heads,
                     flowk_stream_t stream);
+/* Same, writing the operand pair as fp16 arrays (FLOWK_OPERAND_F16 input of the gate GEMM). */
+int flowk_attention_f16(const float* qkv, void* out_hi, void* out_lo, int B, int HW, int C, int heads,
+                        flowk_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -19,12 +19,24 @@ def nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous()
 
 
-def run_conv(tc, x, w, bias, taps, out_mask=None, **kw):
-    """x [B,Cin,H,W] (Cin % 32 == 0), w [N,Cin,k,k]; returns dict of outputs."""
+FORMATS = ["tf32", "f16"]
+
+
+def run_conv(tc, x, w, bias, taps, out_mask=None, fmt="tf32", **kw):
+    """x [B,Cin,H,W] (Cin % 32 == 0 for tf32 pairs, % 8 for fp16 pairs), w [N,Cin,k,k]; returns dict of outputs (the
+    hi / lo operand outputs are returned summed in fp32 under "out_hilo", raw under "out_hi" / "out_lo")."""
     B, Cin, H, W = x.shape
     N = w.shape[0]
-    a_hi, a_lo = tc.split_hilo(nhwc(x).reshape(B * H * W, Cin))
-    w_hi, w_lo = tc.conv_weight_operand(w)
+    rows = nhwc(x).reshape(B * H * W, Cin)
+    odt = torch.float32
+    if fmt == "f16":
+        a_hi, a_lo = tc.split_rows_f16(rows)
+        w_hi, w_lo, sc = tc.conv_weight_operand_f16(w)
+        kw = dict(kw, acc_scale=sc)
+        odt = torch.float16
+    else:
+        a_hi, a_lo = tc.split_hilo(rows)
+        w_hi, w_lo = tc.conv_weight_operand(w)
     status = torch.zeros(1, dtype=torch.int32, device=x.device)
     outs = {"status": status}
     mask = out_mask if out_mask is not None else tc.OUT_F32
@@ -33,16 +45,18 @@ def run_conv(tc, x, w, bias, taps, out_mask=None, **kw):
     if mask & tc.OUT_F32:
         outs["out_f32"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
     if mask & (tc.OUT_HILO | tc.OUT_HILO_POS | tc.OUT_HILO_RELU):
-        outs["out_hi"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
-        outs["out_lo"] = torch.full((B * H * W, nout), float("nan"), device=x.device)
+        outs["out_hi"] = torch.full((B * H * W, nout), float("nan"), device=x.device, dtype=odt)
+        outs["out_lo"] = torch.full((B * H * W, nout), float("nan"), device=x.device, dtype=odt)
     if mask & tc.OUT_HILO_CELU:
-        outs["out_hi"] = torch.full((B * H * W, 2 * nout), float("nan"), device=x.device)
-        outs["out_lo"] = torch.full((B * H * W, 2 * nout), float("nan"), device=x.device)
+        outs["out_hi"] = torch.full((B * H * W, 2 * nout), float("nan"), device=x.device, dtype=odt)
+        outs["out_lo"] = torch.full((B * H * W, 2 * nout), float("nan"), device=x.device, dtype=odt)
     if mask & tc.OUT_NCHW:
         outs["out_nchw"] = torch.full((B, N, H, W), float("nan"), device=x.device)
     tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, mask, bias=bias, **kw, **outs)
     torch.cuda.synchronize()
     assert int(status) == 0, "barrier wait timed out inside the kernel"
+    if "out_hi" in outs:
+        outs["out_hilo"] = outs["out_hi"].float() + outs["out_lo"].float()
     return outs
 
 
@@ -50,10 +64,11 @@ def rel_err(got, ref):
     return float((got.double() - ref).abs().max() / ref.abs().max())
 
 
+@pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("B,Cin,H,W,N,taps", [(2, 32, 8, 16, 16, 1), (4, 64, 16, 16, 96, 1), (64, 96, 16, 16, 288, 1),
                                               (3, 32, 16, 16, 96, 9), (64, 192, 16, 16, 96, 9), (64, 96, 8, 8, 1176, 9),
                                               (19, 96, 4, 4, 2352, 9), (5, 32, 2, 2, 24, 9), (2, 64, 32, 32, 48, 9)])
-def test_conv_gemm_matches_fp64(tc, B, Cin, H, W, N, taps):
+def test_conv_gemm_matches_fp64(tc, fmt, B, Cin, H, W, N, taps):
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(B * 1000 + N)
     k = 3 if taps == 9 else 1
@@ -61,20 +76,22 @@ def test_conv_gemm_matches_fp64(tc, B, Cin, H, W, N, taps):
     w = (torch.randn(N, Cin, k, k, generator=g) / (Cin * taps) ** 0.5).to(dev)
     bias = torch.randn(N, generator=g).to(dev)
     ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)
-    outs = run_conv(tc, x, w, bias, taps, out_mask=tc.OUT_F32 | tc.OUT_NCHW | tc.OUT_HILO_CELU)
+    outs = run_conv(tc, x, w, bias, taps, out_mask=tc.OUT_F32 | tc.OUT_NCHW | tc.OUT_HILO_CELU, fmt=fmt)
     got = outs["out_f32"].view(B, H, W, N).permute(0, 3, 1, 2)
     torch.backends.cudnn.allow_tf32 = False
     lib32 = rel_err(F.conv2d(x, w, bias, padding=k // 2), ref)        # what the fp32 library conv achieves
-    print("K=%d  tcgen05 3xTF32 rel err %.2e   cuDNN fp32 rel err %.2e" % (Cin * taps, rel_err(got, ref), lib32))
+    print("K=%d  tcgen05 %s-pair rel err %.2e   cuDNN fp32 rel err %.2e" % (Cin * taps, fmt, rel_err(got, ref), lib32))
     assert rel_err(got, ref) < max(6e-6, 4 * lib32), (rel_err(got, ref), lib32)
     assert rel_err(outs["out_nchw"], ref) < max(6e-6, 4 * lib32)
     celu = F.elu(torch.cat((nhwc(ref), -nhwc(ref)), dim=-1)).reshape(B * H * W, 2 * N)
-    assert rel_err(outs["out_hi"] + outs["out_lo"], celu) < max(6e-6, 4 * lib32)
-    assert int((outs["out_hi"].view(torch.int32) & 8191).abs().max()) == 0      # hi is exactly TF32-representable
+    assert rel_err(outs["out_hilo"], celu) < max(6e-6, 4 * lib32)
+    if fmt == "tf32":
+        assert int((outs["out_hi"].view(torch.int32) & 8191).abs().max()) == 0      # hi is exactly TF32-representable
 
 
+@pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("B,C,H,W", [(64, 96, 16, 16), (8, 96, 4, 4), (3, 32, 8, 8), (2, 160, 16, 16)])
-def test_glu_residual_layernorm_epilogue(tc, B, C, H, W):
+def test_glu_residual_layernorm_epilogue(tc, fmt, B, C, H, W):
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(B + C)
     x = torch.randn(B, C, H, W, generator=g).to(dev)
@@ -88,10 +105,10 @@ def test_glu_residual_layernorm_epilogue(tc, B, C, H, W):
     glu = y[:, :C] * torch.sigmoid(y[:, C:]) + res.double()
     ref = F.layer_norm(glu, (C,), gamma.double(), beta.double())
     outs = run_conv(tc, x, w, bias, 1, out_mask=tc.OUT_F32 | tc.OUT_HILO_POS, pre=tc.PRE_GLU_RES_LN, res=res,
-                    gamma=gamma, beta=beta, pos=pos)
+                    gamma=gamma, beta=beta, pos=pos, fmt=fmt)
     assert rel_err(outs["out_f32"], ref) < 1e-5, rel_err(outs["out_f32"], ref)
     ref_pos = ref + pos.double().repeat(B, 1)
-    assert rel_err(outs["out_hi"] + outs["out_lo"], ref_pos) < 1e-5
+    assert rel_err(outs["out_hilo"], ref_pos) < 1e-5
 
 
 @pytest.mark.parametrize("c,C,H,W,B,blocks", [(6, 96, 16, 16, 64, 2), (12, 96, 8, 8, 64, 2), (24, 96, 4, 4, 64, 2),
@@ -125,17 +142,22 @@ def test_conditioner_tc_matches_torch_path(tc, c, C, H, W, B, blocks):
 
 @pytest.mark.parametrize("B,HW,C,heads", [(64, 256, 96, 4), (64, 64, 96, 4), (64, 16, 96, 4), (3, 1024, 64, 4),
                                           (5, 4, 32, 4), (2, 256, 160, 4)])
-def test_attention_matches_fp64(tc, B, HW, C, heads):
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_attention_matches_fp64(tc, fmt, B, HW, C, heads):
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(B + HW)
     qkv = torch.randn(B * HW, 3 * C, generator=g).to(dev)
-    hi, lo = tc.attention(qkv, B, HW, C, heads)
+    hi, lo = tc.attention(qkv, B, HW, C, heads, fmt == "f16")
+    if fmt == "f16":
+        assert hi.dtype == torch.float16
+        hi, lo = hi.float(), lo.float()
     d = C // heads
     t = qkv.double().view(B, HW, 3, heads, d)
     k, v, q = (t[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     ref = (torch.softmax((q * d ** -0.5) @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * HW, C)
     assert rel_err(hi + lo, ref) < 2e-5      # fp32-accumulate order over up to 1024 keys; the conditioner budget is 1e-4
-    assert int((hi.view(torch.int32) & 8191).abs().max()) == 0
+    if fmt == "tf32":
+        assert int((hi.view(torch.int32) & 8191).abs().max()) == 0
 
 
 @pytest.mark.parametrize("c,hidden,H,W,B", [(6, 64, 16, 16, 32), (12, 256, 8, 8, 128), (24, 256, 4, 4, 128),
@@ -209,7 +231,8 @@ def test_wide_linear_many_rows(tc):
     assert rel_err(outs["out_f32"], ref) < 1e-5
 
 
-def test_conv_gemm_random_configuration_sweep(tc):
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_conv_gemm_random_configuration_sweep(tc, fmt):
     """Host-side tiling decisions (N tiles / chunks, dx-split, stage counts, epilogue staging) over a seeded sweep of
     layer shapes; every configuration must either be refused with a shape error or match the fp64 convolution."""
     import random
@@ -219,7 +242,7 @@ def test_conv_gemm_random_configuration_sweep(tc):
     for trial in range(28):
         H, W = rnd.choice([(2, 2), (4, 4), (8, 8), (16, 16), (32, 32), (8, 16), (4, 32)])
         B = rnd.choice([1, 3, 16, 64, 130]) if H * W <= 256 else rnd.choice([1, 3, 9])
-        Cin = rnd.choice([32, 64, 96, 160, 192, 256])
+        Cin = rnd.choice([32, 64, 96, 160, 192, 256] + ([8, 24, 40] if fmt == "f16" else []))
         taps = rnd.choice([1, 9])
         pre = rnd.choice([tc.PRE_BIAS, tc.PRE_BIAS, tc.PRE_GLU_RES_LN])
         if pre == tc.PRE_GLU_RES_LN:
@@ -239,7 +262,7 @@ def test_conv_gemm_random_configuration_sweep(tc):
             kw = dict(pre=pre, res=torch.randn(B * H * W, N // 2, generator=g).to(dev),
                       gamma=(torch.rand(N // 2, generator=g) + 0.5).to(dev), beta=torch.randn(N // 2, generator=g).to(dev))
         try:
-            outs = run_conv(tc, x, w, bias, taps, out_mask=mask, **kw)
+            outs = run_conv(tc, x, w, bias, taps, out_mask=mask, fmt=fmt, **kw)
         except AssertionError as e:
             assert "bad shape" in str(e), e          # an honest refusal is fine; anything else is a bug
             continue
@@ -256,11 +279,11 @@ def test_conv_gemm_random_configuration_sweep(tc):
         if mask & tc.OUT_NCHW:
             assert rel_err(outs["out_nchw"], y.view(B, H, W, N).permute(0, 3, 1, 2)) < tol, desc
         if mask & tc.OUT_HILO:
-            assert rel_err(outs["out_hi"] + outs["out_lo"], y) < tol, desc
+            assert rel_err(outs["out_hilo"], y) < tol, desc
         if mask & tc.OUT_HILO_RELU:
-            assert rel_err(outs["out_hi"] + outs["out_lo"], torch.relu(y)) < tol, desc
+            assert rel_err(outs["out_hilo"], torch.relu(y)) < tol, desc
         if mask & tc.OUT_HILO_CELU:
-            assert rel_err(outs["out_hi"] + outs["out_lo"], F.elu(torch.cat((y, -y), dim=-1))) < tol, desc
+            assert rel_err(outs["out_hilo"], F.elu(torch.cat((y, -y), dim=-1))) < tol, desc
     assert ran >= 20, ran
 
 
