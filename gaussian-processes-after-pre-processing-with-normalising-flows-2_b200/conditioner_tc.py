@@ -145,7 +145,7 @@ def mixlogcdf_nn_raw(nn_module, x_id, status=None):
                              status=status, acc_scale=sc)
             heads = blk["heads"]
             if tc.attention_supported(HW, C, heads):
-                t_hi, t_lo = tc.attention(qkv, B, HW, C, heads, F16)
+                t_hi, t_lo = tc.attention(qkv, B, HW, C, heads, F16, status=status)
             else:                                                     # odd head sizes: library matmuls
                 _lib.library_fallback("attention core (seq %d, head dim %d)" % (HW, C // heads), qkv)
                 d = C // heads

@@ -12,24 +12,6 @@
 
 namespace flowk {
 
-// two adjacent output columns -> the (hi, lo) operand arrays: TF32 pairs in fp32 containers, or fp16 pairs (out_f16)
-__device__ __forceinline__ void store_pair(float* out_hi, float* out_lo, size_t off, float v0, float v1, int out_f16) {
-  if (out_f16) {
-    unsigned short h0, l0, h1, l1;
-    split_f16(v0, h0, l0);
-    split_f16(v1, h1, l1);
-    *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned short*>(out_hi) + off) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-    *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned short*>(out_lo) + off) = (uint32_t)l0 | ((uint32_t)l1 << 16);
-  } else {
-    const float a0 = __uint_as_float((__float_as_uint(v0) + 0x1000u) & 0xffffe000u);
-    const float a1 = __uint_as_float((__float_as_uint(v1) + 0x1000u) & 0xffffe000u);
-    const float b0 = __uint_as_float((__float_as_uint(v0 - a0) + 0x1000u) & 0xffffe000u);
-    const float b1 = __uint_as_float((__float_as_uint(v1 - a1) + 0x1000u) & 0xffffe000u);
-    *reinterpret_cast<float2*>(out_hi + off) = make_float2(a0, a1);
-    *reinterpret_cast<float2*>(out_lo + off) = make_float2(b0, b1);
-  }
-}
-
 template <int D>
 __global__ void __launch_bounds__(256, 2) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out_hi,
                                                         float* __restrict__ out_lo, int out_f16, int HW, int C, int heads,

@@ -1,0 +1,290 @@
+// Self-attention core of GatedAttn (flow_modules/mixlogcdf_nn.py:134-147) on the 5th-gen tensor cores, inference.
+//
+//   att[q, :] = softmax_k(q . k / sqrt(d)) v        per (image, head); seq = H*W in {128, 256}, d = C / heads <= 64
+//
+// One CTA per (image, head, 128-query tile):
+//   1. all 8 warps stage Q (pre-scaled by log2(e) / sqrt(d)), K and V^T of the pair from the fp32 in_proj rows
+//      (k | v | q column order) into shared memory as fp16 (hi, lo) operand tiles, written straight in the K-major
+//      128-byte-swizzled layout tcgen05 reads (what a SWIZZLE_128B TMA load would have produced);
+//   2. S = Q K^T: tcgen05.mma kind::f16, M = 128 queries, N = seq keys, accumulators in TMEM (seq columns); fp32
+//      accuracy from the two-term split S = Qh Kh + Ql Kh + Qh Kl (same scheme as the conv GEMMs, csrc/tc_gemm.cu);
+//   3. softmax: a thread owns half of one score row (TMEM lane): row maximum, p = 2^(s - max), row sum; P goes back
+//      to shared memory as the (hi, lo) A operand of the second GEMM, over the dead Q / K tiles;
+//   4. O = P V: M = 128, N = d (padded to 16), K = seq; O lands in the TMEM columns S no longer needs;
+//   5. epilogue: O / rowsum -> the (hi, lo) operand pair of the gate GEMM, fp16 or TF32 containers.
+// Nothing of size seq x seq touches HBM.  Replaces the mma.sync kernel (csrc/attention.cu) for seq in {128, 256}.
+#include <cuda.h>
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace flowk {
+namespace tc {
+
+constexpr int ATT_THREADS = 256;
+constexpr int ROW_B = 128;                      // bytes per swizzle row: 64 fp16
+
+// byte offset of the 16-byte chunk `chunk` (0..7) of row `r` inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw_off(int r, int chunk) { return (uint32_t)(r * ROW_B + ((chunk ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void cvt8(const float* v, uint4& hi, uint4& lo) {
+  unsigned short h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_f16(v[i], h[i], l[i]);
+  hi = make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                  (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+  lo = make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                  (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+}
+
+struct AttParams {
+  const float* qkv;         // [B*HW, 3C], columns (k | v | q)
+  float* out_hi;            // [B*HW, C] operand pair (fp16 when out_f16, else TF32 values in fp32 containers)
+  float* out_lo;
+  int out_f16;
+  int HW, C, heads, D;      // D = C / heads (multiple of 8, <= 64)
+  int dk;                   // D rounded up to 16: contraction length of S and MMA N of O
+  float qscale;             // log2(e) / sqrt(D)
+  int q_off, k_off, v_off, p_off;     // byte offsets of the tile groups in dynamic shared memory
+  int* status;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int failed_flag;
+  __shared__ float red_max[2][128], red_sum[2][128];
+  volatile int* failed = &failed_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x, b = pair / p.heads, h = pair - b * p.heads;
+  const int q0 = blockIdx.y * 128;
+  const int HW = p.HW, D = p.D, C = p.C, row_stride = 3 * C;
+  const int chunks = D >> 3;                    // 16-byte chunks of real data per row
+  const int kchunks = p.dk >> 3;                // chunks the MMAs read (a zero chunk pads D % 16 == 8)
+  const int tmem_cols = HW <= 128 ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    failed_flag = 0;
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  griddep_launch();
+  griddep_wait();                               // the in_proj GEMM's rows are complete from here on
+
+  // ---- 1. stage Q, K (K-major rows) and V^T as fp16 (hi, lo) swizzled operand tiles ----------------------------------
+  uint8_t* q_hi = smem + p.q_off;               // [128 rows][128 B]
+  uint8_t* q_lo = q_hi + 128 * ROW_B;
+  uint8_t* k_hi = smem + p.k_off;               // [HW rows][128 B]
+  uint8_t* k_lo = k_hi + HW * ROW_B;
+  const int vt_tile = p.dk * ROW_B;             // one 64-key block of V^T: [dk rows][128 B]
+  uint8_t* v_hi = smem + p.v_off;               // [HW / 64 blocks][dk rows][128 B]
+  uint8_t* v_lo = v_hi + (HW >> 6) * vt_tile;
+  {
+    const float* base = p.qkv + (size_t)b * HW * row_stride + h * D;
+    // Q rows (columns 2C.. of the in_proj output), scaled
+    for (int i = threadIdx.x; i < 128 * kchunks; i += ATT_THREADS) {
+      const int r = i / kchunks, ch = i - r * kchunks;
+      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+      if (ch < chunks) {
+        const float4* src = reinterpret_cast<const float4*>(base + (size_t)(q0 + r) * row_stride + 2 * C + ch * 8);
+        const float4 a = __ldg(src), c = __ldg(src + 1);
+        const float v[8] = {a.x * p.qscale, a.y * p.qscale, a.z * p.qscale, a.w * p.qscale,
+                            c.x * p.qscale, c.y * p.qscale, c.z * p.qscale, c.w * p.qscale};
+        cvt8(v, hi, lo);
+      }
+      *reinterpret_cast<uint4*>(q_hi + sw_off(r, ch)) = hi;
+      *reinterpret_cast<uint4*>(q_lo + sw_off(r, ch)) = lo;
+    }
+    // K rows (columns 0..C)
+    for (int i = threadIdx.x; i < HW * kchunks; i += ATT_THREADS) {
+      const int r = i / kchunks, ch = i - r * kchunks;
+      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+      if (ch < chunks) {
+        const float4* src = reinterpret_cast<const float4*>(base + (size_t)r * row_stride + ch * 8);
+        const float4 a = __ldg(src), c = __ldg(src + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        cvt8(v, hi, lo);
+      }
+      *reinterpret_cast<uint4*>(k_hi + sw_off(r, ch)) = hi;
+      *reinterpret_cast<uint4*>(k_lo + sw_off(r, ch)) = lo;
+    }
+    // V^T (columns C..2C): rows = head dims, contraction (keys) along the 128-byte rows, 64 keys per block.
+    // A thread reads 8 dims of one key (coalesced along the row) and scatters them to 8 rows of the transposed tile.
+    for (int i = threadIdx.x; i < HW * (p.dk >> 3); i += ATT_THREADS) {
+      const int key = i % HW, ch = i / HW;       // consecutive threads -> consecutive keys (adjacent halves of a row)
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ch < chunks) {
+        const float4* src = reinterpret_cast<const float4*>(base + (size_t)key * row_stride + C + ch * 8);
+        const float4 a = __ldg(src), c = __ldg(src + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+      }
+      const int kb = key >> 6, kk = key & 63;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int dim = ch * 8 + j;
+        unsigned short hh, ll;
+        split_f16(v[j], hh, ll);
+        const uint32_t off = (uint32_t)kb * vt_tile + sw_off(dim, kk >> 3) + ((kk & 7) << 1);
+        *reinterpret_cast<unsigned short*>(v_hi + off) = hh;
+        *reinterpret_cast<unsigned short*>(v_lo + off) = ll;
+      }
+    }
+  }
+  fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
+  __syncthreads();
+
+  // ---- 2. S = Q K^T ------------------------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(HW);
+    const uint64_t dq_hi = make_smem_desc(smem_u32(q_hi)), dq_lo = make_smem_desc(smem_u32(q_lo));
+    const uint64_t dk_hi = make_smem_desc(smem_u32(k_hi)), dk_lo = make_smem_desc(smem_u32(k_lo));
+    const int ksteps = p.dk >> 4;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint64_t ko = (uint64_t)(ks * 2);   // 32 bytes per K = 16 step, in 16-byte units
+      umma_f16(tmem_base, dq_hi + ko, dk_hi + ko, idesc, ks == 0 ? 0u : 1u);
+      umma_f16(tmem_base, dq_lo + ko, dk_hi + ko, idesc, 1u);
+      umma_f16(tmem_base, dq_hi + ko, dk_lo + ko, idesc, 1u);
+    }
+    umma_commit(&bar_s);
+  }
+
+  // ---- 3. softmax: thread = (row, half of the keys) ---------------------------------------------------------------------
+  const int lane_grp = warp & 3, half = warp >> 2;
+  const int row = lane_grp * 32 + lane;
+  const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+  const int ncols = HW >> 1, c0 = half * ncols;
+  mbar_wait(&bar_s, 0, failed);
+  tc_fence_after();
+  float mx = -INFINITY;
+  for (int j = 0; j < ncols; j += 16) {
+    float s[16];
+    tmem_ld16(trow + c0 + j, s);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mx = fmaxf(mx, s[i]);
+  }
+  red_max[half][row] = mx;
+  __syncthreads();                              // (also: every warp is past bar_s, so Q / K are dead: P may overwrite them)
+  mx = fmaxf(red_max[0][row], red_max[1][row]);
+  uint8_t* p_hi = smem + p.p_off;               // [HW / 64 blocks][128 rows][128 B]
+  uint8_t* p_lo = p_hi + (HW >> 6) * (128 * ROW_B);
+  float sum = 0.f;
+  for (int j = 0; j < ncols; j += 16) {
+    float s[16];
+    tmem_ld16(trow + c0 + j, s);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      s[i] = ex2_fast(s[i] - mx);
+      sum += s[i];
+    }
+    const int key = c0 + j, kb = key >> 6, ch = (key & 63) >> 3;       // two 8-key chunks
+    uint4 hi, lo;
+    cvt8(s, hi, lo);
+    *reinterpret_cast<uint4*>(p_hi + kb * (128 * ROW_B) + sw_off(row, ch)) = hi;
+    *reinterpret_cast<uint4*>(p_lo + kb * (128 * ROW_B) + sw_off(row, ch)) = lo;
+    cvt8(s + 8, hi, lo);
+    *reinterpret_cast<uint4*>(p_hi + kb * (128 * ROW_B) + sw_off(row, ch + 1)) = hi;
+    *reinterpret_cast<uint4*>(p_lo + kb * (128 * ROW_B) + sw_off(row, ch + 1)) = lo;
+  }
+  red_sum[half][row] = sum;
+  tc_fence_before();                            // our tcgen05.ld of S are complete before the MMAs overwrite those columns
+  fence_proxy_async();
+  __syncthreads();
+
+  // ---- 4. O = P V (into the first dk columns of the S accumulator) -------------------------------------------------------
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(p.dk);
+    const int kblocks = HW >> 6;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const uint64_t dp_hi = make_smem_desc(smem_u32(p_hi + kb * (128 * ROW_B)));
+      const uint64_t dp_lo = make_smem_desc(smem_u32(p_lo + kb * (128 * ROW_B)));
+      const uint64_t dv_hi = make_smem_desc(smem_u32(v_hi + kb * vt_tile)), dv_lo = make_smem_desc(smem_u32(v_lo + kb * vt_tile));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t ko = (uint64_t)(k * 2);
+        umma_f16(tmem_base, dp_hi + ko, dv_hi + ko, idesc, (kb | k) == 0 ? 0u : 1u);
+        umma_f16(tmem_base, dp_lo + ko, dv_hi + ko, idesc, 1u);
+        umma_f16(tmem_base, dp_hi + ko, dv_lo + ko, idesc, 1u);
+      }
+    }
+    umma_commit(&bar_o);
+  }
+
+  // ---- 5. epilogue: O / rowsum -> operand pair; the two warps of a lane group split the head dims in 8-dim chunks ----------
+  mbar_wait(&bar_o, 0, failed);
+  tc_fence_after();
+  {
+    const float inv = 1.0f / (red_sum[0][row] + red_sum[1][row]);
+    const size_t o0 = (size_t)(b * HW + q0 + row) * C + h * D;
+    for (int ch = half; ch < chunks; ch += 2) {
+      uint32_t r[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                   : "r"(trow + ch * 8));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 8; i += 2)
+        store_pair(p.out_hi, p.out_lo, o0 + ch * 8 + i, __uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv,
+                      p.out_f16);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (threadIdx.x == 0 && failed_flag && p.status) *p.status = 1;
+}
+
+}  // namespace tc
+}  // namespace flowk
+
+using namespace flowk;
+using namespace flowk::tc;
+
+// Same contract as flowk_attention / flowk_attention_f16 (include/flowk.h); returns FLOWK_ERR_SHAPE for shapes this
+// kernel does not take (the caller then uses the mma.sync kernel): seq must be 128 or 256, C / heads a multiple of 8, <= 64.
+extern "C" int flowk_attention_tc(const float* qkv, void* out_hi, void* out_lo, int out_f16, int B, int HW, int C, int heads,
+                                  int* status, flowk_stream_t stream) {
+  if (B < 0 || HW < 1 || C < 1 || heads < 1 || C % heads) return FLOWK_ERR_SHAPE;
+  const int D = C / heads;
+  if ((HW != 128 && HW != 256) || D % 8 || D > 64 || C % 4) return FLOWK_ERR_SHAPE;
+  if (B == 0) return FLOWK_OK;
+  if (!qkv || !out_hi || !out_lo) return FLOWK_ERR_ARG;
+  if ((long long)B * heads > 0x7fffffffLL) return FLOWK_ERR_SHAPE;
+  AttParams p{};
+  p.qkv = qkv;
+  p.out_hi = reinterpret_cast<float*>(out_hi);
+  p.out_lo = reinterpret_cast<float*>(out_lo);
+  p.out_f16 = out_f16;
+  p.HW = HW;
+  p.C = C;
+  p.heads = heads;
+  p.D = D;
+  p.dk = (D + 15) / 16 * 16;
+  p.qscale = 1.4426950408889634f / sqrtf((float)D);
+  p.status = status;
+  // shared memory: [P tiles | over them: Q, K] then V^T
+  const int p_bytes = 2 * (HW / 64) * 128 * ROW_B;           // hi + lo
+  const int qk_bytes = 2 * 128 * ROW_B + 2 * HW * ROW_B;
+  const int first = p_bytes > qk_bytes ? p_bytes : qk_bytes;
+  p.p_off = 0;
+  p.q_off = 0;
+  p.k_off = 2 * 128 * ROW_B;
+  p.v_off = first;
+  const size_t smem = (size_t)first + (size_t)2 * (HW / 64) * p.dk * ROW_B + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  FLOWK_CUDA_OK(launch_pdl(attention_tc_kernel, dim3(B * heads, HW / 128), dim3(ATT_THREADS), smem, stream, p));
+  return launch_status();
+}

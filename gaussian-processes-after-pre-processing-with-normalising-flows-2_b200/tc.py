@@ -109,16 +109,31 @@ def split_rows(x):
     return hi, lo
 
 
-def attention(qkv, B, HW, C, heads, f16=False):
+ATTENTION_TC = __import__("os").environ.get("FLOWK_ATTENTION_TC", "1") != "0"
+
+
+def attention_tc_supported(HW, C, heads):
+    """Shapes the tcgen05 attention kernel (csrc/attention_tc.cu) takes; everything else runs on the mma.sync kernel."""
+    d = C // max(heads, 1)
+    return ATTENTION_TC and C % heads == 0 and HW in (128, 256) and d % 8 == 0 and d <= 64 and C % 4 == 0
+
+
+def attention(qkv, B, HW, C, heads, f16=False, status=None):
     """qkv [B*HW, 3C] (k | v | q) -> (hi, lo) [B*HW, C] of softmax(q k^T / sqrt(d)) v."""
     hi = torch.empty(B * HW, C, device=qkv.device, dtype=torch.float16 if f16 else torch.float32)
     lo = torch.empty_like(hi)
+    if attention_tc_supported(HW, C, heads):
+        _lib.call("flowk_attention_tc", qkv.data_ptr(), hi.data_ptr(), lo.data_ptr(), int(f16), B, HW, C, heads,
+                  _p(status), _stream())
+        return hi, lo
     _lib.call("flowk_attention_f16" if f16 else "flowk_attention", qkv.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, HW, C,
               heads, _stream())
     return hi, lo
 
 
 def attention_supported(HW, C, heads):
+    if attention_tc_supported(HW, C, heads):
+        return True
     return C % heads == 0 and (C // heads) in (8, 16, 24, 32, 40, 64) and (HW <= 256 or HW % 256 == 0) and HW % 4 == 0 \
         and 2 * min(HW, 1 << 30) * (C // heads) * 4 * max(1, 256 // max(HW, 1)) <= 220 * 1024
 

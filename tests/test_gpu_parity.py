@@ -365,7 +365,7 @@ def test_flownet_golden_tensor_core(F, golden, no_library, name):
         _lib.TIMING = None
     assert "flowk_conv_gemm" in names, names
     if "mixlogcdf" in name:
-        assert "flowk_attention" in names and "flowk_mixlogcdf_fwd" in names, names
+        assert names & {"flowk_attention", "flowk_attention_f16"} and "flowk_mixlogcdf_fwd" in names, names
 
 
 def _flownet_golden(F, g, fuse):

@@ -160,6 +160,36 @@ def test_attention_matches_fp64(tc, fmt, B, HW, C, heads):
         assert int((hi.view(torch.int32) & 8191).abs().max()) == 0
 
 
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("B,HW,C,heads", [(64, 256, 96, 4), (3, 128, 64, 4), (2, 256, 160, 4), (5, 256, 32, 4),
+                                          (2, 128, 256, 4), (1, 256, 64, 1)])
+def test_attention_tcgen05_matches_fp64_and_mma_sync(tc, fmt, B, HW, C, heads):
+    """csrc/attention_tc.cu (S = Q K^T and O = P V on tcgen05, softmax from TMEM) against fp64 and against the mma.sync
+    kernel it replaces for seq in {128, 256}; head dims 8, 16, 24, 40, 64 (24 and 40 exercise the zero-padded K = 16 step)."""
+    from flowk import _lib
+    dev = torch.device("cuda:0")
+    assert tc.attention_tc_supported(HW, C, heads)
+    g = torch.Generator(device="cpu").manual_seed(B * HW + C)
+    qkv = (torch.randn(B * HW, 3 * C, generator=g) * 1.5).to(dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    f16 = fmt == "f16"
+    hi, lo = tc.attention(qkv, B, HW, C, heads, f16, status=status)
+    torch.cuda.synchronize()
+    assert int(status) == 0, "barrier wait timed out inside the kernel"
+    got = hi.float() + lo.float()
+    d = C // heads
+    t = qkv.double().view(B, HW, 3, heads, d)
+    k, v, q = (t[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ref = (torch.softmax((q * d ** -0.5) @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * HW, C)
+    assert rel_err(got, ref) < 2e-5, rel_err(got, ref)
+    if d in (8, 16, 24, 32, 40, 64):
+        old_hi = torch.empty_like(hi)
+        old_lo = torch.empty_like(lo)
+        _lib.call("flowk_attention_f16" if f16 else "flowk_attention", qkv.data_ptr(), old_hi.data_ptr(), old_lo.data_ptr(),
+                  B, HW, C, heads, tc._stream())
+        assert rel_err(got, (old_hi.float() + old_lo.float()).double()) < 2e-5
+
+
 @pytest.mark.parametrize("c,hidden,H,W,B", [(6, 64, 16, 16, 32), (12, 256, 8, 8, 128), (24, 256, 4, 4, 128),
                                             (6, 256, 32, 32, 4), (48, 256, 4, 4, 16)])
 def test_affine_conditioner_tc_matches_torch_path(tc, c, hidden, H, W, B):
