@@ -20,20 +20,34 @@
 namespace flowk {
 namespace tc {
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 512;                // 16 warps: 4 threads share a score row (TMEM lane), a quarter of the keys each
 constexpr int ROW_B = 128;                      // bytes per swizzle row: 64 fp16
 
 // byte offset of the 16-byte chunk `chunk` (0..7) of row `r` inside a K-major SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw_off(int r, int chunk) { return (uint32_t)(r * ROW_B + ((chunk ^ (r & 7)) << 4)); }
 
+// 8 floats -> 8 fp16 hi + 8 fp16 lo (x = hi + lo), packed; |x| must be < 65504 (q, k, v and the softmax weights are)
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));      // low half = a
+  return r;
+}
+__device__ __forceinline__ void unpack_h2(uint32_t v, float& a, float& b) {
+  unsigned short lo16 = (unsigned short)(v & 0xffffu), hi16 = (unsigned short)(v >> 16);
+  asm("cvt.f32.f16 %0, %1;" : "=f"(a) : "h"(lo16));
+  asm("cvt.f32.f16 %0, %1;" : "=f"(b) : "h"(hi16));
+}
 __device__ __forceinline__ void cvt8(const float* v, uint4& hi, uint4& lo) {
-  unsigned short h[8], l[8];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) split_f16(v[i], h[i], l[i]);
-  hi = make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
-                  (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
-  lo = make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
-                  (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+    float a, b;
+    unpack_h2(h[i], a, b);
+    l[i] = pack_h2(v[2 * i] - a, v[2 * i + 1] - b);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 struct AttParams {
@@ -46,15 +60,17 @@ struct AttParams {
   float qscale;             // log2(e) / sqrt(D)
   int q_off, k_off, v_off, p_off;     // byte offsets of the tile groups in dynamic shared memory
   int* status;
+  long long* trace;         // optional device [8]: clock64 stamps of CTA (0,0) (profiling), NULL in production
 };
 
+template <int KCH>           // KCH = dk / 8: 16-byte chunks per staged row the MMAs read (compile-time: index math without divisions)
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
   __shared__ int failed_flag;
-  __shared__ float red_max[2][128], red_sum[2][128];
+  __shared__ float red_max[4][128], red_sum[4][128];
   volatile int* failed = &failed_flag;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -62,7 +78,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
   const int q0 = blockIdx.y * 128;
   const int HW = p.HW, D = p.D, C = p.C, row_stride = 3 * C;
   const int chunks = D >> 3;                    // 16-byte chunks of real data per row
-  const int kchunks = p.dk >> 3;                // chunks the MMAs read (a zero chunk pads D % 16 == 8)
+  constexpr int kchunks = KCH;                  // chunks the MMAs read (a zero chunk pads D % 16 == 8)
+  const int hw_shift = HW == 256 ? 8 : 7;
   const int tmem_cols = HW <= 128 ? 128 : 256;
 
   if (threadIdx.x == 0) {
@@ -76,70 +93,79 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const bool tracing = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
   griddep_launch();
   griddep_wait();                               // the in_proj GEMM's rows are complete from here on
+  if (tracing) p.trace[0] = clock64();
 
   // ---- 1. stage Q, K (K-major rows) and V^T as fp16 (hi, lo) swizzled operand tiles ----------------------------------
   uint8_t* q_hi = smem + p.q_off;               // [128 rows][128 B]
   uint8_t* q_lo = q_hi + 128 * ROW_B;
   uint8_t* k_hi = smem + p.k_off;               // [HW rows][128 B]
   uint8_t* k_lo = k_hi + HW * ROW_B;
-  const int vt_tile = p.dk * ROW_B;             // one 64-key block of V^T: [dk rows][128 B]
-  uint8_t* v_hi = smem + p.v_off;               // [HW / 64 blocks][dk rows][128 B]
-  uint8_t* v_lo = v_hi + (HW >> 6) * vt_tile;
+  const int vt_tile = 2 * p.dk * ROW_B;         // one 64-key block of V^T: [dk rows of hi | dk rows of lo][128 B]
+  uint8_t* v_t = smem + p.v_off;                // [HW / 64 blocks][2 dk rows][128 B]
   {
+    // One item = 8 consecutive floats (32 bytes) of one row of Q, K or V.  Every thread first issues the loads of ALL its
+    // items (one L2 round trip for the whole staging phase), then converts and scatters them.
     const float* base = p.qkv + (size_t)b * HW * row_stride + h * D;
-    // Q rows (columns 2C.. of the in_proj output), scaled
-    for (int i = threadIdx.x; i < 128 * kchunks; i += ATT_THREADS) {
-      const int r = i / kchunks, ch = i - r * kchunks;
-      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-      if (ch < chunks) {
-        const float4* src = reinterpret_cast<const float4*>(base + (size_t)(q0 + r) * row_stride + 2 * C + ch * 8);
-        const float4 a = __ldg(src), c = __ldg(src + 1);
-        const float v[8] = {a.x * p.qscale, a.y * p.qscale, a.z * p.qscale, a.w * p.qscale,
-                            c.x * p.qscale, c.y * p.qscale, c.z * p.qscale, c.w * p.qscale};
-        cvt8(v, hi, lo);
-      }
-      *reinterpret_cast<uint4*>(q_hi + sw_off(r, ch)) = hi;
-      *reinterpret_cast<uint4*>(q_lo + sw_off(r, ch)) = lo;
-    }
-    // K rows (columns 0..C)
-    for (int i = threadIdx.x; i < HW * kchunks; i += ATT_THREADS) {
-      const int r = i / kchunks, ch = i - r * kchunks;
-      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-      if (ch < chunks) {
-        const float4* src = reinterpret_cast<const float4*>(base + (size_t)r * row_stride + ch * 8);
-        const float4 a = __ldg(src), c = __ldg(src + 1);
-        const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-        cvt8(v, hi, lo);
-      }
-      *reinterpret_cast<uint4*>(k_hi + sw_off(r, ch)) = hi;
-      *reinterpret_cast<uint4*>(k_lo + sw_off(r, ch)) = lo;
-    }
-    // V^T (columns C..2C): rows = head dims, contraction (keys) along the 128-byte rows, 64 keys per block.
-    // A thread reads 8 dims of one key (coalesced along the row) and scatters them to 8 rows of the transposed tile.
-    for (int i = threadIdx.x; i < HW * (p.dk >> 3); i += ATT_THREADS) {
-      const int key = i % HW, ch = i / HW;       // consecutive threads -> consecutive keys (adjacent halves of a row)
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (ch < chunks) {
-        const float4* src = reinterpret_cast<const float4*>(base + (size_t)key * row_stride + C + ch * 8);
-        const float4 a = __ldg(src), c = __ldg(src + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-      }
-      const int kb = key >> 6, kk = key & 63;
+    const int nq = 128 * kchunks, nk = HW * kchunks, total = nq + 2 * nk;
+    constexpr int MAXI = 6;                     // (128 + 2 * 256) rows * 8 chunks / 512 threads <= 10 -> two rounds at most
+    for (int i0 = threadIdx.x; i0 < total; i0 += MAXI * ATT_THREADS) {
+      float4 a[MAXI], c[MAXI];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int dim = ch * 8 + j;
-        unsigned short hh, ll;
-        split_f16(v[j], hh, ll);
-        const uint32_t off = (uint32_t)kb * vt_tile + sw_off(dim, kk >> 3) + ((kk & 7) << 1);
-        *reinterpret_cast<unsigned short*>(v_hi + off) = hh;
-        *reinterpret_cast<unsigned short*>(v_lo + off) = ll;
+      for (int u = 0; u < MAXI; ++u) {
+        const int i = i0 + u * ATT_THREADS;
+        a[u] = c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total) {
+          int r, ch, col;
+          if (i < nq) { r = q0 + i / kchunks; ch = i % kchunks; col = 2 * C; }
+          else if (i < nq + nk) { r = (i - nq) / kchunks; ch = (i - nq) % kchunks; col = 0; }
+          else { r = (i - nq - nk) & (HW - 1); ch = (i - nq - nk) >> hw_shift; col = C; }   // V: consecutive threads -> consecutive keys
+          if (ch < chunks) {
+            const float4* g = reinterpret_cast<const float4*>(base + (size_t)r * row_stride + col + ch * 8);
+            a[u] = __ldg(g);
+            c[u] = __ldg(g + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < MAXI; ++u) {
+        const int i = i0 + u * ATT_THREADS;
+        if (i >= total) continue;
+        if (i < nq + nk) {                      // Q (scaled) and K: K-major rows as they lie
+          const bool isq = i < nq;
+          const int j = isq ? i : i - nq;
+          const int r = j / kchunks, ch = j % kchunks;
+          const float sc = isq ? p.qscale : 1.f;
+          const float v[8] = {a[u].x * sc, a[u].y * sc, a[u].z * sc, a[u].w * sc, c[u].x * sc, c[u].y * sc, c[u].z * sc, c[u].w * sc};
+          uint4 hi, lo;
+          cvt8(v, hi, lo);
+          *reinterpret_cast<uint4*>((isq ? q_hi : k_hi) + sw_off(r, ch)) = hi;
+          *reinterpret_cast<uint4*>((isq ? q_lo : k_lo) + sw_off(r, ch)) = lo;
+        } else {
+          // V^T: rows = head dims, contraction (keys) along the 128-byte rows, 64 keys per block; the 8 dims of this key are
+          // scattered to 8 rows of the transposed tile.  The lo rows of a block follow its hi rows, so [V_hi ; V_lo] is ONE
+          // B operand of N = 2 dk rows.
+          const int j = i - nq - nk, key = j & (HW - 1), ch = j >> hw_shift;
+          const float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, c[u].x, c[u].y, c[u].z, c[u].w};
+          const int kb = key >> 6, kk = key & 63;
+          uint8_t* tile = v_t + (size_t)kb * vt_tile;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int dim = ch * 8 + jj;
+            unsigned short hh, ll;
+            split_f16(v[jj], hh, ll);
+            *reinterpret_cast<unsigned short*>(tile + sw_off(dim, kk >> 3) + ((kk & 7) << 1)) = hh;
+            *reinterpret_cast<unsigned short*>(tile + sw_off(p.dk + dim, kk >> 3) + ((kk & 7) << 1)) = ll;
+          }
+        }
       }
     }
   }
   fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
   __syncthreads();
+  if (tracing) p.trace[1] = clock64();
 
   // ---- 2. S = Q K^T ------------------------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
@@ -157,13 +183,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
     umma_commit(&bar_s);
   }
 
-  // ---- 3. softmax: thread = (row, half of the keys) ---------------------------------------------------------------------
-  const int lane_grp = warp & 3, half = warp >> 2;
+  // ---- 3. softmax: thread = (row, quarter of the keys) ------------------------------------------------------------------
+  const int lane_grp = warp & 3, quarter = warp >> 2;
   const int row = lane_grp * 32 + lane;
   const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-  const int ncols = HW >> 1, c0 = half * ncols;
+  const int ncols = HW >> 2, c0 = quarter * ncols;
   mbar_wait(&bar_s, 0, failed);
   tc_fence_after();
+  if (tracing) p.trace[2] = clock64();
   float mx = -INFINITY;
   for (int j = 0; j < ncols; j += 16) {
     float s[16];
@@ -171,9 +198,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
 #pragma unroll
     for (int i = 0; i < 16; ++i) mx = fmaxf(mx, s[i]);
   }
-  red_max[half][row] = mx;
+  red_max[quarter][row] = mx;
   __syncthreads();                              // (also: every warp is past bar_s, so Q / K are dead: P may overwrite them)
-  mx = fmaxf(red_max[0][row], red_max[1][row]);
+  if (tracing) p.trace[3] = clock64();
+  mx = fmaxf(fmaxf(red_max[0][row], red_max[1][row]), fmaxf(red_max[2][row], red_max[3][row]));
   uint8_t* p_hi = smem + p.p_off;               // [HW / 64 blocks][128 rows][128 B]
   uint8_t* p_lo = p_hi + (HW >> 6) * (128 * ROW_B);
   float sum = 0.f;
@@ -194,51 +222,80 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
     *reinterpret_cast<uint4*>(p_hi + kb * (128 * ROW_B) + sw_off(row, ch + 1)) = hi;
     *reinterpret_cast<uint4*>(p_lo + kb * (128 * ROW_B) + sw_off(row, ch + 1)) = lo;
   }
-  red_sum[half][row] = sum;
+  red_sum[quarter][row] = sum;
   tc_fence_before();                            // our tcgen05.ld of S are complete before the MMAs overwrite those columns
   fence_proxy_async();
   __syncthreads();
+  if (tracing) p.trace[4] = clock64();
 
-  // ---- 4. O = P V (into the first dk columns of the S accumulator) -------------------------------------------------------
+  // ---- 4. O = P V.  B operand = [V_hi ; V_lo] (N = 2 dk): P_hi [V_hi ; V_lo] fills columns [0, dk) and [dk, 2 dk) in one
+  //         MMA, P_lo V_hi adds to [0, dk); the epilogue sums the two column groups.  (Over S's dead leading columns.)
   if (threadIdx.x == 0) {
     tc_fence_after();
-    const uint32_t idesc = make_idesc_f16(p.dk);
+    const uint32_t idesc2 = make_idesc_f16(2 * p.dk), idesc1 = make_idesc_f16(p.dk);
     const int kblocks = HW >> 6;
     for (int kb = 0; kb < kblocks; ++kb) {
       const uint64_t dp_hi = make_smem_desc(smem_u32(p_hi + kb * (128 * ROW_B)));
       const uint64_t dp_lo = make_smem_desc(smem_u32(p_lo + kb * (128 * ROW_B)));
-      const uint64_t dv_hi = make_smem_desc(smem_u32(v_hi + kb * vt_tile)), dv_lo = make_smem_desc(smem_u32(v_lo + kb * vt_tile));
+      const uint64_t dv = make_smem_desc(smem_u32(v_t + (size_t)kb * vt_tile));
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint64_t ko = (uint64_t)(k * 2);
-        umma_f16(tmem_base, dp_hi + ko, dv_hi + ko, idesc, (kb | k) == 0 ? 0u : 1u);
-        umma_f16(tmem_base, dp_lo + ko, dv_hi + ko, idesc, 1u);
-        umma_f16(tmem_base, dp_hi + ko, dv_lo + ko, idesc, 1u);
+        umma_f16(tmem_base, dp_hi + ko, dv + ko, idesc2, (kb | k) == 0 ? 0u : 1u);
+        umma_f16(tmem_base, dp_lo + ko, dv + ko, idesc1, 1u);
       }
     }
     umma_commit(&bar_o);
   }
 
-  // ---- 5. epilogue: O / rowsum -> operand pair; the two warps of a lane group split the head dims in 8-dim chunks ----------
+  // ---- 5. epilogue: O / rowsum -> operand pair.  fp16 output: through shared memory (the dead P tiles), so that global
+  //         stores are 16-byte chunks of whole head rows; TF32 output: direct pair stores.
   mbar_wait(&bar_o, 0, failed);
   tc_fence_after();
+  if (tracing) p.trace[5] = clock64();
   {
-    const float inv = 1.0f / (red_sum[0][row] + red_sum[1][row]);
+    const float inv = 1.0f / ((red_sum[0][row] + red_sum[1][row]) + (red_sum[2][row] + red_sum[3][row]));
     const size_t o0 = (size_t)(b * HW + q0 + row) * C + h * D;
-    for (int ch = half; ch < chunks; ch += 2) {
+    uint8_t* stage = smem + p.p_off;             // [2 (hi, lo)][128 rows][chunks] 16-byte items
+    for (int ch = quarter; ch < chunks; ch += 4) {
+      float a[8], c[8];
       uint32_t r[8];
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                    : "r"(trow + ch * 8));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int i = 0; i < 8; i += 2)
-        store_pair(p.out_hi, p.out_lo, o0 + ch * 8 + i, __uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv,
-                      p.out_f16);
+      for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(r[i]);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                   : "r"(trow + p.dk + ch * 8));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c[i] = (a[i] + __uint_as_float(r[i])) * inv;
+      if (p.out_f16) {
+        uint4 hi, lo;
+        cvt8(c, hi, lo);
+        *reinterpret_cast<uint4*>(stage + ((size_t)row * chunks + ch) * 16) = hi;
+        *reinterpret_cast<uint4*>(stage + ((size_t)(128 + row) * chunks + ch) * 16) = lo;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) store_pair(p.out_hi, p.out_lo, o0 + ch * 8 + i, c[i], c[i + 1], 0);
+      }
+    }
+    if (p.out_f16) {
+      __syncthreads();
+      const int items = 2 * 128 * chunks;
+      for (int i = threadIdx.x; i < items; i += ATT_THREADS) {
+        const int mat = i / (128 * chunks), rr = (i / chunks) % 128, ch = i % chunks;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)i * 16);
+        unsigned short* dst = reinterpret_cast<unsigned short*>(mat ? p.out_lo : p.out_hi);
+        *reinterpret_cast<uint4*>(dst + (size_t)(b * HW + q0 + rr) * C + h * D + ch * 8) = v;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tracing) p.trace[6] = clock64();
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
   if (threadIdx.x == 0 && failed_flag && p.status) *p.status = 1;
 }
@@ -252,7 +309,7 @@ using namespace flowk::tc;
 // Same contract as flowk_attention / flowk_attention_f16 (include/flowk.h); returns FLOWK_ERR_SHAPE for shapes this
 // kernel does not take (the caller then uses the mma.sync kernel): seq must be 128 or 256, C / heads a multiple of 8, <= 64.
 extern "C" int flowk_attention_tc(const float* qkv, void* out_hi, void* out_lo, int out_f16, int B, int HW, int C, int heads,
-                                  int* status, flowk_stream_t stream) {
+                                  int* status, long long* trace, flowk_stream_t stream) {
   if (B < 0 || HW < 1 || C < 1 || heads < 1 || C % heads) return FLOWK_ERR_SHAPE;
   const int D = C / heads;
   if ((HW != 128 && HW != 256) || D % 8 || D > 64 || C % 4) return FLOWK_ERR_SHAPE;
@@ -271,6 +328,7 @@ extern "C" int flowk_attention_tc(const float* qkv, void* out_hi, void* out_lo, 
   p.dk = (D + 15) / 16 * 16;
   p.qscale = 1.4426950408889634f / sqrtf((float)D);
   p.status = status;
+  p.trace = trace;
   // shared memory: [P tiles | over them: Q, K] then V^T
   const int p_bytes = 2 * (HW / 64) * 128 * ROW_B;           // hi + lo
   const int qk_bytes = 2 * 128 * ROW_B + 2 * HW * ROW_B;
@@ -280,11 +338,21 @@ extern "C" int flowk_attention_tc(const float* qkv, void* out_hi, void* out_lo, 
   p.k_off = 2 * 128 * ROW_B;
   p.v_off = first;
   const size_t smem = (size_t)first + (size_t)2 * (HW / 64) * p.dk * ROW_B + 1024;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+#define FLOWK_LAUNCH_ATT(KCH_)                                                                                          \
+  do {                                                                                                                 \
+    static size_t smem_set = 0;                                                                                        \
+    if (smem > smem_set) {                                                                                             \
+      FLOWK_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<KCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                                 \
+    }                                                                                                                  \
+    FLOWK_CUDA_OK(launch_pdl(attention_tc_kernel<KCH_>, dim3(B * heads, HW / 128), dim3(ATT_THREADS), smem, stream, p)); \
+  } while (0)
+  switch (p.dk >> 3) {
+    case 2: FLOWK_LAUNCH_ATT(2); break;
+    case 4: FLOWK_LAUNCH_ATT(4); break;
+    case 6: FLOWK_LAUNCH_ATT(6); break;
+    default: FLOWK_LAUNCH_ATT(8); break;
   }
-  FLOWK_CUDA_OK(launch_pdl(attention_tc_kernel, dim3(B * heads, HW / 128), dim3(ATT_THREADS), smem, stream, p));
+#undef FLOWK_LAUNCH_ATT
   return launch_status();
 }

@@ -856,6 +856,13 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   int stages = (int)((220 * 1024 - 2048) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 1) return FLOWK_ERR_SHAPE;
+  // Co-residency: kernels whose accumulators fit 256 TMEM columns can share an SM with a second CTA (of the same launch
+  // or of another stream's launch) if they also fit half of the shared memory; their prologues / epilogues, which are
+  // latency-bound, then overlap the neighbour's main loop.  FLOWK_GEMM_SMEM_CAP_KB caps the pipeline depth accordingly.
+  static int smem_cap_kb = -1;
+  if (smem_cap_kb < 0) { const char* e = getenv("FLOWK_GEMM_SMEM_CAP_KB"); smem_cap_kb = e ? atoi(e) : 0; }
+  if (smem_cap_kb > 0 && p.tmem_cols <= 256)
+    while (stages > 1 && (size_t)stages * stage_bytes > (size_t)smem_cap_kb * 1024) --stages;
   // 3x3 dx-split mode: three accumulators (one per column shift) so that an activation tile serves three taps
   p.dxsplit = (a->taps == 9 && a->pre == PRE_BIAS && W <= 32 && 32 % W == 0 && p.n_chunks == 1 && 3 * p.n_chunk <= 512 &&
                p.ksplit == 1) ? 1 : 0;

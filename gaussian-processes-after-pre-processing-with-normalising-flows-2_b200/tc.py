@@ -118,13 +118,13 @@ def attention_tc_supported(HW, C, heads):
     return ATTENTION_TC and C % heads == 0 and HW in (128, 256) and d % 8 == 0 and d <= 64 and C % 4 == 0
 
 
-def attention(qkv, B, HW, C, heads, f16=False, status=None):
+def attention(qkv, B, HW, C, heads, f16=False, status=None, trace=None):
     """qkv [B*HW, 3C] (k | v | q) -> (hi, lo) [B*HW, C] of softmax(q k^T / sqrt(d)) v."""
     hi = torch.empty(B * HW, C, device=qkv.device, dtype=torch.float16 if f16 else torch.float32)
     lo = torch.empty_like(hi)
     if attention_tc_supported(HW, C, heads):
         _lib.call("flowk_attention_tc", qkv.data_ptr(), hi.data_ptr(), lo.data_ptr(), int(f16), B, HW, C, heads,
-                  _p(status), _stream())
+                  _p(status), _p(trace), _stream())
         return hi, lo
     _lib.call("flowk_attention_f16" if f16 else "flowk_attention", qkv.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, HW, C,
               heads, _stream())

@@ -323,9 +323,10 @@ int flowk_attention_f16(const float* qkv, void* out_hi, void* out_lo, int B, int
 /* The same attention core on tcgen05 (csrc/attention_tc.cu): S = Q K^T and O = P V as kind::f16 MMAs with TMEM accumulators,
  * fp16 (hi, lo) operand tiles built in shared memory, softmax between them; out_f16 selects fp16 or TF32-in-fp32 output
  * pairs.  Takes HW in {128, 256} with C/heads a multiple of 8 and <= 64; FLOWK_ERR_SHAPE otherwise (use flowk_attention).
- * `status` (device int, may be NULL) is set to 1 if an internal barrier wait timed out. */
+ * `status` (device int, may be NULL) is set to 1 if an internal barrier wait timed out; `trace` (device long long[8], NULL in
+ * production) receives clock64 stamps of the first CTA's phases. */
 int flowk_attention_tc(const float* qkv, void* out_hi, void* out_lo, int out_f16, int B, int HW, int C, int heads,
-                       int* status, flowk_stream_t stream);
+                       int* status, long long* trace, flowk_stream_t stream);
 
 #ifdef __cplusplus
 }
