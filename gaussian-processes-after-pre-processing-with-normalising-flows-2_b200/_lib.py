@@ -82,7 +82,8 @@ class ConvGemmArgs(ctypes.Structure):
                  "out_f32", "out_hi", "out_lo", "out_nchw", "status", "trace")] + \
                [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")] + \
                [(n, ctypes.c_void_p) for n in ("w2_hi", "w2_lo", "out2_f32")] + [("N2", ctypes.c_int)] + \
-               [("splitk_ws", ctypes.c_void_p), ("operand_format", ctypes.c_int), ("acc_scale", ctypes.c_float)]
+               [("splitk_ws", ctypes.c_void_p), ("operand_format", ctypes.c_int), ("acc_scale", ctypes.c_float),
+                ("dilation", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class WnJob(ctypes.Structure):
@@ -97,7 +98,7 @@ class AdamaxChunk(ctypes.Structure):
 
 
 OPERAND_TF32, OPERAND_F16 = 0, 1
-PRE_BIAS, PRE_GLU_RES_LN = 0, 1
+PRE_BIAS, PRE_GLU_RES_LN, PRE_LSTM = 0, 1, 2
 OUT_F32, OUT_HILO, OUT_HILO_POS, OUT_HILO_CELU, OUT_NCHW, OUT_HILO_RELU = 1, 2, 4, 8, 16, 32
 
 

@@ -43,12 +43,13 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 
 // --------------------------------------------------------------------------------------------------
 // kernel parameters (device view)
 // --------------------------------------------------------------------------------------------------
-enum { PRE_BIAS = 0, PRE_GLU_RES_LN = 1 };
+enum { PRE_BIAS = 0, PRE_GLU_RES_LN = 1, PRE_LSTM = 2 };
 enum { OUT_F32 = 1, OUT_HILO = 2, OUT_HILO_POS = 4, OUT_HILO_CELU = 8, OUT_NCHW = 16, OUT_HILO_RELU = 32 };
 
 struct Params {
   int M, N, HW, W, H;              // M = B*H*W rows, N = total output columns of the GEMM
   int taps, kblocks_per_tap;       // K loop = taps * kblocks_per_tap blocks of 32 channels
+  int ksz, dil;                    // taps = ksz * ksz (1, 3 or 5), tap (ky, kx) reads position + ((ky, kx) - ksz / 2) * dil
   int wt, ht, bt;                  // M tile = bt images x ht rows x wt (= W) columns
   int n_chunk, n_chunks;           // columns per MMA (<=256, %16) and MMAs per k-step; CTA covers n_chunk*n_chunks columns
   int tmem_cols, stages;
@@ -181,7 +182,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         mbar_wait(&empty_bar[s], ph ^ 1u, failed);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const int tap = kb / kpt, cb = cb0 + kb % kpt;
-        const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+        const int dy = (tap / p.ksz - (p.ksz >> 1)) * p.dil, dx = (tap % p.ksz - (p.ksz >> 1)) * p.dil;
         mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
         tma_load_4d(st, &map_a_hi, &full_bar[s], cb * BK, dx, h0 + dy, b0);
         tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[s], cb * BK, dx, h0 + dy, b0);
@@ -422,6 +423,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               store_hilo4<F16>(p.out_hi, p.out_lo, o2 + p.N, t2);
             }
           }
+        }
+      }
+    } else if (PRE == PRE_LSTM) {
+      // ConvLSTM cell (mar_prior/convolutional_rnn/functional.py:30-52): the accumulator row holds the hidden-to-hidden
+      // gate pre-activations [i | f | g | o] (hid columns each); res = the input-to-hidden gates of this step (with their
+      // bias), bias = b_hh, gamma = c_{t-1} [M, hid] -> c_t = sig(f) c + sig(i) tanh(g), h_t = sig(o) tanh(c_t).
+      // c_t goes to out_f32 [M, hid], h_t to the (hi, lo) operand pair [M, hid] the next step / layer consumes.
+      // One thread per row (the first warp of each TMEM lane group), 8 hidden units at a time.
+      const int hid = p.N >> 2;
+      const int m = slab_row0 + lane;
+      if (sub == 0 && m < p.M) {
+        const float* gi = p.res + (size_t)m * p.N;
+        const float* cp = p.gamma + (size_t)m * hid;
+        for (int j = 0; j < hid; j += 8) {
+          float acc[4][8];
+#pragma unroll
+          for (int gte = 0; gte < 4; ++gte) {
+            tmem_ld8(trow + gte * hid + j, acc[gte]);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gi + gte * hid + j));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gi + gte * hid + j + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + gte * hid + j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + gte * hid + j + 4));
+            const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[gte][i] = fmaf(acc[gte][i], sc, bv[i]) + gv[i];
+          }
+          const float4 c0 = __ldg(reinterpret_cast<const float4*>(cp + j)), c1 = __ldg(reinterpret_cast<const float4*>(cp + j + 4));
+          const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          float cn[8], hn[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float ig = 1.f / (1.f + expf(-acc[0][i])), fg = 1.f / (1.f + expf(-acc[1][i]));
+            const float gg = tanhf(acc[2][i]), og = 1.f / (1.f + expf(-acc[3][i]));
+            cn[i] = fg * cv[i] + ig * gg;
+            hn[i] = og * tanhf(cn[i]);
+          }
+          float* co = out_f32 + (size_t)m * hid + j;
+          *reinterpret_cast<float4*>(co) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(co + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          store_hilo4<F16>(p.out_hi, p.out_lo, (size_t)m * hid + j, hn);
+          store_hilo4<F16>(p.out_hi, p.out_lo, (size_t)m * hid + j + 4, hn + 4);
         }
       }
     } else {
@@ -766,7 +809,9 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   if (B < 1 || H < 1 || W < 1 || N < 1) return FLOWK_ERR_SHAPE;
   if (f16 ? (Cin < 8 || Cin % 8) : (Cin < BLOCK_K || Cin % BLOCK_K)) return FLOWK_ERR_SHAPE;   // 16-byte row pitch / whole blocks
   if (f16 && !(a->acc_scale > 0.f)) return FLOWK_ERR_ARG;
-  if (a->taps != 1 && a->taps != 9) return FLOWK_ERR_ARG;
+  if (a->taps != 1 && a->taps != 9 && a->taps != 25) return FLOWK_ERR_ARG;
+  const int dil = a->dilation > 0 ? a->dilation : 1;
+  if (a->pre != PRE_BIAS && a->pre != PRE_GLU_RES_LN && a->pre != PRE_LSTM) return FLOWK_ERR_ARG;
   if (!plan_only && !encode_fn()) return FLOWK_ERR_ARG;      // planning is a pure host computation
   // M tile = bt images x ht rows x W columns = 128 positions
   int wt = W, ht, bt;
@@ -787,6 +832,8 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   p.W = W;
   p.H = H;
   p.taps = a->taps;
+  p.ksz = a->taps == 25 ? 5 : a->taps == 9 ? 3 : 1;
+  p.dil = dil;
   p.kblocks_per_tap = (Cin + bk - 1) / bk;
   p.acc_scale = f16 ? a->acc_scale : 1.f;
   p.wt = wt;
@@ -812,6 +859,12 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
     if ((N & 1) || C % 16 || C > 256 || !a->res || !a->gamma || !a->beta || !a->bias) return FLOWK_ERR_SHAPE;
     if (N <= 256) { p.n_chunk = N; p.n_chunks = 1; }
     else { p.n_chunk = C; p.n_chunks = 2; }
+    n_tiles = 1;
+  } else if (a->pre == PRE_LSTM) {
+    // N = 4 * hid gate columns, all in one CTA (the cell update needs the four gates of a unit together)
+    if (N % 32 || N > 256 || !a->res || !a->gamma || !a->bias || !a->out_f32 || !a->out_hi || !a->out_lo) return FLOWK_ERR_SHAPE;
+    p.n_chunk = N;
+    p.n_chunks = 1;
     n_tiles = 1;
   } else {
     // split N into tiles of <= 256 columns, multiple of 16 (rows past N are zero-filled by TMA)
@@ -864,8 +917,8 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   if (smem_cap_kb > 0 && p.tmem_cols <= 256)
     while (stages > 1 && (size_t)stages * stage_bytes > (size_t)smem_cap_kb * 1024) --stages;
   // 3x3 dx-split mode: three accumulators (one per column shift) so that an activation tile serves three taps
-  p.dxsplit = (a->taps == 9 && a->pre == PRE_BIAS && W <= 32 && 32 % W == 0 && p.n_chunks == 1 && 3 * p.n_chunk <= 512 &&
-               p.ksplit == 1) ? 1 : 0;
+  p.dxsplit = (a->taps == 9 && dil == 1 && a->pre == PRE_BIAS && W <= 32 && 32 % W == 0 && p.n_chunks == 1 &&
+               3 * p.n_chunk <= 512 && p.ksplit == 1) ? 1 : 0;
   if (p.dxsplit) {
     p.tmem_cols = 3 * p.n_chunk <= 256 ? 256 : 512;
     if (3 * p.n_chunk <= 128) p.tmem_cols = 128;
@@ -937,7 +990,9 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
     FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_, NV_, F16_>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, \
                              mw_hi, mw_lo, mw2_hi, mw2_lo, p));                                                     \
   } while (0)
-  if (a->pre == PRE_GLU_RES_LN && N / 2 > 128) {
+  if (a->pre == PRE_LSTM) {
+    if (f16) FLOWK_LAUNCH_GEMM(PRE_LSTM, 1, true); else FLOWK_LAUNCH_GEMM(PRE_LSTM, 1, false);
+  } else if (a->pre == PRE_GLU_RES_LN && N / 2 > 128) {
     if (f16) FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 2, true); else FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 2, false);
   } else if (a->pre == PRE_GLU_RES_LN) {
     if (f16) FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 1, true); else FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 1, false);

@@ -1,11 +1,16 @@
 """mAR channel prior (mar_prior/corr_prior.py:7-182) with the reference's names and state-dict keys: every latent
 channel is Gaussian with mean / log-std predicted by a ConvLSTM from the previous channels (and, at a split, from an
-embedding of the half that continues through the flow).  Plain torch - outside the flow-step hot path; plugs into
-`flowk.marscf.FlowNet(prior=...)`, which calls it like the reference's `c_prior(z, level, reverse=...)`."""
+embedding of the half that continues through the flow).  Plugs into `flowk.marscf.FlowNet(prior=...)`, which calls it
+like the reference's `c_prior(z, level, reverse=...)`.
+
+On CUDA tensors with autograd off (evaluation, sampling) the networks run on the flowk tensor-core kernels
+(`mar_prior/cuda_path.py`: every conv a tcgen05 implicit GEMM, the LSTM cell fused into the recurrent GEMM's epilogue);
+training (autograd) and CPU tensors use the torch layers below."""
 import numpy as np
 import torch
 import torch.nn as nn
 
+from . import cuda_path
 from .lstm import ConvSeqEncoder
 
 _KERNEL_SIZES = [5, 5, 3, 3, 3, 3, 3]        # corr_prior.py:24-25, indexed by level - 1
@@ -40,9 +45,11 @@ class ChannelPriorUniScale(nn.Module):
         return -0.5 * (logs * 2. + ((z - mean) ** 2) / torch.exp(logs * 2.) + self.Log2PI)
 
     def get_likelihood(self, z):
+        fast = cuda_path.usable(self, z[1] if isinstance(z, (tuple, list)) else z) and not (self.training and self.dp_rate > 0)
         if isinstance(z, (tuple, list)):
             z1, z2 = z
-            z1_embd = self.z1_cond_network(z1).unsqueeze(1).repeat(1, z2.size(1), 1, 1, 1)
+            emb = cuda_path.z1_embedding(self.z1_cond_network, z1) if fast else self.z1_cond_network(z1)
+            z1_embd = emb.unsqueeze(1).repeat(1, z2.size(1), 1, 1, 1)
         else:
             z1_embd, z2 = None, z
         z2 = z2.unsqueeze(2)                                            # [B, T = channels, 1, H, W]
@@ -50,13 +57,19 @@ class ChannelPriorUniScale(nn.Module):
         lstm_input = torch.cat([zero, self.dropout_in(z2.clone())[:, :-1]], dim=1)      # teacher forcing
         if z1_embd is not None:
             lstm_input = torch.cat([lstm_input, z1_embd], dim=2)
-        out, _ = self.prior_lstm(lstm_input, None)
+        if fast:
+            out, _ = cuda_path.run_sequence(self.prior_lstm, lstm_input)
+        else:
+            out, _ = self.prior_lstm(lstm_input, None)
         return torch.sum(self.likelihood(out[:, :, 0:1], out[:, :, 1:2], z2), dim=(1, 2, 3, 4))
 
     def get_sample(self, z1=None, batch_size=None, device=None):
         with torch.no_grad():
+            fast = cuda_path.usable(self, z1 if z1 is not None else
+                                    torch.empty(1, 1, self.height, self.width, device=device or next(self.parameters()).device))
             if z1 is not None:
-                z1_embd = self.z1_cond_network(z1).unsqueeze(1)
+                emb = cuda_path.z1_embedding(self.z1_cond_network, z1) if fast else self.z1_cond_network(z1)
+                z1_embd = emb.unsqueeze(1)
                 b, device = z1.size(0), z1.device
                 lstm_input = torch.cat([z1.new_zeros(b, 1, 1, self.height, self.width), z1_embd], dim=2)
             else:
@@ -66,7 +79,10 @@ class ChannelPriorUniScale(nn.Module):
                 lstm_input = torch.zeros(b, 1, 1, self.height, self.width, device=device)
             hidden, chans = None, []
             for _ in range(self.nc):
-                out, hidden = self.prior_lstm(lstm_input, None, hidden)
+                if fast:
+                    out, hidden = cuda_path.run_sequence(self.prior_lstm, lstm_input, hidden)
+                else:
+                    out, hidden = self.prior_lstm(lstm_input, None, hidden)
                 mean, logs = out[:, :, 0:1], out[:, :, 1:2]
                 sample = torch.randn(mean.size()).to(device) * torch.exp(logs) + mean       # corr_prior.py:96-101
                 chans.append(sample)

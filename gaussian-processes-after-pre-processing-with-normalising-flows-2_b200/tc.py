@@ -6,7 +6,7 @@ import torch
 
 from . import _lib
 from ._lib import (OUT_F32, OUT_HILO, OUT_HILO_CELU, OUT_HILO_POS, OUT_HILO_RELU, OUT_NCHW, PRE_BIAS,  # noqa: F401
-                   PRE_GLU_RES_LN)
+                   PRE_GLU_RES_LN, PRE_LSTM)
 
 
 def _stream():
@@ -70,7 +70,7 @@ def _p(t):
 
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias=None, res=None, gamma=None,
               beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None, trace=None,
-              w2_hi=None, w2_lo=None, out2_f32=None, n2=0, split_k=False, acc_scale=None):
+              w2_hi=None, w2_lo=None, out2_f32=None, n2=0, split_k=False, acc_scale=None, dilation=1):
     """The operand format follows the tensors: fp32 tensors = TF32 pairs (FLOWK_OPERAND_TF32), fp16 tensors = fp16 pairs
     (FLOWK_OPERAND_F16, inference; `acc_scale` undoes the weights' power-of-two pre-scaling).
     `split_k=True` (training path: one stream, kernel latency matters) lends the kernel a workspace so that layers
@@ -80,7 +80,7 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias
                              _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status), _p(trace),
                              B, H, W, Cin, N, taps, pre, out_mask, _p(w2_hi), _p(w2_lo), _p(out2_f32), n2, None,
                              _lib.OPERAND_F16 if a_hi.dtype == torch.float16 else _lib.OPERAND_TF32,
-                             1.0 if acc_scale is None else float(acc_scale))
+                             1.0 if acc_scale is None else float(acc_scale), int(dilation), 0)
     assert a_hi.dtype == a_lo.dtype == w_hi.dtype == w_lo.dtype, "operand pair formats must agree"
     assert out_hi is None or out_hi.dtype == a_hi.dtype, "out_hi/out_lo are written in the input operand format"
     if split_k:

@@ -128,6 +128,10 @@ int flowk_mixture_inv_cdf(const float* y, const float* pi, const float* mu, cons
  *   FLOWK_PRE_BIAS        y = D + bias
  *   FLOWK_PRE_GLU_RES_LN  N = 2C: y = LayerNorm_C((D_a + bias_a) * sigmoid(D_b + bias_b) + res) * gamma + beta
  *                         (GatedConv / GatedAttn gate + residual + norm, mixlogcdf_nn.py:92-101,149-151,257-258)
+ *   FLOWK_PRE_LSTM        N = 4 hid gate columns [i | f | g | o] of a ConvLSTM cell (the mAR channel prior,
+ *                         mar_prior/convolutional_rnn/functional.py:30-52): gates = D + bias + res (res = input-to-hidden
+ *                         gates [M, N] of this step), gamma = c_{t-1} [M, hid]; writes c_t = sig(f) c + sig(i) tanh(g) to
+ *                         out_f32 [M, hid] and h_t = sig(o) tanh(c_t) to out_hi / out_lo [M, hid]; out_mask is ignored
  * `out_mask` selects the forms y is written in (Nout = N, or C after the GLU):
  *   FLOWK_OUT_F32        out_f32[m, Nout]
  *   FLOWK_OUT_HILO       out_hi/out_lo[m, Nout]                       operand of the next GEMM
@@ -136,7 +140,7 @@ int flowk_mixture_inv_cdf(const float* y, const float* pi, const float* mu, cons
  *   FLOWK_OUT_NCHW       out_nchw[b, n, hw]                            (raw parameter tensor for flowk_mixlogcdf_*)
  *   FLOWK_OUT_HILO_RELU  out_hi/out_lo[m, Nout] of max(y, 0)            (NN_net activations, affine_coupling.py:77-78)
  * `status` (device int, may be NULL) is set to 1 if an internal barrier wait timed out (never hangs). */
-enum { FLOWK_PRE_BIAS = 0, FLOWK_PRE_GLU_RES_LN = 1 };
+enum { FLOWK_PRE_BIAS = 0, FLOWK_PRE_GLU_RES_LN = 1, FLOWK_PRE_LSTM = 2 };
 enum { FLOWK_OUT_F32 = 1, FLOWK_OUT_HILO = 2, FLOWK_OUT_HILO_POS = 4, FLOWK_OUT_HILO_CELU = 8, FLOWK_OUT_NCHW = 16,
        FLOWK_OUT_HILO_RELU = 32 };
 
@@ -179,6 +183,10 @@ typedef struct flowk_conv_gemm_args {
    *                           must stay below 65504 in magnitude. */
   int operand_format;
   float acc_scale;
+  /* taps = 25 selects a 5x5 kernel; `dilation` (0 or 1 = dense) spaces the taps of 3x3 / 5x5 kernels ("same" zero padding of
+   * dilation * (k - 1) / 2, mar_prior/convolutional_rnn/functional.py:248-272). */
+  int dilation;
+  int reserved;
 } flowk_conv_gemm_args;
 enum { FLOWK_OPERAND_TF32 = 0, FLOWK_OPERAND_F16 = 1 };
 

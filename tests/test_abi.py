@@ -95,8 +95,8 @@ def test_structs_mirror_the_header():
     """ctypes mirrors of the C structs have the layout the header declares (8-byte pointers, 4-byte ints)."""
     assert ctypes.sizeof(_lib.WnJob) == 8 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.AdamaxChunk) == 4 * 8 + 8
-    # N2 is padded to 8 before splitk_ws; operand_format (int) + acc_scale (float) fill the last 8 bytes
-    assert ctypes.sizeof(_lib.ConvGemmArgs) == 15 * 8 + 8 * 4 + 3 * 8 + 8 + 8 + 8
+    # N2 is padded to 8 before splitk_ws; then operand_format (int) + acc_scale (float), dilation (int) + reserved (int)
+    assert ctypes.sizeof(_lib.ConvGemmArgs) == 15 * 8 + 8 * 4 + 3 * 8 + 8 + 8 + 8 + 8
 
 
 def test_no_cpu_fallback():
