@@ -82,10 +82,12 @@ static int launch_affine(const float* x, const float* h, float* y, const float* 
   if (!x || !h || !y) return FLOWK_ERR_ARG;
   if (ldj_out && !ws) return FLOWK_ERR_ARG;
   const long long E = (long long)(C / 2) * HW;
-  const bool vec4 = (HW % 4 == 0) && aligned16(x) && aligned16(h) && aligned16(y) && E >= 4096;
+  const bool vec4 = (HW % 4 == 0) && aligned16(x) && aligned16(h) && aligned16(y);
   LdjWs w = carve_ws(ws, B);
   if (vec4) {
-    dim3 grid(parts_for(E, kThreads * 4), B);
+    // 128-bit accesses whenever the rows allow it; a CTA takes up to 4 vectors per thread, so small samples (E = 1536 at the
+    // first CIFAR level) are ONE CTA each and need no cross-CTA reduction
+    dim3 grid(parts_for(E, kThreads * 4 * (B >= 2 * 148 ? 4 : 1)), B);
     affine_kernel<4, MODE><<<grid, kThreads, 0, st>>>(x, h, y, ldj_in, ldj_out, w, C, HW);
   } else {
     dim3 grid(parts_for(E, kThreads), B);

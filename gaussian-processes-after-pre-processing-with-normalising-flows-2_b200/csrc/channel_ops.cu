@@ -169,19 +169,21 @@ __global__ void __launch_bounds__(128) channel_mix_kernel(const float* __restric
                                                           const float* __restrict__ bias, float* __restrict__ y,
                                                           const float* __restrict__ ldj_in,
                                                           const float* __restrict__ ldj_add,
-                                                          float* __restrict__ ldj_out, int H, int W) {
+                                                          float* __restrict__ ldj_out, int B, int H, int W) {
   __shared__ __align__(16) float w_s[C * C];
   __shared__ float b_s[C];
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) w_s[i] = Wm[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) b_s[i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int HW = H * W;
-  const int b = blockIdx.y;
-  if (ldj_out && blockIdx.x == 0 && threadIdx.x == 0)
-    ldj_out[b] = (ldj_in ? ldj_in[b] : 0.f) + (ldj_add ? ldj_add[0] : 0.f);
-
-  const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * PIX;
-  if (p0 >= HW) return;
+  // Pixel groups are numbered across the WHOLE batch (groups per image = ceil(HW / PIX)): small feature maps (4x4, 8x8)
+  // still fill every lane of the CTA, and the C x C matrix is staged once per 128 pixel groups instead of once per image.
+  const int gpi = (HW + PIX - 1) / PIX;
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= (long long)B * gpi) return;
+  const int b = (int)(gidx / gpi);
+  const int p0 = (int)(gidx - (long long)b * gpi) * PIX;
+  if (ldj_out && p0 == 0) ldj_out[b] = (ldj_in ? ldj_in[b] : 0.f) + (ldj_add ? ldj_add[0] : 0.f);
   const float* xb = x + (size_t)b * C * HW;
   float* yb = y + (size_t)b * C * HW;
 
@@ -282,11 +284,12 @@ static int launch_mix(const float* x, const float* Wm, const float* bias, float*
   const bool vec4 = kCanVec4 && (HW % 4 == 0) && ((long long)B * HW >= 4LL * 148 * 128 * 4) && aligned16(x) &&
                     aligned16(y) && SQ == 0;
   if (vec4) {
-    dim3 grid((HW / 4 + 127) / 128, B);
-    channel_mix_kernel<C, kCanVec4 ? 4 : 1, SQ><<<grid, 128, 0, st>>>(x, Wm, bias, y, ldj_in, ldj_add, ldj_out, H, W);
+    const long long groups = (long long)B * (HW / 4);
+    channel_mix_kernel<C, kCanVec4 ? 4 : 1, SQ><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(x, Wm, bias, y, ldj_in, ldj_add,
+                                                                                                 ldj_out, B, H, W);
   } else {
-    dim3 grid((HW + 127) / 128, B);
-    channel_mix_kernel<C, 1, SQ><<<grid, 128, 0, st>>>(x, Wm, bias, y, ldj_in, ldj_add, ldj_out, H, W);
+    const long long groups = (long long)B * HW;
+    channel_mix_kernel<C, 1, SQ><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(x, Wm, bias, y, ldj_in, ldj_add, ldj_out, B, H, W);
   }
   return launch_status();
 }
