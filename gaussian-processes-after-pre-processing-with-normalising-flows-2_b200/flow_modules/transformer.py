@@ -73,10 +73,40 @@ class Transformer_attn(nn.Module):
             self._g = (key, g)
         return g
 
+    def _kernel_operands(self):
+        """(G [C, C], prm = {offset, offset2, offset3, scale}) for flowk_patch_attention, cached per weight version."""
+        ps = (self.convq1, self.convk1, self.convq2, self.convk2, self.convq3, self.convk3, self.offset, self.offset2,
+              self.offset3, self.scale)
+        key = _lib.param_key(ps)
+        hit = getattr(self, "_kop", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                g = self._bilinear()[:, :, 0, 0].contiguous().float()
+                prm = torch.cat([t.reshape(1) for t in (self.offset, self.offset2, self.offset3, self.scale)]).float().contiguous()
+            hit = self._kop = (key, g, prm)
+        return hit[1], hit[2]
+
     def forward(self, input, logdet=0, reverse=False, permute=False):
         z = input
         b, c, h, w = z.shape
         assert h == w and w % 2 == 0, "Transformer_attn expects square maps with an even side"
+        if (z.is_cuda and z.dtype == torch.float32 and (c * h * w + c * c) * 4 <= 200 * 1024 and
+                not (torch.is_grad_enabled() and (z.requires_grad or any(q.requires_grad for q in self.parameters())))):
+            # inference / sampling: one fused flowk kernel (csrc/patch_attention.cu), one read + one write of the activations
+            g, prm = self._kernel_operands()
+            _lib.check_device(z, "Transformer_attn")
+            z = z.contiguous()
+            out = torch.empty_like(z)
+            ld_in = None
+            if torch.is_tensor(logdet) and logdet.dim() == 1 and logdet.shape[0] == b:
+                ld_in = logdet.float().contiguous()
+            ld_out = torch.empty(b, device=z.device, dtype=torch.float32)
+            _lib.call("flowk_patch_attention", z.data_ptr(), g.data_ptr(), prm.data_ptr(), out.data_ptr(),
+                      None if ld_in is None else ld_in.data_ptr(), ld_out.data_ptr(), b, c, h, w, int(bool(permute)),
+                      int(bool(reverse)), torch.cuda.current_stream().cuda_stream)
+            if ld_in is None:
+                ld_out = ld_out + logdet                         # scalar / broadcastable start value
+            return out, ld_out
         p = w // 2
         full = _patches(z, p)                                   # [B, 4, L]
         mask = self._mask(full.shape[1], full.shape[2], permute, z)

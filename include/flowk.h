@@ -328,6 +328,14 @@ int flowk_attention(const float* qkv, float* out_hi, float* out_lo, int B, int H
 int flowk_attention_f16(const float* qkv, void* out_hi, void* out_lo, int B, int HW, int C, int heads,
                         flowk_stream_t stream);
 
+/* `Transformer_attn`, the fork's invertible patch attention (reference flow_modules/transformer.py:123-326; two per FlowStep,
+ * marscf_main.py:50-51,69-70), inference / sampling, one pass: x, y [B, C, H, W] fp32 (H == W even); G [C, C] =
+ * sum_i Wq_i^T Wk_i; prm = device {offset, offset2, offset3, scale}; ldj_in / ldj_out [B] (NULL allowed).  Forward mixes
+ * the free entries of patches (0, 2) / (1, 3) with the 2x2 attention matrices and adds (log|det M1| + log|det M2|) p (p/2) C
+ * to ldj; reverse applies the closed-form inverses and subtracts. */
+int flowk_patch_attention(const float* x, const float* G, const float* prm, float* y, const float* ldj_in, float* ldj_out,
+                          int B, int C, int H, int W, int permute, int reverse, flowk_stream_t stream);
+
 /* The same attention core on tcgen05 (csrc/attention_tc.cu): S = Q K^T and O = P V as kind::f16 MMAs with TMEM accumulators,
  * fp16 (hi, lo) operand tiles built in shared memory, softmax between them; out_f16 selects fp16 or TF32-in-fp32 output
  * pairs.  Takes HW in {128, 256} with C/heads a multiple of 8 and <= 64; FLOWK_ERR_SHAPE otherwise (use flowk_attention).

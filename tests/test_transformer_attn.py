@@ -97,3 +97,30 @@ def test_full_model_with_attn_matches_oracle():
     z_o, outs, ldj_o, nll_o = O.normal_flow(sd, x.cpu(), noise.cpu(), 2, 2, "affine", attn=True)
     torch.testing.assert_close(z.cpu(), z_o, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(nll.cpu(), nll_o, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,H,B", [(12, 16, 64), (24, 8, 64), (48, 4, 64), (12, 32, 5), (96, 4, 3)])
+def test_patch_attention_kernel_matches_torch_ops(C, H, B):
+    """csrc/patch_attention.cu (the fused inference / sampling kernel) against the torch-op form of the same layer (taken
+    when autograd is on) at every level shape of the BASELINE configs, both mask parities, forward and reverse."""
+    from flowk import _lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(C + H)
+    m = Transformer_attn(C).to(dev).eval()
+    with torch.no_grad():
+        m.scale.fill_(7.0)                                      # make the attention matrices depend visibly on the scores
+    x = torch.randn(B, C, H, H, device=dev)
+    ld0 = torch.randn(B, device=dev)
+    for permute in (False, True):
+        for reverse in (False, True):
+            _lib.TIMING = {}
+            try:
+                with torch.no_grad():
+                    y, ld = m(x, logdet=ld0, reverse=reverse, permute=permute)
+                assert "flowk_patch_attention" in _lib.TIMING
+            finally:
+                _lib.TIMING = None
+            y_t, ld_t = m(x.clone().requires_grad_(), logdet=ld0, reverse=reverse, permute=permute)     # torch ops
+            assert float((y - y_t).abs().max()) <= 1e-5 * max(1.0, float(y_t.abs().max()))
+            assert float((ld - ld_t).abs().max()) <= 1e-4 * max(1.0, float(ld_t.abs().max()))
