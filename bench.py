@@ -492,6 +492,10 @@ def run_flowk(args):
     if not args.no_inverse:
         inverse = inverse_leg(args, model, device, rank, world, dist)
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        other = other_configs_leg(args, device)
+
     mar = None
     if not args.no_mar:
         mar = mar_prior_leg(args, device, rank, world, dist)
@@ -529,6 +533,7 @@ def run_flowk(args):
             "train_strong": train_strong,
             "inverse": inverse,
             "mar_prior": mar,
+            "other_configs": other,
             "roofline_flow_kernels": roofline_flow_kernels,
             "elementwise_bytes_per_image": ew_bytes,
             "kernels": kernels,
@@ -632,6 +637,54 @@ def inverse_leg(args, model, device, rank, world, dist):
             "finite": finite,
             "note": "sampling = inverse pass of the whole stack incl. drawing the latents; MixLogCDF: register-resident "
                     "per-element bisection (log_dist.py:43-72), affine: closed form"}
+
+
+def other_configs_leg(args, device):
+    """Driver-visible numbers for the BASELINE.json configs the headline does not run (rank 0, one GPU, a few seconds
+    each): forward (z, log-det, bits/dim) and inverse (sampling) images/s by CUDA-graph replay, `depth` batches in flight.
+    Parity of each config at its real width is tests/test_gpu_parity.py::test_baseline_config_vs_oracle."""
+    from flowk.graphs import DensityPipeline, GraphedSampler
+    out = {}
+    for name in ("cfg1", "cfg3", "cfg4", "cfg5"):
+        if name == args.workload:
+            continue
+        coupling, image, L, K, hidden, batch = WORKLOADS[name]
+        model = build_model(name, device)
+        xs = [t.to(device) for t in synthetic_batches(4, batch, image, seed=400)]
+        depth = max(1, args.depth)
+        pipe = DensityPipeline(model, xs[0], depth=depth)
+        lanes = [GraphedSampler(model, batch, image) for _ in range(depth)]
+
+        def fwd(steps):
+            for i in range(steps):
+                pipe.submit(xs[i % len(xs)])
+            pipe.drain()
+
+        def inv(steps):
+            for i in range(steps):
+                lanes[i % depth].run()
+            for lane in lanes:
+                torch.cuda.current_stream().wait_stream(lane.stream)
+
+        res = {}
+        for key, fn in (("forward", fwd), ("inverse", inv)):
+            fn(3)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = max(5, args.steps)
+            s.record()
+            fn(steps)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e)
+            res[key] = {"value": batch * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps}
+        res["workload"] = DESCRIBE[name]
+        res["batch"] = batch
+        res["batches_in_flight"] = depth
+        out[name] = res
+        del pipe, lanes, model
+        torch.cuda.empty_cache()
+    return out
 
 
 def mar_prior_leg(args, device, rank, world, dist):
@@ -791,6 +844,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--no-inverse", action="store_true")
     ap.add_argument("--no-mar", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "flowk" else args.warmup
     if args.impl == "reference":

@@ -213,6 +213,12 @@ __global__ void __launch_bounds__(128) channel_mix_kernel(const float* __restric
       float4 t = ld_stream4(xb + (size_t)i * HW + p0);
       v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
     }
+  } else if (PIX == 2 && SQ != 1 && full) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      float2 t = __ldcs(reinterpret_cast<const float2*>(xb + (size_t)i * HW + p0));
+      v[i][0] = t.x; v[i][PIX - 1] = t.y;
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < C; ++i)
@@ -239,6 +245,8 @@ __global__ void __launch_bounds__(128) channel_mix_kernel(const float* __restric
     }
     if (PIX == 4 && SQ != 2 && full) {
       st_stream4(yb + (size_t)o * HW + p0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    } else if (PIX == 2 && SQ != 2 && full) {
+      __stcs(reinterpret_cast<float2*>(yb + (size_t)o * HW + p0), make_float2(acc[0], acc[PIX - 1]));
     } else {
 #pragma unroll
       for (int q = 0; q < PIX; ++q)
@@ -283,6 +291,16 @@ static int launch_mix(const float* x, const float* Wm, const float* bias, float*
   constexpr bool kCanVec4 = (C <= 24);
   const bool vec4 = kCanVec4 && (HW % 4 == 0) && ((long long)B * HW >= 4LL * 148 * 128 * 4) && aligned16(x) &&
                     aligned16(y) && SQ == 0;
+  // wider matrices: two pixels per thread halve the shared-memory (matrix) reads per FMA, the bound of this kernel for C >= 32
+  constexpr bool kCanVec2 = (C > 24 && C <= 48);
+  const bool vec2 = kCanVec2 && (HW % 2 == 0) && ((long long)B * HW >= 2LL * 148 * 128 * 4) && SQ == 0 &&
+                    (reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0;
+  if (vec2) {
+    const long long groups = (long long)B * (HW / 2);
+    channel_mix_kernel<C, kCanVec2 ? 2 : 1, SQ><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(x, Wm, bias, y, ldj_in, ldj_add,
+                                                                                                 ldj_out, B, H, W);
+    return launch_status();
+  }
   if (vec4) {
     const long long groups = (long long)B * (HW / 4);
     channel_mix_kernel<C, kCanVec4 ? 4 : 1, SQ><<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(x, Wm, bias, y, ldj_in, ldj_add,
