@@ -115,7 +115,11 @@ ATTENTION_TC = __import__("os").environ.get("FLOWK_ATTENTION_TC", "1") != "0"
 def attention_tc_supported(HW, C, heads):
     """Shapes the tcgen05 attention kernel (csrc/attention_tc.cu) takes; everything else runs on the mma.sync kernel."""
     d = C // max(heads, 1)
-    return ATTENTION_TC and C % heads == 0 and HW in (128, 256) and d % 8 == 0 and d <= 64 and C % 4 == 0
+    if not (ATTENTION_TC and C % heads == 0 and HW in (128, 256) and d % 8 == 0 and d <= 64 and C % 4 == 0):
+        return False
+    dk = (d + 15) // 16 * 16                     # shared memory: P (over Q, K) + V^T + epilogue staging + static
+    smem = max(4 * (HW // 64) * 128 * 64, 4 * HW * 128) + 2 * (HW // 64) * dk * 128 + 2 * 128 * (d // 8) * 16 + 9 * 1024
+    return smem <= 227 * 1024
 
 
 def attention(qkv, B, HW, C, heads, f16=False, status=None, trace=None):
