@@ -162,10 +162,11 @@ def test_attention_matches_fp64(tc, fmt, B, HW, C, heads):
 
 @pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("B,HW,C,heads", [(64, 256, 96, 4), (3, 128, 64, 4), (2, 256, 160, 4), (5, 256, 32, 4),
-                                          (2, 128, 256, 4), (1, 256, 64, 1)])
+                                          (2, 128, 256, 4), (1, 128, 64, 1), (3, 256, 48, 1)])
 def test_attention_tcgen05_matches_fp64_and_mma_sync(tc, fmt, B, HW, C, heads):
     """csrc/attention_tc.cu (S = Q K^T and O = P V on tcgen05, softmax from TMEM) against fp64 and against the mma.sync
-    kernel it replaces for seq in {128, 256}; head dims 8, 16, 24, 40, 64 (24 and 40 exercise the zero-padded K = 16 step)."""
+    kernel it replaces for seq in {128, 256}; head dims 8, 16, 24, 40, 48, 64 (24 and 40 exercise the zero-padded K = 16 step;
+    seq 256 with head dim 64 exceeds the shared memory and stays on the mma.sync kernel)."""
     from flowk import _lib
     dev = torch.device("cuda:0")
     assert tc.attention_tc_supported(HW, C, heads)
