@@ -27,38 +27,42 @@ __global__ void __launch_bounds__(PA_THREADS) patch_attention_kernel(const float
   extern __shared__ __align__(16) float sm[];
   const int HW = H * W, n_el = C * HW, p = W >> 1, pp = p * p;
   float* xs = sm;                         // [C][H][W]
-  float* gs = sm + ((n_el + 3) & ~3);     // [C][C]
+  float* xm = sm + ((n_el + 3) & ~3);     // the same with the free entries zeroed (the conditioning part the scores see)
+  float* gs = xm + ((n_el + 3) & ~3);     // [C][C]
   __shared__ float red[PA_THREADS / 32][8];
   __shared__ float mat[8];                // a1 b1 c1 d1 a2 b2 c2 d2 (already inverted when reverse)
   const int b = blockIdx.x;
   const float* xb = x + (size_t)b * n_el;
   float* yb = y + (size_t)b * n_el;
-  for (int i = threadIdx.x; i < n_el; i += PA_THREADS) xs[i] = __ldcs(xb + i);
-  for (int i = threadIdx.x; i < C * C; i += PA_THREADS) gs[i] = __ldg(G + i);
-  __syncthreads();
-
   // conditioning mask of entry l = c p^2 + i p + j of patch n: (n + l) even, inverted by `permute`
   const int perm = permute ? 1 : 0;
   auto is_cond = [&](int n, int c, int i, int j) -> bool { return (((n + c * pp + i * p + j) & 1) ^ perm) == 0; };
+  for (int e = threadIdx.x; e < n_el; e += PA_THREADS) {
+    const float v = __ldcs(xb + e);
+    const int xx = e % W, t = e / W, yy = t % H, c = t / H;
+    const int lower = yy >= p, right = xx >= p;
+    xs[e] = v;
+    xm[e] = is_cond((lower << 1) | right, c, yy - (lower ? p : 0), xx - (right ? p : 0)) ? v : 0.f;
+  }
+  for (int i = threadIdx.x; i < C * C; i += PA_THREADS) gs[i] = __ldg(G + i);
+  __syncthreads();
 
   // ---- scores: item = (patch m, in-patch pixel, output channel c): v = sum_c' G[c, c'] u_m[c'], then u_n[c] v for both n
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // (0,0) (0,2) (2,0) (2,2) (1,1) (1,3) (3,1) (3,3)
   for (int it = threadIdx.x; it < n_el; it += PA_THREADS) {
     const int c = it % C, r = it / C, m = r & 3, pix = r >> 2;
     const int i = pix / p, j = pix - i * p;
-    const int ym = i + ((m >> 1) ? p : 0), xm = j + ((m & 1) ? p : 0);
+    const int ym = i + ((m >> 1) ? p : 0), xm_col = j + ((m & 1) ? p : 0);
     float v = 0.f;
     const float* grow = gs + c * C;
-    const float* xcol = xs + ym * W + xm;
-    for (int cc = 0; cc < C; ++cc) {
-      const float u = is_cond(m, cc, i, j) ? xcol[cc * HW] : 0.f;
-      v = fmaf(grow[cc], u, v);
-    }
+    const float* xcol = xm + ym * W + xm_col;
+#pragma unroll 4
+    for (int cc = 0; cc < C; ++cc) v = fmaf(grow[cc], xcol[cc * HW], v);
     // rows n of equal parity: n = m & 1 (upper patch) and n = (m & 1) + 2 (lower patch)
     const int n0 = m & 1, n1 = n0 + 2;
     const int y0 = i, x0 = j + (n0 ? p : 0), y1 = i + p, x1 = x0;
-    const float u0 = is_cond(n0, c, i, j) ? xs[(c * H + y0) * W + x0] : 0.f;
-    const float u1 = is_cond(n1, c, i, j) ? xs[(c * H + y1) * W + x1] : 0.f;
+    const float u0 = xm[(c * H + y0) * W + x0];
+    const float u1 = xm[(c * H + y1) * W + x1];
     const int base = (m & 1) ? 4 : 0, col = m >> 1;               // score[n, m]: column index of m within its parity class
     acc[base + col] += u0 * v;                                     // n = n0 (row 0 of the 2x2 block)
     acc[base + 2 + col] += u1 * v;                                 // n = n1 (row 1)
@@ -123,7 +127,7 @@ extern "C" int flowk_patch_attention(const float* x, const float* G, const float
   if (B < 0 || C < 1 || H < 2 || H != W || (W & 1)) return FLOWK_ERR_SHAPE;
   if (B == 0) return FLOWK_OK;
   if (!x || !G || !prm || !y) return FLOWK_ERR_ARG;
-  const size_t smem = ((size_t)((C * H * W + 3) & ~3) + (size_t)C * C) * sizeof(float);
+  const size_t smem = ((size_t)2 * ((C * H * W + 3) & ~3) + (size_t)C * C) * sizeof(float);
   if (smem > 200 * 1024) return FLOWK_ERR_SHAPE;
   static size_t smem_set = 48 * 1024;
   if (smem > smem_set) {
