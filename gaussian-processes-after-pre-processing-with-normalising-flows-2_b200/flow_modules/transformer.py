@@ -90,7 +90,7 @@ class Transformer_attn(nn.Module):
         z = input
         b, c, h, w = z.shape
         assert h == w and w % 2 == 0, "Transformer_attn expects square maps with an even side"
-        if (z.is_cuda and z.dtype == torch.float32 and (c * h * w + c * c) * 4 <= 200 * 1024 and
+        if (z.is_cuda and z.dtype == torch.float32 and (2 * c * h * w + c * c) * 4 <= 200 * 1024 and
                 not (torch.is_grad_enabled() and (z.requires_grad or any(q.requires_grad for q in self.parameters())))):
             # inference / sampling: one fused flowk kernel (csrc/patch_attention.cu), one read + one write of the activations
             g, prm = self._kernel_operands()
