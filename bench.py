@@ -839,7 +839,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-oracle step (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large", action="store_true")
-    ap.add_argument("--depth", type=int, default=6, help="batches in flight (graph instances on separate streams)")
+    ap.add_argument("--depth", type=int, default=10, help="batches in flight (graph instances on separate streams)")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--no-inverse", action="store_true")

@@ -84,7 +84,7 @@ class ConvGemmArgs(ctypes.Structure):
                [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")] + \
                [(n, ctypes.c_void_p) for n in ("w2_hi", "w2_lo", "out2_f32")] + [("N2", ctypes.c_int)] + \
                [("splitk_ws", ctypes.c_void_p), ("operand_format", ctypes.c_int), ("acc_scale", ctypes.c_float),
-                ("dilation", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("dilation", ctypes.c_int), ("acc_scale2", ctypes.c_float)]
 
 
 class WnJob(ctypes.Structure):

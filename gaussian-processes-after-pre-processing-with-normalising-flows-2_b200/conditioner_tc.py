@@ -21,8 +21,9 @@ from . import _lib, tc
 F16 = os.environ.get("FLOWK_F16", "1") != "0"   # operand format of the inference chain: fp16 (hi, lo) pairs (tcgen05
                     # kind::f16: half the operand bytes, twice the MMA rate, same 22-bit accuracy) or TF32 pairs ("0")
 ENABLED = True      # set False to force the torch/cuDNN conditioner (used by tests to A/B the two paths)
-CHAIN = False       # gate -> in_proj fused into one launch (works, tested; measured no faster than two PDL launches: the
-                    # second GEMM's weights cannot be prefetched for lack of shared memory) - off by default
+CHAIN = os.environ.get("FLOWK_CHAIN", "1") != "0"   # gate -> LayerNorm -> (+pos) -> in_proj as ONE launch: the epilogue warps
+                    # write the normalised rows as (hi, lo) operand tiles into swizzled shared memory and the MMA warp runs
+                    # the second GEMM while its weights stream in behind the GLU / LayerNorm epilogue
 
 
 def supported(channels, h, w):
@@ -127,13 +128,13 @@ def mixlogcdf_nn_raw(nn_module, x_id, status=None):
         if has_attn:
             pos = nn_module.mid_convs[bi].attn._pos_enc(HW, C, dev).reshape(HW, C).contiguous()
             qkv = buf(M, 3 * C)
-            if CHAIN and not F16 and tc.chain_supported(C, 3 * C):
+            if CHAIN and tc.chain_supported(C, 3 * C, F16):
                 # G2 + G3 in one launch: the normalised rows (+ positional encoding) go from the epilogue into swizzled
                 # shared-memory operand tiles and are multiplied by in_proj's weight in the same CTA
-                w3_hi, w3_lo, _, _ = blk["in_proj"]
+                w3_hi, w3_lo, _, sc3 = blk["in_proj"]
                 tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN, tc.OUT_F32, bias=bias,
                              res=x, gamma=blk["ln1"][0], beta=blk["ln1"][1], pos=pos, out_f32=x1, status=status,
-                             w2_hi=w3_hi, w2_lo=w3_lo, out2_f32=qkv, n2=3 * C)
+                             w2_hi=w3_hi, w2_lo=w3_lo, out2_f32=qkv, n2=3 * C, acc_scale=sc, acc_scale2=sc3)
             else:
                 p_hi, p_lo = obuf(M, C), obuf(M, C)
                 tc.conv_gemm(c1_hi, c1_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN,

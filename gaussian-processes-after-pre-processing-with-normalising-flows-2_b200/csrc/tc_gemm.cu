@@ -70,6 +70,7 @@ struct Params {
   int chain, n2, n2_chunk, n2_chunks, a3_offset, w2_offset;
   float* out2_f32;                 // [M, n2]
   float acc_scale;                 // F16: the weights were scaled by 1 / acc_scale (a power of two)
+  float acc_scale2;                // the same for the chained second GEMM's weights
   int ksplit;                      // > 1: blockIdx.z takes a slice of every tap's channel blocks; fp32 partial rows go to
                                    // out_f32 + z*M*N (no bias) and flowk's split-K reduce kernel finishes the layer
   int* status;                     // set to 1 if a barrier wait timed out
@@ -199,13 +200,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         // GEMM to retire; the load then hides behind the GLU/LayerNorm epilogue
         mbar_wait(tmem_full_bar, 0, failed);
         const int w2_chunk_bytes = p.n2_chunk * ROW_BYTES, w2_half = w2_chunk_bytes * p.n2_chunks;
-        const int kb2 = (p.N >> 1) / BLOCK_K;
+        const int kb2 = ((p.N >> 1) + BK - 1) / BK;
         for (int kb = 0; kb < kb2; ++kb) {
           mbar_wait(w2_empty_bar, ((uint32_t)kb & 1u) ^ 1u, failed);
           mbar_expect_tx(w2_full_bar, 2u * (uint32_t)w2_half);
           for (int c = 0; c < p.n2_chunks; ++c) {
-            tma_load_2d(smem + p.w2_offset + c * w2_chunk_bytes, &map_w2_hi, w2_full_bar, kb * BLOCK_K, c * p.n2_chunk);
-            tma_load_2d(smem + p.w2_offset + w2_half + c * w2_chunk_bytes, &map_w2_lo, w2_full_bar, kb * BLOCK_K,
+            tma_load_2d(smem + p.w2_offset + c * w2_chunk_bytes, &map_w2_hi, w2_full_bar, kb * BK, c * p.n2_chunk);
+            tma_load_2d(smem + p.w2_offset + w2_half + c * w2_chunk_bytes, &map_w2_lo, w2_full_bar, kb * BK,
                         c * p.n2_chunk);
           }
         }
@@ -282,8 +283,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       if (p.chain) {
         mbar_wait(a3_full_bar, 0, failed);                           // epilogue warps have written the operand tiles
         tc_fence_after();
-        const uint32_t idesc2 = make_idesc(p.n2_chunk);           // (chain mode is tf32-only: checked on the host)
-        const int kb2 = (p.N >> 1) / BLOCK_K;
+        const uint32_t idesc2 = make_idesc_t<F16>(p.n2_chunk);
+        const int kb2 = ((p.N >> 1) + BK - 1) / BK;
         const uint32_t w2_half = (uint32_t)(p.n2_chunk * ROW_BYTES * p.n2_chunks);
         const uint64_t chunk2_units = (uint64_t)((uint32_t)(p.n2_chunk * ROW_BYTES) >> 4);
         for (int kb = 0; kb < kb2; ++kb) {
@@ -293,15 +294,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const uint64_t da_lo = da_hi + (A_TILE_BYTES >> 4);
           const uint64_t db_hi = make_smem_desc(smem_u32(smem + p.w2_offset)), db_lo = db_hi + (w2_half >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);
             for (int c = 0; c < p.n2_chunks; ++c) {
               const uint64_t co = ko + c * chunk2_units;
               const uint32_t d = tmem_base + p.N + c * p.n2_chunk;   // second accumulator: columns after the first
-              if ((kb | k) == 0) umma_tf32(d, da_hi + ko, db_hi + co, idesc2, 0u);
-              else umma_tf32_acc(d, da_hi + ko, db_hi + co, idesc2);
-              umma_tf32_acc(d, da_lo + ko, db_hi + co, idesc2);
-              umma_tf32_acc(d, da_hi + ko, db_lo + co, idesc2);
+              umma<F16>(d, da_hi + ko, db_hi + co, idesc2, (kb | k) == 0 ? 0u : 1u);
+              umma<F16>(d, da_lo + ko, db_hi + co, idesc2, 1u);
+              umma<F16>(d, da_hi + ko, db_lo + co, idesc2, 1u);
             }
           }
           umma_commit(w2_empty_bar);
@@ -554,7 +554,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c4 = v * 128 + lane * 4;
-        if (v >= nv || c4 >= C) continue;
+        if (v >= nv || c4 >= C) {
+          // fp16 chain: the second GEMM's last 64-channel k-block is zero beyond C; the lanes that own no column write it
+          if (F16 && p.chain && v < nv && c4 < ((C + 63) & ~63)) {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const int R = lane_grp * 32 + sub * 8 + rr;
+              uint8_t* t = smem + p.a3_offset + (size_t)(c4 >> 6) * 2 * A_TILE_BYTES + R * 128 + ((((c4 & 63) >> 3) ^ (R & 7)) << 4) +
+                           ((c4 & 7) << 1);
+              *reinterpret_cast<uint2*>(t) = make_uint2(0u, 0u);
+              *reinterpret_cast<uint2*>(t + A_TILE_BYTES) = make_uint2(0u, 0u);
+            }
+          }
+          continue;
+        }
         const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + c4));
         const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c4));
         const float gs[4] = {ga.x, ga.y, ga.z, ga.w}, bs[4] = {be.x, be.y, be.z, be.w};
@@ -563,10 +576,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const int m = slab_row0 + sub * 8 + rr;
           if (m >= p.M) {
             if (p.chain) {
-              const int R = lane_grp * 32 + sub * 8 + rr, kb = c4 >> 5, chunk = (c4 & 31) >> 2;
-              uint8_t* t = smem + p.a3_offset + (size_t)kb * 2 * A_TILE_BYTES + R * 128 + ((chunk ^ (R & 7)) << 4);
-              *reinterpret_cast<float4*>(t) = make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(t + A_TILE_BYTES) = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int R = lane_grp * 32 + sub * 8 + rr;
+              if (F16) {
+                uint8_t* t = smem + p.a3_offset + (size_t)(c4 >> 6) * 2 * A_TILE_BYTES + R * 128 +
+                             ((((c4 & 63) >> 3) ^ (R & 7)) << 4) + ((c4 & 7) << 1);
+                *reinterpret_cast<uint2*>(t) = make_uint2(0u, 0u);
+                *reinterpret_cast<uint2*>(t + A_TILE_BYTES) = make_uint2(0u, 0u);
+              } else {
+                const int kb = c4 >> 5, chunk = (c4 & 31) >> 2;
+                uint8_t* t = smem + p.a3_offset + (size_t)kb * 2 * A_TILE_BYTES + R * 128 + ((chunk ^ (R & 7)) << 4);
+                *reinterpret_cast<float4*>(t) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(t + A_TILE_BYTES) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
             }
             continue;
           }
@@ -596,13 +617,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             // operand of the chained GEMM, written where the tensor core will read it: K-major tile of 128 rows x 128 B
             // per 32-column block, 16-byte chunks XOR-swizzled with (row % 8) - the layout a SWIZZLE_128B TMA load
             // would have produced
-            const int R = lane_grp * 32 + sub * 8 + rr, kb = c4 >> 5, chunk = (c4 & 31) >> 2;
-            float h[4], l[4];
+            const int R = lane_grp * 32 + sub * 8 + rr;
+            if (F16) {                               // 64 channels per 128-byte row: this lane's 4 columns are half a 16-byte chunk
+              unsigned short h[4], l[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_tf32(y[i] + pe[rr][v][i], h[i], l[i]);
-            uint8_t* t = smem + p.a3_offset + (size_t)kb * 2 * A_TILE_BYTES + R * 128 + ((chunk ^ (R & 7)) << 4);
-            *reinterpret_cast<float4*>(t) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(t + A_TILE_BYTES) = make_float4(l[0], l[1], l[2], l[3]);
+              for (int i = 0; i < 4; ++i) split_f16(y[i] + pe[rr][v][i], h[i], l[i]);
+              uint8_t* t = smem + p.a3_offset + (size_t)(c4 >> 6) * 2 * A_TILE_BYTES + R * 128 +
+                           ((((c4 & 63) >> 3) ^ (R & 7)) << 4) + ((c4 & 7) << 1);
+              *reinterpret_cast<uint2*>(t) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+              *reinterpret_cast<uint2*>(t + A_TILE_BYTES) =
+                  make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+            } else {
+              const int kb = c4 >> 5, chunk = (c4 & 31) >> 2;
+              float h[4], l[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) split_tf32(y[i] + pe[rr][v][i], h[i], l[i]);
+              uint8_t* t = smem + p.a3_offset + (size_t)kb * 2 * A_TILE_BYTES + R * 128 + ((chunk ^ (R & 7)) << 4);
+              *reinterpret_cast<float4*>(t) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(t + A_TILE_BYTES) = make_float4(l[0], l[1], l[2], l[3]);
+            }
           }
         }
       }
@@ -616,13 +649,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         tc_fence_after();
         if (tracing && threadIdx.x == 64) p.trace[10] = clock64();
         const int n2 = p.n2, pitch2 = n2 + 4;
+        const float sc2 = F16 ? p.acc_scale2 : 1.f;
         float* slab2 = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch2);   // all smem is idle again
         for (int j = sub * 16; j < n2; j += 16 * (EPI_WARPS / 4)) {
           float v16[16];
           tmem_ld16(trow + p.N + j, v16);
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(slab2 + lane * pitch2 + j + i) = make_float4(v16[i], v16[i + 1], v16[i + 2], v16[i + 3]);
+            *reinterpret_cast<float4*>(slab2 + lane * pitch2 + j + i) =
+                make_float4(v16[i] * sc2, v16[i + 1] * sc2, v16[i + 2] * sc2, v16[i + 3] * sc2);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         for (int c4 = lane * 4; c4 < n2; c4 += 128) {
@@ -942,16 +977,18 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   p.chain = 0;
   if (a->w2_hi && a->w2_lo && a->out2_f32 && a->N2 > 0) {
     const int C = N / 2, n2 = a->N2;
-    if (f16) return FLOWK_ERR_ARG;                           // the chained second GEMM exists for tf32 operands only
-    if (a->pre != PRE_GLU_RES_LN || p.n_chunks != 1 || C % BLOCK_K || n2 % 16 || N + n2 > 512) return FLOWK_ERR_SHAPE;
+    if (a->pre != PRE_GLU_RES_LN || p.n_chunks != 1 || C % (f16 ? 8 : BLOCK_K) || n2 % 16 || N + n2 > 512) return FLOWK_ERR_SHAPE;
+    if (f16 && !(a->acc_scale2 > 0.f)) return FLOWK_ERR_ARG;
+    const int kb2 = (C + bk - 1) / bk;                       // k-blocks of the second GEMM
+    p.acc_scale2 = f16 ? a->acc_scale2 : 1.f;
     p.n2 = n2;
     p.n2_chunks = n2 <= 256 ? 1 : 2;
     p.n2_chunk = n2 / p.n2_chunks;
     if (p.n2_chunk % 16 || p.n2_chunk > 256) return FLOWK_ERR_SHAPE;
     const size_t slab = (size_t)4 * 32 * (C + 4) * sizeof(float);
     p.a3_offset = (int)((slab + 1023) / 1024 * 1024);
-    p.w2_offset = p.a3_offset + (C / BLOCK_K) * 2 * A_TILE_BYTES;
-    const size_t chain_end = (size_t)p.w2_offset + (size_t)2 * n2 * BLOCK_K * 4;
+    p.w2_offset = p.a3_offset + kb2 * 2 * A_TILE_BYTES;
+    const size_t chain_end = (size_t)p.w2_offset + (size_t)2 * n2 * ROW_BYTES;
     const size_t slab2 = (size_t)4 * 32 * (n2 + 4) * sizeof(float);
     if (chain_end > region) region = (chain_end + 1023) / 1024 * 1024;
     if (slab2 > region) region = (slab2 + 1023) / 1024 * 1024;
@@ -969,7 +1006,8 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
       !make_map_w(&mw_hi, a->w_hi, N, Ktot, p.n_chunk, es) || !make_map_w(&mw_lo, a->w_lo, N, Ktot, p.n_chunk, es))
     return FLOWK_ERR_ARG;
   if (p.chain) {
-    if (!make_map_w(&mw2_hi, a->w2_hi, p.n2, N / 2, p.n2_chunk, 4) || !make_map_w(&mw2_lo, a->w2_lo, p.n2, N / 2, p.n2_chunk, 4))
+    const int k2tot = f16 ? ((N / 2 + bk - 1) / bk) * bk : N / 2;          // fp16 weights: rows padded to whole 64-channel blocks
+    if (!make_map_w(&mw2_hi, a->w2_hi, p.n2, k2tot, p.n2_chunk, es) || !make_map_w(&mw2_lo, a->w2_lo, p.n2, k2tot, p.n2_chunk, es))
       return FLOWK_ERR_ARG;
   } else {
     mw2_hi = mw_hi;

@@ -70,7 +70,7 @@ def _p(t):
 
 def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias=None, res=None, gamma=None,
               beta=None, pos=None, out_f32=None, out_hi=None, out_lo=None, out_nchw=None, status=None, trace=None,
-              w2_hi=None, w2_lo=None, out2_f32=None, n2=0, split_k=False, acc_scale=None, dilation=1):
+              w2_hi=None, w2_lo=None, out2_f32=None, n2=0, split_k=False, acc_scale=None, dilation=1, acc_scale2=None):
     """The operand format follows the tensors: fp32 tensors = TF32 pairs (FLOWK_OPERAND_TF32), fp16 tensors = fp16 pairs
     (FLOWK_OPERAND_F16, inference; `acc_scale` undoes the weights' power-of-two pre-scaling).
     `split_k=True` (training path: one stream, kernel latency matters) lends the kernel a workspace so that layers
@@ -80,7 +80,8 @@ def conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, taps, pre, out_mask, bias
                              _p(out_f32), _p(out_hi), _p(out_lo), _p(out_nchw), _p(status), _p(trace),
                              B, H, W, Cin, N, taps, pre, out_mask, _p(w2_hi), _p(w2_lo), _p(out2_f32), n2, None,
                              _lib.OPERAND_F16 if a_hi.dtype == torch.float16 else _lib.OPERAND_TF32,
-                             1.0 if acc_scale is None else float(acc_scale), int(dilation), 0)
+                             1.0 if acc_scale is None else float(acc_scale), int(dilation),
+                             1.0 if acc_scale2 is None else float(acc_scale2))
     assert a_hi.dtype == a_lo.dtype == w_hi.dtype == w_lo.dtype, "operand pair formats must agree"
     assert out_hi is None or out_hi.dtype == a_hi.dtype, "out_hi/out_lo are written in the input operand format"
     if split_k:
@@ -142,9 +143,10 @@ def attention_supported(HW, C, heads):
         and 2 * min(HW, 1 << 30) * (C // heads) * 4 * max(1, 256 // max(HW, 1)) <= 220 * 1024
 
 
-def chain_supported(C, n2):
+def chain_supported(C, n2, f16=False):
     """gate -> in_proj fusion: both accumulators in TMEM (2C + n2 <= 512 columns) and the operand tiles in smem."""
-    if C % 32 or n2 % 16 or 2 * C > 256 or 2 * C + n2 > 512:
+    if C % (8 if f16 else 32) or n2 % 16 or 2 * C > 256 or 2 * C + n2 > 512:
         return False
     slab = ((4 * 32 * (C + 4) * 4 + 1023) // 1024) * 1024
-    return slab + (C // 32) * 32768 + 2 * n2 * 128 + 2048 <= 227 * 1024
+    kblocks = (C + 63) // 64 if f16 else C // 32
+    return slab + kblocks * 32768 + 2 * n2 * 128 + 2048 <= 227 * 1024

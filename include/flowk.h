@@ -186,7 +186,7 @@ typedef struct flowk_conv_gemm_args {
   /* taps = 25 selects a 5x5 kernel; `dilation` (0 or 1 = dense) spaces the taps of 3x3 / 5x5 kernels ("same" zero padding of
    * dilation * (k - 1) / 2, mar_prior/convolutional_rnn/functional.py:248-272). */
   int dilation;
-  int reserved;
+  float acc_scale2;       /* FLOWK_OPERAND_F16 with a chained GEMM: 1 / (power-of-two pre-scaling of w2) */
 } flowk_conv_gemm_args;
 enum { FLOWK_OPERAND_TF32 = 0, FLOWK_OPERAND_F16 = 1 };
 

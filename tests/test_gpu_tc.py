@@ -219,31 +219,43 @@ def test_affine_conditioner_tc_matches_torch_path(tc, c, hidden, H, W, B):
     assert e_tc < max(3e-5, 4 * e_lib)       # K = 9*256: tensor-core fp32 accumulation order
 
 
+@pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("B,C,H,W", [(64, 96, 16, 16), (64, 96, 4, 4), (3, 32, 8, 8), (5, 64, 4, 4)])
-def test_chained_gate_in_proj(tc, B, C, H, W):
-    """GLU+residual+LayerNorm GEMM with the in_proj GEMM chained inside the same CTA == the two separate launches."""
+def test_chained_gate_in_proj(tc, fmt, B, C, H, W):
+    """GLU+residual+LayerNorm GEMM with the in_proj GEMM chained inside the same CTA == the two separate launches (both
+    operand formats; with fp16 pairs C = 96 / 32 leave the second GEMM's last 64-channel k-block partly zero-padded)."""
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(B * 7 + C)
     M = B * H * W
+    f16 = fmt == "f16"
     a = torch.randn(M, 2 * C, generator=g).to(dev)
-    a_hi, a_lo = tc.split_hilo(a)
-    w_hi, w_lo = tc.split_hilo((torch.randn(2 * C, 2 * C, generator=g) / (2 * C) ** 0.5).to(dev))
+    w = (torch.randn(2 * C, 2 * C, generator=g) / (2 * C) ** 0.5).to(dev)
     w2 = (torch.randn(3 * C, C, generator=g) / C ** 0.5).to(dev)
-    w2_hi, w2_lo = tc.split_hilo(w2)
+    kw = {}
+    if f16:
+        a_hi, a_lo = tc.split_rows_f16(a)
+        w_hi, w_lo, sc = tc.conv_weight_operand_f16(w)
+        w2_hi, w2_lo, sc2 = tc.conv_weight_operand_f16(w2)
+        kw = dict(acc_scale=sc, acc_scale2=sc2)
+    else:
+        a_hi, a_lo = tc.split_hilo(a)
+        w_hi, w_lo = tc.split_hilo(w)
+        w2_hi, w2_lo = tc.split_hilo(w2)
     bias = torch.randn(2 * C, generator=g).to(dev)
     res = torch.randn(M, C, generator=g).to(dev)
     gamma = (torch.rand(C, generator=g) + 0.5).to(dev)
     beta = torch.randn(C, generator=g).to(dev)
     pos = torch.randn(H * W, C, generator=g).to(dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    assert tc.chain_supported(C, 3 * C)
+    assert tc.chain_supported(C, 3 * C, f16)
     x1 = torch.empty(M, C, device=dev)
     qkv = torch.full((M, 3 * C), float("nan"), device=dev)
     tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, 2 * C, 2 * C, 1, tc.PRE_GLU_RES_LN, tc.OUT_F32, bias=bias, res=res,
-                 gamma=gamma, beta=beta, pos=pos, out_f32=x1, status=status, w2_hi=w2_hi, w2_lo=w2_lo, out2_f32=qkv, n2=3 * C)
+                 gamma=gamma, beta=beta, pos=pos, out_f32=x1, status=status, w2_hi=w2_hi, w2_lo=w2_lo, out2_f32=qkv, n2=3 * C,
+                 **kw)
     torch.cuda.synchronize()
     assert int(status) == 0
-    y = a.double() @ (w_hi + w_lo).double().t() + bias.double()
+    y = a.double() @ w.double().t() + bias.double()
     ln = F.layer_norm(y[:, :C] * torch.sigmoid(y[:, C:]) + res.double(), (C,), gamma.double(), beta.double())
     ref = (ln + pos.double().repeat(B, 1)) @ w2.double().t()
     assert rel_err(x1, ln) < 1e-5
