@@ -37,7 +37,8 @@ for name, H, W, Cin, N, taps, pre in shapes:
     out = torch.empty(M, nout, device=dev)
     oh, ol = torch.empty(M, 2 * nout, device=dev, dtype=odt), torch.empty(M, 2 * nout, device=dev, dtype=odt)
     kw = dict(bias=bias, out_f32=out, out_hi=oh, out_lo=ol, acc_scale=sc)
-    mask = tc.OUT_F32 | tc.OUT_HILO_CELU
+    mask = {"f32": tc.OUT_F32, "celu": tc.OUT_HILO_CELU, "hilo": tc.OUT_F32 | tc.OUT_HILO}.get(
+        os.environ.get("FLOWK_PROBE_MASK", ""), tc.OUT_F32 | tc.OUT_HILO_CELU)
     if pre == tc.PRE_GLU_RES_LN:
         kw.update(res=torch.randn(M, nout, device=dev), gamma=torch.ones(nout, device=dev), beta=torch.zeros(nout, device=dev))
     if name == "out_conv":
