@@ -474,8 +474,91 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int pitch = C + 4;
       float* slab = reinterpret_cast<float*>(smem) + lane_grp * (32 * pitch);      // shared by the 4 warps of the group
       const int bar_id = 1 + lane_grp;                               // named barrier of this lane group (128 threads)
-      // 0. residual rows of this warp's 8 rows x 4 columns per lane: issue the loads now, they land during step 1
       const int nv = (C + 127) / 128;
+      float g[8][NV][4], pe[8][NV][4];
+      float mean[8], rstd[8];
+      bool normalized = false;                                       // true: the slab already holds LayerNorm(g) * gamma + beta
+      if (NV == 1) {
+        // C <= 128.  Everything row-wise happens in the TMEM-lane layout (lane == row): GLU, residual add, BOTH LayerNorm
+        // statistics are thread-local sums over the <= 32 columns this thread owns, combined across the four warps of the
+        // lane group through 2 x 128 floats of shared memory - no warp-shuffle reductions, no second pass over the slab.
+        __shared__ float ln_part[2][4][4][32];                       // [statistic][lane group][warp of the group][lane]
+        const int m_row = slab_row0 + lane;
+        const bool row_ok = m_row < p.M;
+        float gb[2][16];
+        float psum = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int j = sub * 16 + ci * 64;
+          if (j < C) {
+            float a[16], b[16];
+            tmem_ld16(trow + j, a);
+            tmem_ld16(trow + C + j, b);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + j + i));
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + C + j + i));
+              const float4 rs = row_ok ? __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m_row * C + j + i))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+              gb[ci][i] = fmaf(a[i], sc, ba.x) * sigmoid_fast(fmaf(b[i], sc, bb.x)) + rs.x;
+              gb[ci][i + 1] = fmaf(a[i + 1], sc, ba.y) * sigmoid_fast(fmaf(b[i + 1], sc, bb.y)) + rs.y;
+              gb[ci][i + 2] = fmaf(a[i + 2], sc, ba.z) * sigmoid_fast(fmaf(b[i + 2], sc, bb.z)) + rs.z;
+              gb[ci][i + 3] = fmaf(a[i + 3], sc, ba.w) * sigmoid_fast(fmaf(b[i + 3], sc, bb.w)) + rs.w;
+              psum += (gb[ci][i] + gb[ci][i + 1]) + (gb[ci][i + 2] + gb[ci][i + 3]);
+            }
+          }
+        }
+        ln_part[0][lane_grp][sub][lane] = psum;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const float mu = ((ln_part[0][lane_grp][0][lane] + ln_part[0][lane_grp][1][lane]) +
+                          (ln_part[0][lane_grp][2][lane] + ln_part[0][lane_grp][3][lane])) / (float)C;
+        float pvar = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+          if (sub * 16 + ci * 64 < C) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pvar = fmaf(gb[ci][i] - mu, gb[ci][i] - mu, pvar);
+          }
+        ln_part[1][lane_grp][sub][lane] = pvar;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const float rs_ = rsqrtf(((ln_part[1][lane_grp][0][lane] + ln_part[1][lane_grp][1][lane]) +
+                                  (ln_part[1][lane_grp][2][lane] + ln_part[1][lane_grp][3][lane])) / (float)C + 1e-5f);
+        if (tracing && threadIdx.x == 64) p.trace[6] = clock64();
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int j = sub * 16 + ci * 64;
+          if (j < C) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + j + i));
+              const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + j + i));
+              *reinterpret_cast<float4*>(slab + lane * pitch + j + i) =
+                  make_float4(fmaf((gb[ci][i] - mu) * rs_, ga.x, be.x), fmaf((gb[ci][i + 1] - mu) * rs_, ga.y, be.y),
+                              fmaf((gb[ci][i + 2] - mu) * rs_, ga.z, be.z), fmaf((gb[ci][i + 3] - mu) * rs_, ga.w, be.w));
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (tracing && threadIdx.x == 64) p.trace[7] = clock64();
+        normalized = true;
+        // warp `sub` owns rows sub*8..+7, a lane 4 consecutive columns: read the normalised rows back for the output forms
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = sub * 8 + rr, m = slab_row0 + r;
+          const int c4 = lane * 4;
+          float4 ps = make_float4(0.f, 0.f, 0.f, 0.f), gv = ps;
+          if (c4 < C) {
+            gv = *reinterpret_cast<const float4*>(slab + r * pitch + c4);
+            if (((p.out_mask & OUT_HILO_POS) || (p.chain && p.pos)) && m < p.M)
+              ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(m % p.HW) * C + c4));
+          }
+          g[rr][0][0] = gv.x; g[rr][0][1] = gv.y; g[rr][0][2] = gv.z; g[rr][0][3] = gv.w;
+          pe[rr][0][0] = ps.x; pe[rr][0][1] = ps.y; pe[rr][0][2] = ps.z; pe[rr][0][3] = ps.w;
+          mean[rr] = 0.f;
+          rstd[rr] = 1.f;
+        }
+      } else {
+      // 0. residual rows of this warp's 8 rows x 4 columns per lane: issue the loads now, they land during step 1
       float4 resv[8][NV];
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
@@ -507,7 +590,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       if (tracing && threadIdx.x == 64) p.trace[6] = clock64();
       // 2. warp `sub` owns rows sub*8..+7; a lane owns 4 consecutive columns (x2 when C > 128).  Residual add,
       //    two-pass row statistics (warp-shuffle reductions), normalisation and every output form, all in registers.
-      float g[8][NV][4], pe[8][NV][4];
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
         const int r = sub * 8 + rr, m = slab_row0 + r;
@@ -526,7 +608,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
       }
       if (tracing && threadIdx.x == 64) p.trace[7] = clock64();
-      float mean[8], rstd[8];
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
         float sacc = 0.f;
@@ -549,6 +630,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vacc += __shfl_xor_sync(0xffffffffu, vacc, o);
         rstd[rr] = rsqrtf(vacc / (float)C + 1e-5f);
+      }
       }
       if (tracing && threadIdx.x == 64) p.trace[8] = clock64();
 #pragma unroll
@@ -593,7 +675,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           }
           float y[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) y[i] = (g[rr][v][i] - mean[rr]) * rstd[rr] * gs[i] + bs[i];
+          for (int i = 0; i < 4; ++i) y[i] = normalized ? g[rr][v][i] : (g[rr][v][i] - mean[rr]) * rstd[rr] * gs[i] + bs[i];
           const size_t o = (size_t)m * C + c4;
           if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
           if (p.out_mask & (OUT_HILO | OUT_HILO_POS)) {
