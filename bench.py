@@ -404,15 +404,16 @@ def run_flowk(args):
             "us_per_launch": us, "launches_timed": n, "peak_source": peak_src,
             "note": "eager launches timed with CUDA events (includes the launch gap); operands were just written by "
                     "the conditioner and partly sit in L2 at this batch size; roofline_large is the HBM-resident figure"}
-        # dominant kernel of the step: the tcgen05 implicit-GEMM conditioner layer with the largest total time
+        # dominant kernel of the step: the tcgen05 implicit-GEMM conditioner layer with the most work (launches x flops)
         roofline = roofline_elementwise
         if "flowk_conv_gemm" in kernels:
             tf_peak, tf_src = tensor_peak()
             top = None
             for meta, (n, us) in kernels["flowk_conv_gemm"].items():
                 gb, gh, gw, cin, nn, taps, pre = eval(meta)
-                if top is None or n * us > top[0]:
-                    top = (n * us, n, us, (gb, gh, gw, cin, nn, taps, pre))
+                work = n * 2.0 * gb * gh * gw * nn * taps * cin      # eager per-launch times are host-launch-bound (all
+                if top is None or work > top[0]:                     # ~equal): rank the layers by algorithmic work
+                    top = (work, n, us, (gb, gh, gw, cin, nn, taps, pre))
             _, n, us_eager, (gb, gh, gw, cin, nn, taps, pre) = top
             flops = 2.0 * gb * gh * gw * nn * taps * cin
             from flowk import conditioner_tc
