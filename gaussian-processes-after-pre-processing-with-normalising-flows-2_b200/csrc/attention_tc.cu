@@ -170,7 +170,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
   if (tracing) p.trace[1] = clock64();
 
   // ---- 2. S_t = Q_t K^T for every query tile, issued back to back (tile t into TMEM columns [t HW, t HW + HW)) ---------
-  if (threadIdx.x == 0) {
+  // (MMAs are issued by warp 0 as a whole with uniform operands, the instruction predicated on the elected lane: umma.cuh)
+  const uint32_t leader = warp == 0 ? elect_one() : 0u;
+  if (warp == 0) {
     tc_fence_after();
     const uint32_t idesc = make_idesc_f16(HW);
     const uint64_t dk_hi = make_smem_desc(smem_u32(k_hi)), dk_lo = make_smem_desc(smem_u32(k_lo));
@@ -180,11 +182,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
       const uint32_t d = tmem_base + (uint32_t)(t * HW);
       for (int ks = 0; ks < ksteps; ++ks) {
         const uint64_t ko = (uint64_t)(ks * 2); // 32 bytes per K = 16 step, in 16-byte units
-        umma_f16(d, dq_hi + ko, dk_hi + ko, idesc, ks == 0 ? 0u : 1u);
-        umma_f16(d, dq_lo + ko, dk_hi + ko, idesc, 1u);
-        umma_f16(d, dq_hi + ko, dk_lo + ko, idesc, 1u);
+        umma_elect<true>(d, dq_hi + ko, dk_hi + ko, idesc, ks == 0 ? 0u : 1u, leader);
+        umma_elect<true>(d, dq_lo + ko, dk_hi + ko, idesc, 1u, leader);
+        umma_elect<true>(d, dq_hi + ko, dk_lo + ko, idesc, 1u, leader);
       }
-      umma_commit(&bar_s[t]);
+      umma_commit_elect(&bar_s[t], leader);
     }
   }
 
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
 
     // ---- 4. O_t = P V.  B operand = [V_hi ; V_lo] (N = 2 dk): P_hi [V_hi ; V_lo] fills columns [0, dk) and [dk, 2 dk) of S_t's
     //         (dead) leading columns in one MMA, P_lo V_hi adds to [0, dk); the epilogue sums the two column groups.
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
       tc_fence_after();
       const uint32_t idesc2 = make_idesc_f16(2 * p.dk), idesc1 = make_idesc_f16(p.dk);
       const uint32_t d = tmem_base + (uint32_t)(t * HW);
@@ -292,11 +294,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const AttP
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t ko = (uint64_t)(k * 2);
-          umma_f16(d, dp_hi + ko, dv + ko, idesc2, (kb | k) == 0 ? 0u : 1u);
-          umma_f16(d, dp_lo + ko, dv + ko, idesc1, 1u);
+          umma_elect<true>(d, dp_hi + ko, dv + ko, idesc2, (kb | k) == 0 ? 0u : 1u, leader);
+          umma_elect<true>(d, dp_lo + ko, dv + ko, idesc1, 1u, leader);
         }
       }
-      umma_commit(&bar_o[t]);
+      umma_commit_elect(&bar_o[t], leader);
     }
     // ---- 5. the PREVIOUS tile's epilogue runs while this tile's P V MMAs execute
     if (t > 0) epilogue(t - 1);

@@ -214,7 +214,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp runs the loop (uniform operands); only the elected lane's tcgen05 instructions execute (umma.cuh)
+    const uint32_t leader = elect_one();
+    {
       const uint32_t idesc = make_idesc_t<F16>(p.n_chunk);
       if (p.dxsplit) {
         const uint32_t w_ring = smem_u32(smem + (size_t)p.a_slots * 2 * A_TILE_BYTES);
@@ -232,8 +234,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           mbar_wait(&full_bar[sa], ((uint32_t)(g / p.a_slots)) & 1u, failed);
           mbar_wait(&wfull_bar[sw], ((uint32_t)(g / p.w_slots)) & 1u, failed);
           tc_fence_after();
-          if (tracing && g == 0) p.trace[1] = clock64();
-          if (tracing && g == groups - 1) p.trace[2] = clock64();
+          if (tracing && lane == 0 && g == 0) p.trace[1] = clock64();
+          if (tracing && lane == 0 && g == groups - 1) p.trace[2] = clock64();
           const uint32_t a_hi = smem_u32(smem + (size_t)sa * 2 * A_TILE_BYTES);
           const uint32_t w_hi = w_ring + (uint32_t)sw * 6u * (uint32_t)w_tile_bytes;
           const uint64_t da_hi = make_smem_desc(a_hi), da_lo = da_hi + (A_TILE_BYTES >> 4);
@@ -244,23 +246,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             for (int q = 0; q < n_mma; ++q) {
               const uint64_t bo = ko + q * per_units;
               const uint32_t d = tmem_base + q * n_per;
-              umma<F16>(d, da_hi + ko, db_hi + bo, idesc_w, (g | k) == 0 ? 0u : 1u);
-              umma<F16>(d, da_lo + ko, db_hi + bo, idesc_w, 1u);
-              umma<F16>(d, da_hi + ko, db_lo + bo, idesc_w, 1u);
+              umma_elect<F16>(d, da_hi + ko, db_hi + bo, idesc_w, (g | k) == 0 ? 0u : 1u, leader);
+              umma_elect<F16>(d, da_lo + ko, db_hi + bo, idesc_w, 1u, leader);
+              umma_elect<F16>(d, da_hi + ko, db_lo + bo, idesc_w, 1u, leader);
             }
           }
-          umma_commit(&wempty_bar[sw]);
-          umma_commit(&empty_bar[sa]);
+          umma_commit_elect(&wempty_bar[sw], leader);
+          umma_commit_elect(&empty_bar[sa], leader);
         }
-        umma_commit(tmem_full_bar);
+        umma_commit_elect(tmem_full_bar, leader);
       } else {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph, failed);
         tc_fence_after();
-        if (tracing && kb == 0) p.trace[1] = clock64();
-        if (tracing && kb == num_kb - 1) p.trace[2] = clock64();
+        if (tracing && lane == 0 && kb == 0) p.trace[1] = clock64();
+        if (tracing && lane == 0 && kb == num_kb - 1) p.trace[2] = clock64();
         const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint64_t da_hi0 = make_smem_desc(a_hi), da_lo0 = da_hi0 + (A_TILE_BYTES >> 4);
         const uint64_t db_hi0 = da_hi0 + (2 * A_TILE_BYTES >> 4), db_lo0 = db_hi0 + ((uint32_t)w_tile_bytes >> 4);
@@ -271,14 +273,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           for (int c = 0; c < p.n_chunks; ++c) {
             const uint64_t co = ko + c * chunk_units;
             const uint32_t d = tmem_base + c * p.n_chunk;
-            umma<F16>(d, da_hi0 + ko, db_hi0 + co, idesc, (kb | k) == 0 ? 0u : 1u);
-            umma<F16>(d, da_lo0 + ko, db_hi0 + co, idesc, 1u);
-            umma<F16>(d, da_hi0 + ko, db_lo0 + co, idesc, 1u);
+            umma_elect<F16>(d, da_hi0 + ko, db_hi0 + co, idesc, (kb | k) == 0 ? 0u : 1u, leader);
+            umma_elect<F16>(d, da_lo0 + ko, db_hi0 + co, idesc, 1u, leader);
+            umma_elect<F16>(d, da_hi0 + ko, db_lo0 + co, idesc, 1u, leader);
           }
         }
-        umma_commit(&empty_bar[s]);                                  // smem slot free once these MMAs retire
+        umma_commit_elect(&empty_bar[s], leader);                                  // smem slot free once these MMAs retire
       }
-      umma_commit(tmem_full_bar);                                    // accumulator complete
+      umma_commit_elect(tmem_full_bar, leader);                                    // accumulator complete
       }
       if (p.chain) {
         mbar_wait(a3_full_bar, 0, failed);                           // epilogue warps have written the operand tiles
@@ -299,14 +301,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             for (int c = 0; c < p.n2_chunks; ++c) {
               const uint64_t co = ko + c * chunk2_units;
               const uint32_t d = tmem_base + p.N + c * p.n2_chunk;   // second accumulator: columns after the first
-              umma<F16>(d, da_hi + ko, db_hi + co, idesc2, (kb | k) == 0 ? 0u : 1u);
-              umma<F16>(d, da_lo + ko, db_hi + co, idesc2, 1u);
-              umma<F16>(d, da_hi + ko, db_lo + co, idesc2, 1u);
+              umma_elect<F16>(d, da_hi + ko, db_hi + co, idesc2, (kb | k) == 0 ? 0u : 1u, leader);
+              umma_elect<F16>(d, da_lo + ko, db_hi + co, idesc2, 1u, leader);
+              umma_elect<F16>(d, da_hi + ko, db_lo + co, idesc2, 1u, leader);
             }
           }
-          umma_commit(w2_empty_bar);
+          umma_commit_elect(w2_empty_bar, leader);
         }
-        umma_commit(acc2_full_bar);
+        umma_commit_elect(acc2_full_bar, leader);
       }
     }
   } else {
@@ -1003,6 +1005,18 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
       p.n_chunk /= 2;
       n_tiles *= 2;
     }
+    // 3x3 layers (long main loop bound by the ~45 B/clk one SM ingests through TMA; every CTA streams its slice of the
+    // weights): take the finest split of N into equal multiples of 16 columns that still fits one wave - N = 96: 6 x 16
+    // columns on 8 M tiles, 3 x 32 on 32 M tiles.
+    if (a->taps == 9 && p.n_chunks == 1 && N % 16 == 0 && p.n_chunk * n_tiles == N) {
+      const int units = N / 16;
+      for (int d = units; d > n_tiles; --d)
+        if (units % d == 0 && m_tiles * d <= 148) {
+          n_tiles = d;
+          p.n_chunk = N / d;
+          break;
+        }
+    }
   }
   if (p.n_chunk % 16 || p.n_chunk > 256) return FLOWK_ERR_SHAPE;
   // split-K: only the plain bias epilogue with a single fp32 destination, and only when the caller lends a workspace
@@ -1039,9 +1053,10 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   if (p.dxsplit) {
     p.tmem_cols = 3 * p.n_chunk <= 256 ? 256 : 512;
     if (3 * p.n_chunk <= 128) p.tmem_cols = 128;
-    p.a_slots = 2;
-    if (const char* e = getenv("FLOWK_A_SLOTS")) p.a_slots = atoi(e);   // tuning knob
     const int w_slot_bytes = 6 * cols * ROW_BYTES;              // 3 column shifts x (hi, lo)
+    // narrow N tiles (deep levels): the activation tiles dominate the bytes, so give THEM the deeper ring
+    p.a_slots = (220 * 1024 - 2048 - 4 * 2 * A_TILE_BYTES) / w_slot_bytes >= 3 ? 4 : 2;
+    if (const char* e = getenv("FLOWK_A_SLOTS")) p.a_slots = atoi(e);   // tuning knob
     int ws = (int)((220 * 1024 - 2048 - p.a_slots * 2 * A_TILE_BYTES) / w_slot_bytes);
     p.w_slots = ws > 4 ? 4 : ws;
     if (p.w_slots < 2) p.dxsplit = 0;

@@ -113,7 +113,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // the whole warp runs the loop with uniform operands; only the elected lane's tcgen05 instructions execute (umma.cuh)
+    const uint32_t leader = elect_one();
+    {
       const uint32_t idesc = p.rows ? make_idesc_mn(p.c_tile) : make_idesc(p.c_tile);
       for (int kb = kb0; kb < kb1; ++kb) {
         const int i = kb - kb0, s = i % p.stages;
@@ -138,14 +140,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
         for (int k = 0; k < ksteps; ++k) {
           // K-major: 32 bytes further inside the 128-byte row; MN-major: 8 rows = 1024 bytes further
           const uint64_t ko = p.rows ? (uint64_t)(k * 1024 >> 4) : (uint64_t)(k * UMMA_K * 4 >> 4);
-          if ((i | k) == 0) umma_tf32(tmem_base, dg_hi + ko, dx_hi + ko, idesc, 0u);
-          else umma_tf32_acc(tmem_base, dg_hi + ko, dx_hi + ko, idesc);
-          umma_tf32_acc(tmem_base, dg_lo + ko, dx_hi + ko, idesc);
-          umma_tf32_acc(tmem_base, dg_hi + ko, dx_lo + ko, idesc);
+          umma_elect<false>(tmem_base, dg_hi + ko, dx_hi + ko, idesc, (i | k) == 0 ? 0u : 1u, leader);
+          umma_elect<false>(tmem_base, dg_lo + ko, dx_hi + ko, idesc, 1u, leader);
+          umma_elect<false>(tmem_base, dg_hi + ko, dx_lo + ko, idesc, 1u, leader);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit_elect(&empty_bar[s], leader);
       }
-      umma_commit(&acc_full);
+      umma_commit_elect(&acc_full, leader);
     }
   } else {
     // ===================== converters: lo = rna(x - trunc(x)) at the same (swizzled) offsets =====================
