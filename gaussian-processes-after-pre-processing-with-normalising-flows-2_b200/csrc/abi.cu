@@ -1,7 +1,7 @@
 // ABI bookkeeping for libflowk.so: version, status strings, workspace sizing.
 #include "common.cuh"
 
-extern "C" int flowk_abi_version(void) { return 1; }
+extern "C" int flowk_abi_version(void) { return 2; }   // 2: flowk_conv_gemm_args grew (operand_format, acc_scale, dilation, acc_scale2)
 
 extern "C" size_t flowk_ldj_workspace_bytes(int B) {
   if (B < 1) B = 1;

@@ -20,7 +20,7 @@ def test_header_symbols_exported():
 
 
 def test_abi_version_and_strings():
-    assert _lib.lib.flowk_abi_version() == 1
+    assert _lib.lib.flowk_abi_version() == 2
     assert _lib.lib.flowk_error_string(0) == b"ok"
     assert _lib.lib.flowk_error_string(1) == b"bad shape"
     assert _lib.lib.flowk_ldj_workspace_bytes(64) == 64 * 65 * 4
