@@ -52,7 +52,9 @@ METRIC = "mAR-SCF CIFAR10 MixLogCDF fwd+logdet images/s"
 def shared_config(workload, batch, world, depth):
     """The `config` object BOTH arms print (the driver compares them): workload, batch and what one step is."""
     return {"workload": DESCRIBE[workload], "batch_per_gpu": batch, "global_batch": batch * world,
-            "step": "one forward pass (z, log-det, bits/dim) of the whole flow stack over one batch"}
+            "step": "one forward pass (z, log-det, bits/dim) of the whole flow stack over one batch",
+            "l2": "no explicit flush: inputs larger than L2 - one step streams the conditioner weight operands of 12 "
+                  "couplings (cfg2: > 170 MB) through the 126 MB L2 and rotates over 8 input batches"}
 
 
 def peaks():
