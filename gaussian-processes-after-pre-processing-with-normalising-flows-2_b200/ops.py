@@ -163,6 +163,29 @@ def _mix_out_shape(x: Tensor, in_squeeze: bool, out_unsqueeze: bool) -> List[int
     return [b, c, h, w]
 
 
+MIX_TC_MIN_ELEMENTS = int(__import__("os").environ.get("FLOWK_MIX_TC_MIN", str(1 << 23)))   # below: one launch of the
+#                                          CUDA-core kernel is latency-bound either way (10-20 us at the named batch sizes)
+_MIX_W = {}
+
+
+def _mix_on_tensor_cores(x: Tensor, c: int, h: int, w: int, in_squeeze: bool, out_unsqueeze: bool) -> bool:
+    if in_squeeze or out_unsqueeze or c < 48 or c % 8 or x.numel() < MIX_TC_MIN_ELEMENTS:
+        return False
+    hw = h * w
+    return w <= 128 and 128 % w == 0 and ((hw % 128 == 0) if hw >= 128 else (128 % hw == 0))
+
+
+def _mix_weight_operand(weight: Tensor):
+    """fp16 (hi, lo) operand of the [C, C] mixing matrix, cached per weight version (its scale needs one host read)."""
+    key = (weight.data_ptr(), weight._version, _lib.GENERATION, tuple(weight.shape))
+    hit = _MIX_W.get(weight.device)
+    if hit is None or hit[0] != key:
+        from . import tc
+        hit = (key, tc.conv_weight_operand_f16(weight))
+        _MIX_W[weight.device] = hit
+    return hit[1]
+
+
 @torch.library.custom_op("flowk::channel_mix", mutates_args=(), device_types="cuda")
 def channel_mix(x: Tensor, weight: Tensor, bias: Optional[Tensor], ldj: Tensor, ldj_add: Tensor,
                 in_squeeze: bool, out_unsqueeze: bool) -> Tuple[Tensor, Tensor]:
@@ -178,6 +201,15 @@ def channel_mix(x: Tensor, weight: Tensor, bias: Optional[Tensor], ldj: Tensor, 
         assert c % 4 == 0, "{}".format(c)
     assert weight.shape[0] == c and weight.shape[1] == c, "weight must be [%d,%d]" % (c, c)
     y = x.new_empty(_mix_out_shape(x, in_squeeze, out_unsqueeze))
+    if _mix_on_tensor_cores(x, c, h, w, in_squeeze, out_unsqueeze):
+        # Wide 1x1 convs over large batches: the CUDA-core kernel is FP32-FMA-bound from C = 48 up (2 C^2 flop per 8 C bytes),
+        # so the channel GEMM runs on tcgen05: NCHW -> NHWC fp16 (hi, lo) rows, implicit GEMM with taps = 1, NCHW epilogue.
+        from . import tc
+        a_hi, a_lo = tc.nchw_to_nhwc_hilo(x, c, True)
+        w_hi, w_lo, sc = _mix_weight_operand(_f32c(weight, "weight"))
+        tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, b, h, w, c, c, 1, tc.PRE_BIAS, tc.OUT_NCHW,
+                     bias=None if bias is None else _f32c(bias, "bias"), out_nchw=y, acc_scale=sc)
+        return y, ldj + ldj_add
     out = torch.empty_like(ldj)
     _lib.call("flowk_channel_mix", x.data_ptr(), _f32c(weight, "weight").data_ptr(),
               _ptr(None if bias is None else _f32c(bias, "bias")), y.data_ptr(), _f32c(ldj, "ldj").data_ptr(),

@@ -848,3 +848,32 @@ def test_eval_caches_follow_raw_pointer_updates(F, no_library):
         assert torch.isfinite(nll1).all() and torch.isfinite(nll2).all()
         assert float((nll1 - nll0).abs().max()) > 1e-3, "the update must change the model output"
         assert float((nll1 - nll2).abs().max()) <= 1e-5 * max(1.0, float(nll2.abs().max())), coupling
+
+
+@pytest.mark.parametrize("C,H,B", [(48, 4, 64), (96, 4, 40), (48, 8, 16)])
+def test_channel_mix_tensor_core_route_matches_cuda_core_kernel(F, C, H, B):
+    """The 1x1 invertible conv as a tcgen05 channel GEMM (the route large batches of wide levels take, ops.channel_mix)
+    against the CUDA-core kernel and a float64 matmul."""
+    from flowk import ops
+    gen = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, H, generator=gen).to(dev())
+    mat = torch.linalg.qr(torch.randn(C, C, generator=gen))[0].contiguous().to(dev())
+    bias = torch.randn(C, generator=gen).to(dev())
+    ldj = torch.randn(B, generator=gen).to(dev())
+    add = torch.full((1,), 3.5, device=dev())
+    y_ref, l_ref = ops.channel_mix(x, mat, bias, ldj, add, False, False)
+    old = ops.MIX_TC_MIN_ELEMENTS
+    ops.MIX_TC_MIN_ELEMENTS = 0
+    try:
+        from flowk import _lib
+        _lib.TIMING = {}
+        y_tc, l_tc = ops.channel_mix(x, mat, bias, ldj, add, False, False)
+        torch.cuda.synchronize()
+        assert "flowk_conv_gemm" in _lib.TIMING
+    finally:
+        ops.MIX_TC_MIN_ELEMENTS = old
+        _lib.TIMING = None
+    ref64 = torch.einsum("oi,bihw->bohw", mat.double(), x.double()) + bias.double().view(1, -1, 1, 1)
+    parity(y_tc, ref64.float().cpu(), rel=2e-6, what="tcgen05 channel mix vs fp64")
+    parity(y_tc, y_ref.cpu(), rel=2e-6, what="tcgen05 vs CUDA-core channel mix")
+    assert torch.allclose(l_tc, l_ref)
