@@ -862,8 +862,8 @@ def test_channel_mix_tensor_core_route_matches_cuda_core_kernel(F, C, H, B):
     ldj = torch.randn(B, generator=gen).to(dev())
     add = torch.full((1,), 3.5, device=dev())
     y_ref, l_ref = ops.channel_mix(x, mat, bias, ldj, add, False, False)
-    old = ops.MIX_TC_MIN_ELEMENTS
-    ops.MIX_TC_MIN_ELEMENTS = 0
+    old, old_c = ops.MIX_TC_MIN_ELEMENTS, ops.MIX_TC_MIN_CHANNELS
+    ops.MIX_TC_MIN_ELEMENTS, ops.MIX_TC_MIN_CHANNELS = 0, 48
     try:
         from flowk import _lib
         _lib.TIMING = {}
@@ -871,7 +871,7 @@ def test_channel_mix_tensor_core_route_matches_cuda_core_kernel(F, C, H, B):
         torch.cuda.synchronize()
         assert "flowk_conv_gemm" in _lib.TIMING
     finally:
-        ops.MIX_TC_MIN_ELEMENTS = old
+        ops.MIX_TC_MIN_ELEMENTS, ops.MIX_TC_MIN_CHANNELS = old, old_c
         _lib.TIMING = None
     ref64 = torch.einsum("oi,bihw->bohw", mat.double(), x.double()) + bias.double().view(1, -1, 1, 1)
     parity(y_tc, ref64.float().cpu(), rel=2e-6, what="tcgen05 channel mix vs fp64")
