@@ -109,7 +109,10 @@ class StandardNormalPrior(nn.Module):
     def forward(self, z, level, reverse=False, eps_std=None, batch_size=None, device=None):
         if not reverse:
             z2 = z[1] if isinstance(z, (tuple, list)) else z
-            return GaussianDiag.logp(torch.zeros_like(z2), torch.zeros_like(z2), z2)
+            # log N(z2; 0, I) per sample = -(sum z^2 + D log 2 pi) / 2: GaussianDiag.logp with zero mean / log-std in two
+            # launches instead of ~12 (common_modules.py:223-240; same value up to fp32 summation order)
+            d = z2[0].numel()
+            return -0.5 * (z2.square().flatten(1).sum(1) + d * GaussianDiag.Log2PI)
         if z is None:
             return torch.randn((batch_size,) + self.final_shape, device=device) * (eps_std or 1.0)
         return torch.randn_like(z) * (eps_std or 1.0)

@@ -49,7 +49,7 @@ def conv_weight_operand_f16(w):
     if cin_pad != cin:
         wk = torch.nn.functional.pad(wk, (0, cin_pad - cin))
     wk = wk.reshape(n, kh * kw * cin_pad).contiguous()
-    amax = float(wk.abs().max()) if wk.numel() else 0.0          # (host sync: weight preparation is cached per version)
+    amax = float(torch.linalg.vector_norm(wk, float("inf"))) if wk.numel() else 0.0   # (host sync: cached per weight version)
     import math
     e = 14 - math.floor(math.log2(amax)) if amax > 0 and math.isfinite(amax) else 0
     e = max(-14, min(24, e))
