@@ -46,6 +46,8 @@ SIGNATURES = {
     "flowk_nchw_to_nhwc_hilo_f16": ([_fp, ctypes.c_longlong, _i, _i, _i, _i, _fp, _fp, _st], _i),
     "flowk_split_hilo_f16": ([_fp, _fp, _fp, ctypes.c_longlong, ctypes.c_float, _st], _i),
     "flowk_attention_f16": ([_fp, _fp, _fp, _i, _i, _i, _i, _st], _i),
+    "flowk_pack_weight_f16": ([_fp, _fp, _i, ctypes.c_float, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _st], _i),
+    "flowk_fold_actnorm_invconv": ([_fp] * 7 + [_i, _i, _i, _i, _fp, _fp, _fp, _st], _i),
     "flowk_patch_attention": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _st], _i),
     "flowk_attention_tc": ([_fp, _fp, _fp, _i, _i, _i, _i, _i, _fp, _fp, _st], _i),
     "flowk_attention": ([_fp, _fp, _fp, _i, _i, _i, _i, _st], _i),
@@ -100,6 +102,7 @@ class AdamaxChunk(ctypes.Structure):
 
 OPERAND_TF32, OPERAND_F16 = 0, 1
 PRE_BIAS, PRE_GLU_RES_LN, PRE_LSTM = 0, 1, 2
+PACK_PLAIN, PACK_WEIGHT_NORM, PACK_EXP_GAIN = 0, 1, 2
 OUT_F32, OUT_HILO, OUT_HILO_POS, OUT_HILO_CELU, OUT_NCHW, OUT_HILO_RELU = 1, 2, 4, 8, 16, 32
 
 
@@ -113,6 +116,7 @@ DIMS = {
     "flowk_mixture_log_cdf": slice(5, 8), "flowk_mixture_log_pdf": slice(5, 8), "flowk_mixture_inv_cdf": slice(5, 8),
     "flowk_nchw_to_nhwc_hilo": slice(2, 6), "flowk_split_hilo": slice(3, 4), "flowk_attention": slice(3, 7),
     "flowk_nchw_to_nhwc_hilo_f16": slice(2, 6), "flowk_split_hilo_f16": slice(3, 4), "flowk_attention_f16": slice(3, 7), "flowk_attention_tc": slice(4, 8), "flowk_patch_attention": slice(6, 10),
+    "flowk_pack_weight_f16": slice(6, 10), "flowk_fold_actnorm_invconv": slice(7, 11),
 }
 
 

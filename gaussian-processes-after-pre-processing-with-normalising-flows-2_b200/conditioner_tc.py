@@ -70,8 +70,11 @@ def _cin_pad(c):
 
 def _wn_operand(core):
     """(w_hi, w_lo, bias, acc_scale) of a weight-normed conv / linear (`_WeightNormed`)."""
-    w_hi, w_lo, sc = _weight_operand(core.normed_weight())
     bias = None if core.bias is None else core.bias.detach().contiguous()
+    if F16:                                            # weight norm fused into the operand packing (two launches)
+        w_hi, w_lo, sc = tc.conv_weight_operand_f16(core.weight_v, core.weight_g, _lib.PACK_WEIGHT_NORM)
+        return w_hi, w_lo, bias, sc
+    w_hi, w_lo, sc = _weight_operand(core.normed_weight())
     return w_hi, w_lo, bias, sc
 
 
@@ -191,6 +194,15 @@ def _affine_operands(net):
     """NN_net (flow_modules/affine_coupling.py:68-80) with both ActNorms folded into the conv weights:
     (conv(x) + b) e^{logs} = conv(x; w e^{logs}) + b e^{logs};  Conv2dZeros: (conv + bias) e^{3 logs}."""
     ops = []
+    if F16:                                            # gains and biases folded by the packing kernel
+        for conv in (net.conv1, net.conv2):
+            w_hi, w_lo, sc, b = tc.conv_weight_operand_f16(conv.weight, conv.actnorm.logs, _lib.PACK_EXP_GAIN, 1.0,
+                                                           conv.actnorm.bias)
+            ops.append((w_hi, w_lo, b, sc))
+        w_hi, w_lo, sc, b = tc.conv_weight_operand_f16(net.conv3.weight, net.conv3.logs, _lib.PACK_EXP_GAIN,
+                                                       float(net.conv3.logscale_factor), net.conv3.bias)
+        ops.append((w_hi, w_lo, b, sc))
+        return ops
     for conv in (net.conv1, net.conv2):
         gain = torch.exp(conv.actnorm.logs.detach().reshape(-1))
         w_hi, w_lo, sc = _weight_operand(conv.weight.detach() * gain.view(-1, 1, 1, 1))

@@ -226,6 +226,9 @@ class GaussianDiag:
         return mean + torch.exp(logs) * eps
 
 
+FOLD_KERNEL = True      # False: assemble the fold with torch ops (tests A/B the two)
+
+
 def fold_actnorm_invconv(actnorm, invconv, x_hw, reverse):
     """ActNorm followed by the 1x1 conv (or their inverses in reverse order) as ONE per-pixel affine
     map, so FlowStep needs a single pass over the activations (marscf_main.py:64-68 / :95-97):
@@ -237,6 +240,20 @@ def fold_actnorm_invconv(actnorm, invconv, x_hw, reverse):
     log-det terms: sum(logs) H W (common_modules.py:167) and sum(log_s) W^2 (common_modules.py:104).
     """
     h, w = x_hw
+    c = invconv.w_shape[0]
+    params = (actnorm.bias, actnorm.logs) + tuple(invconv._params())
+    if (FOLD_KERNEL and invconv.LU and c <= 158 and all(t.is_cuda and t.dtype == torch.float32 for t in params)
+            and not (torch.is_grad_enabled() and any(t.requires_grad for t in params))):
+        # inference / sampling: the whole assembly (masks, triangular inverses in fp64, products, fold) is one flowk launch
+        _lib.check_device(invconv.l, "fold_actnorm_invconv")
+        dev = invconv.l.device
+        mat = torch.empty(c, c, device=dev, dtype=torch.float32)
+        out = torch.empty(c + 1, device=dev, dtype=torch.float32)
+        ptr = lambda t: t.detach().contiguous().data_ptr()       # noqa: E731 (parameters / buffers are contiguous: no copy)
+        _lib.call("flowk_fold_actnorm_invconv", ptr(invconv.l), ptr(invconv.u), ptr(invconv.log_s), ptr(invconv.p),
+                  ptr(invconv.sign_s), ptr(actnorm.logs), ptr(actnorm.bias), c, int(h), int(w), int(bool(reverse)),
+                  mat.data_ptr(), out.data_ptr(), out[c:].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return mat, out[:c], out[c:]
     mat, logabsdet = invconv.weight_and_logabsdet(reverse)
     logs = actnorm.logs.view(-1)
     bias = actnorm.bias.view(-1)

@@ -37,24 +37,30 @@ def conv_weight_operand(w, cin_pad=None):
     return split_hilo(wk.reshape(n, kh * kw * cin_pad))
 
 
-def conv_weight_operand_f16(w):
+def conv_weight_operand_f16(w, gain=None, mode=_lib.PACK_PLAIN, factor=1.0, bias=None):
     """[N, Cin, kh, kw] conv weight (or [N, Cin] linear weight) -> fp16 (hi, lo) pair [N, taps * ceil64(Cin)] in (tap, c)
     order for FLOWK_OPERAND_F16, pre-scaled by a power of two s so that max|w s| lies in [2^14, 2^15): the lo part then
-    keeps its 11 bits clear of fp16's subnormal range.  Returns (hi, lo, 1 / s); 1 / s goes to conv_gemm(acc_scale=)."""
+    keeps its 11 bits clear of fp16's subnormal range.  `gain` / `mode` fuse a per-output-channel factor (weight norm, or an
+    ActNorm's exp(factor * logs) with `bias` scaled alike) - see flowk_pack_weight_f16.  Two launches per weight.
+    Returns (hi, lo, 1 / s[, bias * gain]); 1 / s goes to conv_gemm(acc_scale=)."""
     if w.dim() == 2:
         w = w[:, :, None, None]
     n, cin, kh, kw = w.shape
     cin_pad = (cin + 63) // 64 * 64
-    wk = w.permute(0, 2, 3, 1).float()
-    if cin_pad != cin:
-        wk = torch.nn.functional.pad(wk, (0, cin_pad - cin))
-    wk = wk.reshape(n, kh * kw * cin_pad).contiguous()
-    amax = float(torch.linalg.vector_norm(wk, float("inf"))) if wk.numel() else 0.0   # (host sync: cached per weight version)
-    import math
-    e = 14 - math.floor(math.log2(amax)) if amax > 0 and math.isfinite(amax) else 0
-    e = max(-14, min(24, e))
-    hi, lo = split_rows_f16(wk, 2.0 ** e)
-    return hi, lo, 2.0 ** (-e)
+    taps = kh * kw
+    w = w.detach().contiguous().float()
+    _lib.check_device(w, "conv_weight_operand_f16")
+    hi = torch.empty(n, taps * cin_pad, device=w.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    ws = torch.empty(n + 2, device=w.device, dtype=torch.float32)
+    g = None if gain is None else gain.detach().reshape(-1).contiguous().float()
+    b_in = None if bias is None else bias.detach().reshape(-1).contiguous().float()
+    b_out = None if bias is None else torch.empty_like(b_in)
+    assert g is None or g.numel() == n
+    _lib.call("flowk_pack_weight_f16", w.data_ptr(), _p(g), int(mode), float(factor), _p(b_in), _p(b_out), n, cin, taps,
+              cin_pad, hi.data_ptr(), lo.data_ptr(), ws.data_ptr(), _stream())
+    acc_scale = float(ws[n + 1])                       # (host sync: cached per weight version)
+    return (hi, lo, acc_scale) if bias is None else (hi, lo, acc_scale, b_out)
 
 
 def split_rows_f16(x, scale=1.0):

@@ -205,6 +205,29 @@ int flowk_nchw_to_nhwc_hilo_f16(const float* x, long long batch_stride, int B, i
                                 void* hi, void* lo, flowk_stream_t stream);
 int flowk_split_hilo_f16(const float* x, void* hi, void* lo, long long n, float scale, flowk_stream_t stream);
 
+/* Weight preparation for FLOWK_OPERAND_F16 in two launches (csrc/weight_pack.cu), once per weight version: w [N, cin, taps]
+ * (torch conv / linear layout) times a per-output-channel gain
+ *   FLOWK_PACK_PLAIN        1
+ *   FLOWK_PACK_WEIGHT_NORM  gain[n] / ||w[n]||      weight_g / weight_v of mixlogcdf_nn.py:19-21
+ *   FLOWK_PACK_EXP_GAIN     exp(factor * gain[n])   ActNorm / Conv2dZeros scale folded into the conv (affine_coupling.py:31-63);
+ *                                                   bias_out[n] = bias_in[n] * exp(factor * gain[n]) when bias_out is given
+ * -> K-major fp16 (hi, lo) rows [N, taps * cin_pad] in (tap, c) order (cin_pad % 8 == 0, zero padding), pre-scaled by the power
+ * of two that puts max|w| into [2^14, 2^15).  ws: N + 2 floats {row gains [N], max bits, acc_scale}; ws[N + 1] is the
+ * `acc_scale` to hand to flowk_conv_gemm. */
+enum { FLOWK_PACK_PLAIN = 0, FLOWK_PACK_WEIGHT_NORM = 1, FLOWK_PACK_EXP_GAIN = 2 };
+int flowk_pack_weight_f16(const float* w, const float* gain, int mode, float factor, const float* bias_in, float* bias_out,
+                          int N, int cin, int taps, int cin_pad, void* hi, void* lo, float* ws, flowk_stream_t stream);
+
+/* ActNorm followed by the LU-parametrised invertible 1x1 conv (common_modules.py:57-127,130-187; a FlowStep's first two
+ * layers, marscf_main.py:64-68 / :95-97) folded into one per-pixel affine map for flowk_channel_mix_*: l, u, p [C, C],
+ * log_s, sign_s [C] (InvertibleConv1x1), logs, bias [C] (Actnormlayer); assembled in fp64 by one CTA.
+ *   forward (reverse = 0)  mat = P (L U) diag(e^logs),  bias_out = mat bias,  ldj[0] = sum(logs) H W + sum(log_s) W^2
+ *   reverse                mat = diag(e^-logs) U^-1 L^-1 P^T,  bias_out = -bias,  ldj[0] = -(...)
+ * C <= 158 (the fp64 matrix lives in shared memory). */
+int flowk_fold_actnorm_invconv(const float* l, const float* u, const float* log_s, const float* p, const float* sign_s,
+                               const float* logs, const float* bias, int C, int H, int W, int reverse, float* mat,
+                               float* bias_out, float* ldj, flowk_stream_t stream);
+
 /* Fused pointwise layers of the Flow++ conditioner (training path), tensors viewed as [outer, channels, inner]
  * (inner = H*W for NCHW / dim 1, inner = 1 for NHWC / last dim):
  *   concat_elu: x [outer, C, inner] -> y [outer, 2C, inner] = elu(cat(x, -x))        mixlogcdf_nn.py:8-10

@@ -25,5 +25,7 @@ for row in csv.DictReader(lines):
 print("| launches | total us | share | kernel |\n|---:|---:|---:|---|")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("| %d | %.1f | %.1f%% | `%s` |" % (n, t, 100 * t / total, k))
+own = sum(t for k, (n, t) in agg.items() if re.search(r"flowk::|tc::|attn_train::", k))
+print("\nflowk kernels: %.1f%% of the device time (the rest: ATen / cuBLAS / MAGMA glue)" % (100 * own / total))
 print("\ntotal: %d launches, %.1f us (cold-cache, serialised under ncu: compare shares, not absolutes)"
       % (sum(a[0] for a in agg.values()), total))

@@ -877,3 +877,30 @@ def test_channel_mix_tensor_core_route_matches_cuda_core_kernel(F, C, H, B):
     parity(y_tc, ref64.float().cpu(), rel=2e-6, what="tcgen05 channel mix vs fp64")
     parity(y_tc, y_ref.cpu(), rel=2e-6, what="tcgen05 vs CUDA-core channel mix")
     assert torch.allclose(l_tc, l_ref)
+
+
+@pytest.mark.parametrize("C", [3, 12, 48, 96, 150])
+def test_fold_kernel_matches_torch_assembly(F, C):
+    """flowk_fold_actnorm_invconv (one launch: masks, triangular solves in fp64, P L U products, ActNorm fold, log-det) vs
+    the same fold assembled with torch ops (common_modules.fold_actnorm_invconv with the kernel switched off)."""
+    np.random.seed(C)
+    gen = torch.Generator().manual_seed(C)
+    an = F.cm.Actnormlayer(C).to(dev()).eval()
+    ic = F.cm.InvertibleConv1x1(C).to(dev()).eval()
+    with torch.no_grad():
+        an.bias.copy_(torch.randn(1, C, 1, 1, generator=gen) * 0.3)
+        an.logs.copy_(torch.randn(1, C, 1, 1, generator=gen) * 0.2)
+        ic.l.add_(torch.randn(C, C, generator=gen).to(dev()) * 0.02)      # also off the triangle: must be masked out
+        ic.u.add_(torch.randn(C, C, generator=gen).to(dev()) * 0.02)
+        ic.log_s.add_(torch.randn(C, generator=gen).to(dev()) * 0.05)
+        for reverse in (False, True):
+            got = F.cm.fold_actnorm_invconv(an, ic, (8, 16), reverse)
+            F.cm.FOLD_KERNEL = False
+            try:
+                want = F.cm.fold_actnorm_invconv(an, ic, (8, 16), reverse)
+            finally:
+                F.cm.FOLD_KERNEL = True
+            for g, w, what in zip(got, want, ("matrix", "bias", "ldj")):
+                scale = max(1.0, float(w.abs().max()))
+                assert g.shape == w.shape, what
+                assert float((g - w).abs().max()) <= 2e-6 * scale * (4 if reverse else 1), (what, reverse)

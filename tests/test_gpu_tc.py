@@ -600,3 +600,44 @@ def test_training_attention_fwd_bwd_match_fp64(B, S, C, heads, p):
     tc_autograd.advance_dropout_seed(dev)
     if p > 0:
         assert not torch.equal(tc_autograd.attention_core(qkv.detach(), heads, p, salt), out.detach())
+
+
+@pytest.mark.parametrize("shape", [(96, 192, 3), (192, 96, 1), (12, 6, 3), (130, 40, 5), (288, 96, None)])
+@pytest.mark.parametrize("mode", ["plain", "weight_norm", "exp_gain"])
+def test_pack_weight_f16_matches_torch_formula(tc, shape, mode):
+    """flowk_pack_weight_f16 (weight norm / ActNorm gain, permute, pad, power-of-two scaling, hi/lo split in two launches)
+    against the same operand written with torch ops: hi + lo reproduces w * gain * 2^e to 2^-22 relative, the padding is
+    zero, and acc_scale is the exact inverse power of two with max|w 2^e| in [2^14, 2^15)."""
+    from flowk import _lib
+    dev = torch.device("cuda:0")
+    n, cin, k = shape
+    torch.manual_seed(n + cin)
+    w = torch.randn((n, cin) if k is None else (n, cin, k, k), device=dev) * 0.07
+    taps = 1 if k is None else k * k
+    gain = bias = None
+    if mode == "plain":
+        hi, lo, sc = tc.conv_weight_operand_f16(w)
+        w_eff = w
+    elif mode == "weight_norm":
+        gain = torch.rand(n, 1, device=dev) + 0.5
+        hi, lo, sc = tc.conv_weight_operand_f16(w, gain, _lib.PACK_WEIGHT_NORM)
+        norm = w.reshape(n, -1).double().norm(dim=1)
+        w_eff = (w.double().reshape(n, -1) * (gain.double().reshape(-1) / norm)[:, None]).reshape(w.shape)
+    else:
+        gain = torch.randn(1, n, 1, 1, device=dev) * 0.3
+        bias = torch.randn(n, device=dev)
+        hi, lo, sc, b = tc.conv_weight_operand_f16(w, gain, _lib.PACK_EXP_GAIN, 3.0, bias)
+        g = torch.exp(gain.double().reshape(-1) * 3.0)
+        w_eff = (w.double().reshape(n, -1) * g[:, None]).reshape(w.shape)
+        torch.testing.assert_close(b.double(), bias.double() * g, rtol=1e-6, atol=0)
+    cin_pad = (cin + 63) // 64 * 64
+    assert hi.shape == lo.shape == (n, taps * cin_pad) and hi.dtype == torch.float16
+    m, e = math.frexp(1.0 / sc)
+    assert m == 0.5                                               # a power of two
+    want = w_eff.double().reshape(n, cin, taps).permute(0, 2, 1) / sc          # [n, taps, cin] scaled
+    amax = float(want.abs().max())
+    assert 2.0 ** 14 * (1 - 1e-6) <= amax < 2.0 ** 15 * (1 + 1e-6)
+    got = (hi.double() + lo.double()).reshape(n, taps, cin_pad)
+    assert float(got[:, :, cin:].abs().max()) == 0.0 if cin_pad > cin else True
+    err = float((got[:, :, :cin] - want).abs().max()) / amax
+    assert err < 2.0 ** -21, err
