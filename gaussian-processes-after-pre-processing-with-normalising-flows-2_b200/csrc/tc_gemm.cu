@@ -55,6 +55,8 @@ struct Params {
   int tmem_cols, stages;
   int bar_offset;                  // byte offset of the mbarriers: past the pipeline stages AND the epilogue staging area
   int dxsplit, a_slots, w_slots;   // 3x3 "dx-split" mode: one accumulator per column shift, activation tile reused by 3 taps
+  int pair, w_unit, pair_nmma;     // dx-split on CTA pairs (cta_group::2, M = 256 per MMA): each CTA of the pair stages half of
+                                   // the weight rows, in TMA boxes of w_unit rows (umma.cuh)
   int pre, out_mask;
   const float* bias;               // [N] or null
   const float* res;                // [M, C] residual (PRE_GLU_RES_LN), C = N/2
@@ -77,7 +79,10 @@ struct Params {
   long long* trace;                // optional [16] clock64 stamps of CTA (0,0): setup, first full, last mma, epi start, epi end
 };
 
-template <int PRE, int NV, bool F16>   // NV: 128-column groups per lane in the LayerNorm epilogue (1: C <= 128, 2: C <= 256)
+// NV: 128-column groups per lane in the LayerNorm epilogue (1: C <= 128, 2: C <= 256); PAIR: the CTA-pair (cta_group::2)
+// build of the dx-split main loop - a separate instantiation, because a kernel that contains cta_group::2 instructions can
+// only be launched as a cluster
+template <int PRE, int NV, bool F16, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -132,9 +137,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     prefetch_tmap(&map_w_hi);
     prefetch_tmap(&map_w_lo);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;       // pair mode: rank 0 issues the MMAs of both CTAs
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();         // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool tracing = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
@@ -151,7 +161,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       else { b0 = m_tile / tiles_per_img; h0 = (m_tile % tiles_per_img) * p.ht; }
       griddep_wait();               // PDL: everything before this overlapped the previous kernel's tail; its output is
                                     // complete and visible from here on (all our global writes come after these loads)
-      if (p.dxsplit) {
+      if (PAIR && p.dxsplit) {
+        // CTA pair: the same groups; this CTA stages its own activation rows and its HALF of every MMA's weight rows
+        // (MMA q of a k-step covers the stacked [dx][n] rows [q n_per, (q + 1) n_per): rank r holds the r-th half), in
+        // boxes of w_unit rows that never straddle a dx block.  All transactions count on the LEADER's full barriers.
+        uint8_t* w_ring = smem + (size_t)p.a_slots * 2 * A_TILE_BYTES;
+        const int groups = 3 * p.kblocks_per_tap;
+        const int n_total = 3 * p.n_chunk;
+        int n_mma = (n_total + 255) / 256;
+        if ((n_total / n_mma) % 16 || n_total % n_mma) n_mma = 3;
+        if (p.pair_nmma) n_mma = p.pair_nmma;
+        const int half = n_total / n_mma / 2;                        // rows of one MMA's weight tile held by this CTA
+        const int lo_off = (n_total / 2) * ROW_BYTES;                // the lo tiles follow the hi tiles inside a slot
+        for (int g = 0; g < groups; ++g) {
+          const int dyi = g / p.kblocks_per_tap, cb = g % p.kblocks_per_tap;
+          const int sa = g % p.a_slots;
+          mbar_wait(&empty_bar[sa], (((uint32_t)(g / p.a_slots)) & 1u) ^ 1u, failed);
+          uint8_t* at = smem + (size_t)sa * 2 * A_TILE_BYTES;
+          const uint32_t afull = mapa_rank(&full_bar[sa], 0);
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[sa], 4u * A_TILE_BYTES);
+          tma_load_4d_pair(at, &map_a_hi, afull, cb * BK, 0, h0 + dyi - 1, b0);
+          tma_load_4d_pair(at + A_TILE_BYTES, &map_a_lo, afull, cb * BK, 0, h0 + dyi - 1, b0);
+          const int sw = g % p.w_slots;
+          mbar_wait(&wempty_bar[sw], (((uint32_t)(g / p.w_slots)) & 1u) ^ 1u, failed);
+          uint8_t* wt = w_ring + (size_t)sw * 3 * w_tile_bytes;
+          const uint32_t wfull = mapa_rank(&wfull_bar[sw], 0);
+          if (cta_rank == 0) mbar_expect_tx(&wfull_bar[sw], 6u * (uint32_t)w_tile_bytes);
+          for (int q = 0; q < n_mma; ++q)
+            for (int j = 0; j < half; j += p.w_unit) {
+              const int r = q * 2 * half + (int)cta_rank * half + j;  // stacked row = dx * n_chunk + n
+              const int dxi = r / p.n_chunk, n = r - dxi * p.n_chunk;
+              const int kcol = ((dyi * 3 + dxi) * p.kblocks_per_tap + cb) * BK;
+              uint8_t* dst = wt + (size_t)(q * half + j) * ROW_BYTES;
+              tma_load_2d_pair(dst, &map_w_hi, wfull, kcol, n_base + n);
+              tma_load_2d_pair(dst + lo_off, &map_w_lo, wfull, kcol, n_base + n);
+            }
+        }
+      } else if (p.dxsplit) {
         // group g = (dy, channel block): ONE activation tile (rows shifted by dy, columns unshifted) feeds the three
         // taps (dy, dx = -1, 0, +1); each tap streams its own weight tile.  Activation traffic / 3.
         uint8_t* w_ring = smem + (size_t)p.a_slots * 2 * A_TILE_BYTES;
@@ -218,7 +264,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const uint32_t leader = elect_one();
     {
       const uint32_t idesc = make_idesc_t<F16>(p.n_chunk);
-      if (p.dxsplit) {
+      if (PAIR && p.dxsplit) {
+        if (cta_rank == 0) {
+          // M = 256 MMAs over both CTAs' activation tiles; each CTA's slot holds its half of every weight tile
+          const uint32_t w_ring = smem_u32(smem + (size_t)p.a_slots * 2 * A_TILE_BYTES);
+          const int groups = 3 * p.kblocks_per_tap;
+          const int n_total = 3 * p.n_chunk;
+          int n_mma = (n_total + 255) / 256;
+          if ((n_total / n_mma) % 16 || n_total % n_mma) n_mma = 3;
+          if (p.pair_nmma) n_mma = p.pair_nmma;
+          const int n_per = n_total / n_mma;
+          const uint32_t idesc_w = make_idesc_f16_pair(n_per);
+          const uint64_t per_units = (uint64_t)((uint32_t)((n_per / 2) * ROW_BYTES) >> 4);
+          const uint64_t lo_units = (uint64_t)((uint32_t)((n_total / 2) * ROW_BYTES) >> 4);
+          for (int g = 0; g < groups; ++g) {
+            const int sa = g % p.a_slots, sw = g % p.w_slots;
+            mbar_wait(&full_bar[sa], ((uint32_t)(g / p.a_slots)) & 1u, failed);
+            mbar_wait(&wfull_bar[sw], ((uint32_t)(g / p.w_slots)) & 1u, failed);
+            tc_fence_after();
+            if (tracing && lane == 0 && g == 0) p.trace[1] = clock64();
+            if (tracing && lane == 0 && g == groups - 1) p.trace[2] = clock64();
+            const uint32_t a_hi = smem_u32(smem + (size_t)sa * 2 * A_TILE_BYTES);
+            const uint32_t w_hi = w_ring + (uint32_t)sw * 3u * (uint32_t)w_tile_bytes;
+            const uint64_t da_hi = make_smem_desc(a_hi), da_lo = da_hi + (A_TILE_BYTES >> 4);
+            const uint64_t db_hi = make_smem_desc(w_hi), db_lo = db_hi + lo_units;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);
+              for (int q = 0; q < n_mma; ++q) {
+                const uint64_t bo = ko + q * per_units;
+                const uint32_t d = tmem_base + q * n_per;
+                umma_f16_pair_elect(d, da_hi + ko, db_hi + bo, idesc_w, (g | k) == 0 ? 0u : 1u, leader);
+                umma_f16_pair_elect(d, da_lo + ko, db_hi + bo, idesc_w, 1u, leader);
+                umma_f16_pair_elect(d, da_hi + ko, db_lo + bo, idesc_w, 1u, leader);
+              }
+            }
+            umma_commit_pair_elect(&wempty_bar[sw], leader);
+            umma_commit_pair_elect(&empty_bar[sa], leader);
+          }
+          umma_commit_pair_elect(tmem_full_bar, leader);
+        }
+      } else if (p.dxsplit) {
         const uint32_t w_ring = smem_u32(smem + (size_t)p.a_slots * 2 * A_TILE_BYTES);
         const int groups = 3 * p.kblocks_per_tap;
         // the three accumulators are the TMEM columns [0, 3*n_chunk): cover them with as few MMAs as possible
@@ -757,9 +843,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   }
   if (tracing && threadIdx.x == 64) p.trace[4] = clock64();
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();         // neither CTA of a pair may retire while the other still uses its memory
+  else __syncthreads();
   if (tracing && threadIdx.x == 0) p.trace[5] = clock64();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
   if (threadIdx.x == 0 && *failed && p.status) *p.status = 1;
 }
 
@@ -1050,10 +1140,36 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   // 3x3 dx-split mode: three accumulators (one per column shift) so that an activation tile serves three taps
   p.dxsplit = (a->taps == 9 && dil == 1 && a->pre == PRE_BIAS && W <= 32 && 32 % W == 0 && p.n_chunks == 1 &&
                3 * p.n_chunk <= 512 && p.ksplit == 1) ? 1 : 0;
+  // CTA pairs (cta_group::2) for the dx-split 3x3 layers that fill the machine: the main loop of these is bound by the
+  // bytes ONE SM ingests through TMA, most of them weights that every CTA streams in full - a pair shares them, each CTA
+  // staging half of the rows.  Needs an even number of M tiles (the pair = M tiles 2i, 2i + 1) and fp16 operands.
+  p.pair = 0;
+  if (p.dxsplit && f16) {
+    static int pair_env = -1, nmma_env = 0;
+    if (pair_env < 0) {
+      const char* e = getenv("FLOWK_PAIR");
+      pair_env = e ? atoi(e) : 0;
+      e = getenv("FLOWK_PAIR_NMMA");
+      nmma_env = e ? atoi(e) : 0;
+    }
+    const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int n_total = 3 * p.n_chunk;
+    int n_mma = (n_total + 255) / 256;
+    if ((n_total / n_mma) % 16 || n_total % n_mma) n_mma = 3;
+    if (nmma_env == 3) n_mma = p.pair_nmma = 3;
+    const int half = n_total / n_mma / 2;
+    int unit = half;                                             // largest box that tiles `half` without straddling a dx block
+    while (unit > 0 && (half % unit || p.n_chunk % unit || unit % 8)) unit -= 8;
+    if (pair_env && m_tiles % 2 == 0 && p.M % BLOCK_M == 0 && m_tiles * n_tiles >= 64 && (n_total / n_mma) % 16 == 0 &&
+        half % 8 == 0 && unit >= 8) {
+      p.pair = 1;
+      p.w_unit = unit;
+    }
+  }
   if (p.dxsplit) {
     p.tmem_cols = 3 * p.n_chunk <= 256 ? 256 : 512;
     if (3 * p.n_chunk <= 128) p.tmem_cols = 128;
-    const int w_slot_bytes = 6 * cols * ROW_BYTES;              // 3 column shifts x (hi, lo)
+    const int w_slot_bytes = (p.pair ? 3 : 6) * cols * ROW_BYTES;   // 3 column shifts x (hi, lo); a pair's CTA holds half
     // narrow N tiles (deep levels): the activation tiles dominate the bytes, so give THEM the deeper ring
     p.a_slots = (220 * 1024 - 2048 - 4 * 2 * A_TILE_BYTES) / w_slot_bytes >= 3 ? 4 : 2;
     if (const char* e = getenv("FLOWK_A_SLOTS")) p.a_slots = atoi(e);   // tuning knob
@@ -1067,7 +1183,7 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   if ((p.out_mask & (OUT_F32 | OUT_HILO | OUT_HILO_POS | OUT_HILO_CELU | OUT_HILO_RELU)) && (N & 3)) return FLOWK_ERR_SHAPE;
   while (stages > 1 && (size_t)stages * stage_bytes + 2048 > 227 * 1024) --stages;
   size_t region = (size_t)stages * stage_bytes;
-  if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * 6 * cols * ROW_BYTES;
+  if (p.dxsplit) region = (size_t)p.a_slots * 2 * A_TILE_BYTES + (size_t)p.w_slots * (p.pair ? 3 : 6) * cols * ROW_BYTES;
   if (epi_bytes > region) region = (epi_bytes + 1023) / 1024 * 1024;
   if (region + 2048 > 227 * 1024) return FLOWK_ERR_SHAPE;
   // chained second GEMM (gate -> in_proj): needs both accumulators in TMEM and the operand / weight tiles in smem
@@ -1100,7 +1216,8 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   alignas(64) CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo;
   const int Ktot = a->taps * p.kblocks_per_tap * bk;          // weights: every tap padded to whole k-blocks
   if (!make_map_act(&ma_hi, a->a_hi, B, H, W, Cin, bt, ht, wt, es) || !make_map_act(&ma_lo, a->a_lo, B, H, W, Cin, bt, ht, wt, es) ||
-      !make_map_w(&mw_hi, a->w_hi, N, Ktot, p.n_chunk, es) || !make_map_w(&mw_lo, a->w_lo, N, Ktot, p.n_chunk, es))
+      !make_map_w(&mw_hi, a->w_hi, N, Ktot, p.pair ? p.w_unit : p.n_chunk, es) ||
+      !make_map_w(&mw_lo, a->w_lo, N, Ktot, p.pair ? p.w_unit : p.n_chunk, es))
     return FLOWK_ERR_ARG;
   if (p.chain) {
     const int k2tot = f16 ? ((N / 2 + bk - 1) / bk) * bk : N / 2;          // fp16 weights: rows padded to whole 64-channel blocks
@@ -1114,25 +1231,27 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, n_tiles, p.ksplit);
   // one launch helper per (epilogue, LayerNorm width, operand format) instantiation; each remembers the largest dynamic
   // shared-memory opt-in it has requested
-#define FLOWK_LAUNCH_GEMM(PRE_, NV_, F16_)                                                                         \
+#define FLOWK_LAUNCH_GEMM(PRE_, NV_, F16_, PAIR_)                                                                         \
   do {                                                                                                              \
     static size_t smem_set = 0;                                                                                     \
     if (smem_bytes > smem_set) {                                                                                    \
-      FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_, NV_, F16_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      FLOWK_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<PRE_, NV_, F16_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem_bytes));                                                         \
       smem_set = smem_bytes;                                                                                        \
     }                                                                                                               \
-    FLOWK_CUDA_OK(launch_pdl(conv_gemm_kernel<PRE_, NV_, F16_>, grid, dim3(NUM_THREADS), smem_bytes, stream, ma_hi, ma_lo, \
-                             mw_hi, mw_lo, mw2_hi, mw2_lo, p));                                                     \
+    FLOWK_CUDA_OK(launch_pdl_cluster(conv_gemm_kernel<PRE_, NV_, F16_, PAIR_>, grid, dim3(NUM_THREADS), smem_bytes, stream,          \
+                                     PAIR_ ? 2 : 1, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, p));               \
   } while (0)
   if (a->pre == PRE_LSTM) {
-    if (f16) FLOWK_LAUNCH_GEMM(PRE_LSTM, 1, true); else FLOWK_LAUNCH_GEMM(PRE_LSTM, 1, false);
+    if (f16) FLOWK_LAUNCH_GEMM(PRE_LSTM, 1, true, false); else FLOWK_LAUNCH_GEMM(PRE_LSTM, 1, false, false);
   } else if (a->pre == PRE_GLU_RES_LN && N / 2 > 128) {
-    if (f16) FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 2, true); else FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 2, false);
+    if (f16) FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 2, true, false); else FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 2, false, false);
   } else if (a->pre == PRE_GLU_RES_LN) {
-    if (f16) FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 1, true); else FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 1, false);
+    if (f16) FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 1, true, false); else FLOWK_LAUNCH_GEMM(PRE_GLU_RES_LN, 1, false, false);
+  } else if (p.pair) {
+    FLOWK_LAUNCH_GEMM(PRE_BIAS, 1, true, true);
   } else {
-    if (f16) FLOWK_LAUNCH_GEMM(PRE_BIAS, 1, true); else FLOWK_LAUNCH_GEMM(PRE_BIAS, 1, false);
+    if (f16) FLOWK_LAUNCH_GEMM(PRE_BIAS, 1, true, false); else FLOWK_LAUNCH_GEMM(PRE_BIAS, 1, false, false);
   }
 #undef FLOWK_LAUNCH_GEMM
   if (p.ksplit > 1) {

@@ -641,3 +641,49 @@ def test_pack_weight_f16_matches_torch_formula(tc, shape, mode):
     assert float(got[:, :, cin:].abs().max()) == 0.0 if cin_pad > cin else True
     err = float((got[:, :, :cin] - want).abs().max()) / amax
     assert err < 2.0 ** -21, err
+
+
+def test_cta_pair_mode_matches_single_cta_kernel(tmp_path):
+    """FLOWK_PAIR=1 (csrc/tc_gemm.cu: the dx-split 3x3 main loop on CTA pairs - cta_group::2, M = 256 MMAs, each CTA staging
+    half of the weight rows, multicast commits) against fp64 and against the default single-CTA kernel, at the level-1 shape
+    of cfg2 and with the one-MMA-per-column-shift variant.  The option is read once per process: subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch, torch.nn.functional as F
+sys.path.insert(0, %r)
+import flowk
+from flowk import tc
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+B, Cin, N, H, W = 64, 192, 96, 16, 16
+x = torch.randn(B, Cin, H, W, device=dev)
+w = torch.randn(N, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5
+bias = torch.randn(N, device=dev)
+rows = x.permute(0, 2, 3, 1).reshape(B * H * W, Cin).contiguous()
+a_hi, a_lo = tc.split_rows_f16(rows)
+w_hi, w_lo, sc = tc.conv_weight_operand_f16(w)
+out = torch.full((B * H * W, N), float("nan"), device=dev)
+status = torch.zeros(1, dtype=torch.int32, device=dev)
+tc.conv_gemm(a_hi, a_lo, w_hi, w_lo, B, H, W, Cin, N, 9, tc.PRE_BIAS, tc.OUT_F32, bias=bias, out_f32=out, status=status,
+             acc_scale=sc)
+torch.cuda.synchronize()
+assert int(status) == 0
+ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1).reshape(B * H * W, N)
+err = float((out.double() - ref).abs().max() / ref.abs().max())
+assert err < 2e-6, err
+torch.save(out.cpu(), sys.argv[1])
+print("ok", err)
+''' % root
+    outs = []
+    for i, env in enumerate(({"FLOWK_PAIR": "0"}, {"FLOWK_PAIR": "1"}, {"FLOWK_PAIR": "1", "FLOWK_PAIR_NMMA": "3"})):
+        path = os.path.join(tmp_path, "out%d.pt" % i)
+        r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, **env), capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(torch.load(path))
+    # same products in the same k order, accumulated by the same tensor cores
+    assert float((outs[0] - outs[1]).abs().max()) <= 1e-5 * float(outs[0].abs().max())
+    assert float((outs[0] - outs[2]).abs().max()) <= 1e-5 * float(outs[0].abs().max())
