@@ -86,13 +86,13 @@ class ConvGemmArgs(ctypes.Structure):
                [(n, ctypes.c_int) for n in ("B", "H", "W", "Cin", "N", "taps", "pre", "out_mask")] + \
                [(n, ctypes.c_void_p) for n in ("w2_hi", "w2_lo", "out2_f32")] + [("N2", ctypes.c_int)] + \
                [("splitk_ws", ctypes.c_void_p), ("operand_format", ctypes.c_int), ("acc_scale", ctypes.c_float),
-                ("dilation", ctypes.c_int), ("acc_scale2", ctypes.c_float)]
+                ("dilation", ctypes.c_int), ("acc_scale2", ctypes.c_float), ("acc_scale_ptr", ctypes.c_void_p)]
 
 
 class WnJob(ctypes.Structure):
     """Mirror of `flowk_wn_job` (include/flowk.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("v", "g", "norm", "w", "fwd_hi", "fwd_lo", "dg_hi", "dg_lo")] + \
-               [(n, ctypes.c_int) for n in ("N", "cin", "taps", "cin_pad", "n_pad", "reserved")]
+               [(n, ctypes.c_int) for n in ("N", "cin", "taps", "cin_pad", "n_pad", "fwd_f16")]
 
 
 class AdamaxChunk(ctypes.Structure):

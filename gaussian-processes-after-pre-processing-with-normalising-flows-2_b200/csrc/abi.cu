@@ -1,7 +1,7 @@
 // ABI bookkeeping for libflowk.so: version, status strings, workspace sizing.
 #include "common.cuh"
 
-extern "C" int flowk_abi_version(void) { return 2; }   // 2: flowk_conv_gemm_args grew (operand_format, acc_scale, dilation, acc_scale2)
+extern "C" int flowk_abi_version(void) { return 3; }   // 2: flowk_conv_gemm_args grew (operand_format, acc_scale, dilation, acc_scale2); 3: + acc_scale_ptr, flowk_wn_job.fwd_f16
 
 extern "C" size_t flowk_ldj_workspace_bytes(int B) {
   if (B < 1) B = 1;

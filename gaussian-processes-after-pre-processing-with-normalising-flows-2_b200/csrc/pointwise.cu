@@ -280,6 +280,125 @@ __global__ void __launch_bounds__(256) wn_bwd_partials_kernel(
   }
 }
 
+// Transposed partials ([s][t][c][n]: the output channel is the fastest index): one CTA takes R consecutive output channels,
+// so every load is a whole 16- / 32-byte run of one sector instead of one float per sector.  Narrow layers (cols <= 128:
+// the Linear layers, up to 64 split-K slices) leave most of the 256 threads without a column, so the slices are dealt out
+// to SG = 256 / cols thread groups (contiguous ranges, each summed in index order) and the group sums are added in group
+// order: a fixed summation tree, bit-reproducible.
+template <int R>
+__global__ void __launch_bounds__(256) wn_bwd_partials_t_kernel(
+    const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norm,
+    const float* __restrict__ partial, float* __restrict__ gv, float* __restrict__ gg, int N, int cin, int taps, int splits) {
+  extern __shared__ float wn_sm[];            // gw_rows [R][cols] in (t, c) order, then psum [SG][R][cols] when SG > 1
+  __shared__ float part[8][R];
+  const int row0 = blockIdx.x * R, cols = cin * taps;
+  const int jt = cols >= 256 ? 256 : (cols + 31) / 32 * 32;      // column lanes
+  const int sgs = 256 / jt;                                      // split groups
+  const int jl = threadIdx.x % jt, sg = threadIdx.x / jt;
+  const int chunk = (splits + sgs - 1) / sgs;
+  float* gw_rows = wn_sm;
+  float* psum = wn_sm + R * cols;
+  const size_t split_stride = (size_t)taps * N * cin;
+  float d[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) d[r] = 0.f;
+  for (int j0 = 0; j0 < cols; j0 += jt) {
+    const int j = j0 + jl;
+    const bool live = j < cols && sg < sgs;
+    const int t = live ? j / cin : 0, c = live ? j - t * cin : 0;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    if (live) {
+      const float4* q = reinterpret_cast<const float4*>(partial + ((size_t)t * cin + c) * N + row0);
+      int s = sg * chunk;
+      const int s_end = s + chunk < splits ? s + chunk : splits;
+      for (; s + 8 <= s_end; s += 8) {         // eight slices' loads in flight (L2-latency-bound), added in index order
+        float4 a[8][R / 4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int h = 0; h < R / 4; ++h) a[u][h] = __ldg(q + ((size_t)(s + u) * split_stride) / 4 + h);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int h = 0; h < R / 4; ++h) {
+            acc[4 * h] += a[u][h].x;
+            acc[4 * h + 1] += a[u][h].y;
+            acc[4 * h + 2] += a[u][h].z;
+            acc[4 * h + 3] += a[u][h].w;
+          }
+      }
+      for (; s + 4 <= s_end; s += 4) {         // four slices' loads in flight
+        float4 a[4][R / 4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int h = 0; h < R / 4; ++h) a[u][h] = __ldg(q + ((size_t)(s + u) * split_stride) / 4 + h);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int h = 0; h < R / 4; ++h) {
+            acc[4 * h] += a[u][h].x;
+            acc[4 * h + 1] += a[u][h].y;
+            acc[4 * h + 2] += a[u][h].z;
+            acc[4 * h + 3] += a[u][h].w;
+          }
+      }
+      for (; s < s_end; ++s)
+#pragma unroll
+        for (int h = 0; h < R / 4; ++h) {
+          const float4 a = __ldg(q + ((size_t)s * split_stride) / 4 + h);
+          acc[4 * h] += a.x;
+          acc[4 * h + 1] += a.y;
+          acc[4 * h + 2] += a.z;
+          acc[4 * h + 3] += a.w;
+        }
+    }
+    if (sgs > 1) {                             // (then cols <= jt: a single pass of this loop)
+      if (live) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) psum[(sg * R + r) * cols + j] = acc[r];
+      }
+      __syncthreads();
+      if (live && sg == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float tot = acc[r];
+          for (int k = 1; k < sgs; ++k) tot += psum[(k * R + r) * cols + j];
+          acc[r] = tot;
+        }
+      }
+    }
+    if (live && sg == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        gw_rows[r * cols + j] = acc[r];
+        d[r] = fmaf(acc[r], v[(size_t)(row0 + r) * cols + (size_t)c * taps + t], d[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) d[r] = warp_sum(d[r]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) part[threadIdx.x >> 5][r] = d[r];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R * cols; i += 256) {
+    const int r = i / cols, ii = i - r * cols;
+    const int c = ii / taps, t = ii - c * taps;
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dot += part[k][r];
+    const float nr = norm[row0 + r], gr = g[row0 + r];
+    const float sc = gr / nr, k3 = dot * gr / (nr * nr * nr);
+    if (ii == 0) gg[row0 + r] = dot / nr;
+    const size_t at = (size_t)(row0 + r) * cols + ii;
+    gv[at] = gw_rows[r * cols + t * cin + c] * sc - v[at] * k3;
+  }
+}
+
 }  // namespace flowk
 
 extern "C" int flowk_weight_norm_bwd_partials(const float* v, const float* g, const float* norm, const float* partial,
@@ -288,8 +407,17 @@ extern "C" int flowk_weight_norm_bwd_partials(const float* v, const float* g, co
   if (N < 1 || cin < 1 || taps < 1 || splits < 1) return FLOWK_ERR_SHAPE;
   if (!v || !g || !norm || !partial || !gv || !gg) return FLOWK_ERR_ARG;
   if ((size_t)cin * taps * sizeof(float) > 48 * 1024) return FLOWK_ERR_SHAPE;
-  wn_bwd_partials_kernel<<<N, 256, (size_t)cin * taps * sizeof(float), stream>>>(v, g, norm, partial, gv, gg, N, cin, taps,
-                                                                              splits, transposed);
+  const size_t row_bytes = (size_t)cin * taps * sizeof(float);
+  const bool al16 = aligned16(partial) && ((size_t)taps * N * cin) % 4 == 0;
+  // shared memory: the R reduced rows, plus one copy per split group when the layer is narrow (cols <= 128)
+  const int cols = cin * taps, jt = cols >= 256 ? 256 : (cols + 31) / 32 * 32, sgs = 256 / jt;
+  const size_t per_row = row_bytes * (sgs > 1 ? 1 + sgs : 1);
+  if (transposed && al16 && N % 8 == 0 && 8 * per_row <= 48 * 1024)
+    wn_bwd_partials_t_kernel<8><<<N / 8, 256, 8 * per_row, stream>>>(v, g, norm, partial, gv, gg, N, cin, taps, splits);
+  else if (transposed && al16 && N % 4 == 0 && 4 * per_row <= 48 * 1024)
+    wn_bwd_partials_t_kernel<4><<<N / 4, 256, 4 * per_row, stream>>>(v, g, norm, partial, gv, gg, N, cin, taps, splits);
+  else
+    wn_bwd_partials_kernel<<<N, 256, row_bytes, stream>>>(v, g, norm, partial, gv, gg, N, cin, taps, splits, transposed);
   return launch_status();
 }
 
@@ -304,10 +432,24 @@ __global__ void wn_norm_batched_kernel(const flowk_wn_job* __restrict__ jobs) {
   if (row >= j.N) return;
   const int cols = j.cin * j.taps;
   const float* p = j.v + (size_t)row * cols;
-  float s = 0.f;
-  for (int i = threadIdx.x & 31; i < cols; i += 32) s = fmaf(p[i], p[i], s);
+  float s = 0.f, mx = 0.f;
+  for (int i = threadIdx.x & 31; i < cols; i += 32) {
+    s = fmaf(p[i], p[i], s);
+    mx = fmaxf(mx, fabsf(p[i]));
+  }
   s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) j.norm[row] = sqrtf(s);
+  if (j.fwd_f16) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    const float nr = sqrtf(s);
+    j.norm[row] = nr;
+    if (j.fwd_f16) {                                       // max |w| of the layer -> norm[N] (zeroed by the caller)
+      const float top = fabsf(j.g[row] / nr) * mx;
+      if (top > 0.f && top <= 3.0e38f) atomicMax(reinterpret_cast<unsigned*>(j.norm + j.N), __float_as_uint(top));
+    }
+  }
 }
 
 __global__ void wn_operands_batched_kernel(const flowk_wn_job* __restrict__ jobs) {
@@ -322,7 +464,32 @@ __global__ void wn_operands_batched_kernel(const flowk_wn_job* __restrict__ jobs
       j.w[i] = j.v[i] * (j.g[n] / j.norm[n]);
     }
   }
-  if (j.fwd_hi) {
+  if (j.fwd_hi && j.fwd_f16) {
+    // fp16 (hi, lo) forward operand, pre-scaled by the power of two that puts the layer's max |w| into [2^14, 2^15)
+    // (FLOWK_OPERAND_F16, see flowk_pack_weight_f16); 1 / scale goes to norm[N + 1] for flowk_conv_gemm's acc_scale_ptr
+    const unsigned bits = reinterpret_cast<const unsigned*>(j.norm)[N];
+    int e = 0;
+    if (bits != 0u) {
+      const int field = (int)((bits >> 23) & 0xffu);
+      e = field == 0 ? 24 : 14 - (field - 127);
+      e = e < -14 ? -14 : (e > 24 ? 24 : e);
+    }
+    const float scale = __int_as_float((127 + e) << 23);
+    if (t0 == 0) j.norm[N + 1] = __int_as_float((127 - e) << 23);
+    unsigned short* hi16 = reinterpret_cast<unsigned short*>(j.fwd_hi);
+    unsigned short* lo16 = reinterpret_cast<unsigned short*>(j.fwd_lo);
+    const unsigned total = N * taps * cin_pad, row = taps * cin_pad;
+    for (unsigned i = t0; i < total; i += stride) {
+      const unsigned n = i / row, r = i - n * row;
+      const unsigned t = r / cin_pad, c = r - t * cin_pad;
+      float val = 0.f;
+      if (c < cin) val = (j.v[(n * cin + c) * taps + t] * (j.g[n] / j.norm[n])) * scale;
+      unsigned short h, l;
+      split_f16(val, h, l);
+      hi16[i] = h;
+      lo16[i] = l;
+    }
+  } else if (j.fwd_hi) {
     const unsigned total = N * taps * cin_pad, row = taps * cin_pad;
     for (unsigned i = t0; i < total; i += stride) {
       const unsigned n = i / row, r = i - n * row;

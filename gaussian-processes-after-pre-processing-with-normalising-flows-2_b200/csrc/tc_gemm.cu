@@ -73,6 +73,7 @@ struct Params {
   float* out2_f32;                 // [M, n2]
   float acc_scale;                 // F16: the weights were scaled by 1 / acc_scale (a power of two)
   float acc_scale2;                // the same for the chained second GEMM's weights
+  const float* acc_scale_ptr;      // non-null: device copy of acc_scale (read in the epilogue)
   int ksplit;                      // > 1: blockIdx.z takes a slice of every tap's channel blocks; fp32 partial rows go to
                                    // out_f32 + z*M*N (no bias) and flowk's split-K reduce kernel finishes the layer
   int* status;                     // set to 1 if a barrier wait timed out
@@ -409,9 +410,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int slab_row0 = m_tile * BLOCK_M + lane_grp * 32;          // first global row of the 32-row slab
     const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const int ncols_cta = p.n_chunk * p.n_chunks;
-    const float sc = F16 ? p.acc_scale : 1.f;                        // undoes the power-of-two pre-scaling of fp16 weights
     mbar_wait(tmem_full_bar, 0, failed);
     tc_fence_after();
+    // undoes the power-of-two pre-scaling of fp16 weights; from device memory when the weights were packed on the device
+    // (read after the accumulator wait: everything this launch depends on is complete by then)
+    const float sc = F16 ? (p.acc_scale_ptr ? __ldg(p.acc_scale_ptr) : p.acc_scale) : 1.f;
     if (tracing && threadIdx.x == 64) p.trace[3] = clock64();
 
     if (PRE == PRE_BIAS) {
@@ -1045,6 +1048,7 @@ static int conv_gemm_impl(const flowk_conv_gemm_args* a, flowk_stream_t stream, 
   p.dil = dil;
   p.kblocks_per_tap = (Cin + bk - 1) / bk;
   p.acc_scale = f16 ? a->acc_scale : 1.f;
+  p.acc_scale_ptr = f16 ? a->acc_scale_ptr : nullptr;
   p.wt = wt;
   p.ht = ht;
   p.bt = bt;

@@ -23,6 +23,10 @@ import torch
 from . import _lib, tc
 
 ENABLED = True
+FWD_F16 = __import__("os").environ.get("FLOWK_TRAIN_FWD_F16", "1") != "0"
+# Forward GEMMs of the batched weight-norm path on fp16 (hi, lo) operand pairs (FLOWK_OPERAND_F16: half the operand bytes and
+# MMA instructions, the same 22 significant bits; activations are O(1) in magnitude and the weights are scaled on the device).
+# Gradient GEMMs stay on TF32 pairs: gradients need fp32's exponent range.
 
 
 def conv_supported(x, w):
@@ -327,21 +331,27 @@ class WeightNormBatch:
         dev = self.modules[0].weight_v.device
         jobs = (_lib.WnJob * len(self.modules))()
         self.max_rows = 1
+        # one buffer for every layer's [row norms | max |w| scratch | acc_scale]: a single fill resets all the scratch words
+        offs = [0]
+        for m in self.modules:
+            offs.append(offs[-1] + (m.weight_v.shape[0] + 2 + 3) // 4 * 4)
+        self.norms = torch.zeros(offs[-1], device=dev, dtype=torch.float32)
         for i, m in enumerate(self.modules):
             v, g = m.weight_v, m.weight_g
             n, cin = v.shape[0], v.shape[1]
             taps = v.numel() // (n * cin)
             linear = v.dim() == 2
-            cin_pad = cin if linear else _pad32(cin)
+            f16 = FWD_F16 and cin % 8 == 0
+            cin_pad = (cin + 63) // 64 * 64 if f16 else (cin if linear else _pad32(cin))
             n_pad = n if linear else _pad32(n)
             want_w = linear and n % 32 != 0                      # the Linear dgrad falls back to g2 @ w
-            norm = torch.empty(n, device=dev, dtype=torch.float32)
+            norm = self.norms[offs[i]:offs[i] + n + 2]
             w = torch.empty(v.shape, device=dev, dtype=torch.float32) if want_w else None
-            fwd = torch.empty(2, n, taps * cin_pad, device=dev, dtype=torch.float32)
+            fwd = torch.empty(2, n, taps * cin_pad, device=dev, dtype=torch.float16 if f16 else torch.float32)
             dg = None if want_w else torch.empty(2, cin, taps * n_pad, device=dev, dtype=torch.float32)
             jobs[i] = _lib.WnJob(v.data_ptr(), g.data_ptr(), norm.data_ptr(), tc._p(w), fwd[0].data_ptr(), fwd[1].data_ptr(),
                                  None if dg is None else dg[0].data_ptr(), None if dg is None else dg[1].data_ptr(),
-                                 n, cin, taps, cin_pad, n_pad, 0)
+                                 n, cin, taps, cin_pad, n_pad, int(f16))
             self.max_rows = max(self.max_rows, n)
             self.slots.append((norm, w, fwd, dg))
         raw = bytes(jobs)
@@ -352,6 +362,7 @@ class WeightNormBatch:
             return
         if self._pointers() != self._key:          # parameters were re-allocated (.to(), load with assign=True, ...)
             self._build()
+        self.norms.zero_()                          # the per-layer max |w| words accumulate by atomicMax
         _lib.call("flowk_weight_norm_operands_batched", self.table.data_ptr(), len(self.modules), self.max_rows,
                   tc._stream())
         for m, slot in zip(self.modules, self.slots):
@@ -379,10 +390,18 @@ class _WNConv2d(torch.autograd.Function):
             norm, _, fwd, dg = prepared
         else:
             norm, _, fwd, dg = _wn_operands(vd, gd, cp, np_, want_dg=ctx.needs_input_grad[0])
-        a_hi, a_lo = _nchw_operand(x, cp)
         y = torch.empty(b, n, h, ww, device=x.device, dtype=torch.float32)
-        tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], b, h, ww, cp, n, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW,
-                     bias=None if bias is None else bias.detach().contiguous(), out_nchw=y, split_k=True)
+        bias_d = None if bias is None else bias.detach().contiguous()
+        if fwd.dtype == torch.float16:              # batched operands in fp16 pairs; norm = [row norms | scratch | acc_scale]
+            c8 = (cin + 7) // 8 * 8
+            a_hi, a_lo = tc.nchw_to_nhwc_hilo(x.contiguous(), c8, True)
+            tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], b, h, ww, c8, n, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW, bias=bias_d,
+                         out_nchw=y, acc_scale=1.0, acc_scale_ptr=norm[n + 1:])
+            norm = norm[:n]
+        else:
+            a_hi, a_lo = _nchw_operand(x, cp)
+            tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], b, h, ww, cp, n, kh * kw, tc.PRE_BIAS, tc.OUT_NCHW, bias=bias_d,
+                         out_nchw=y, split_k=True)
         ctx.save_for_backward(x, vd, gd, norm, dg)
         ctx.has_bias = bias is not None
         return y
@@ -426,10 +445,17 @@ class _WNLinearFn(torch.autograd.Function):
             norm, w, fwd, dg = prepared
         else:
             norm, w, fwd, dg = _wn_operands(vd, gd, k, n, want_w=not tc_dgrad, want_dg=tc_dgrad)
-        a_hi, a_lo = tc.split_rows(x2)
         y = torch.empty(x2.shape[0], n, device=x.device, dtype=torch.float32)
-        tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], *_rows_as_images(x2.shape[0]), k, n, 1, tc.PRE_BIAS, tc.OUT_F32,
-                     bias=None if bias is None else bias.detach().contiguous(), out_f32=y, split_k=True)
+        bias_d = None if bias is None else bias.detach().contiguous()
+        if fwd.dtype == torch.float16:
+            a_hi, a_lo = tc.split_rows_f16(x2)
+            tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], *_rows_as_images(x2.shape[0]), k, n, 1, tc.PRE_BIAS, tc.OUT_F32,
+                         bias=bias_d, out_f32=y, acc_scale=1.0, acc_scale_ptr=norm[n + 1:])
+            norm = norm[:n]
+        else:
+            a_hi, a_lo = tc.split_rows(x2)
+            tc.conv_gemm(a_hi, a_lo, fwd[0], fwd[1], *_rows_as_images(x2.shape[0]), k, n, 1, tc.PRE_BIAS, tc.OUT_F32,
+                         bias=bias_d, out_f32=y, split_k=True)
         ctx.save_for_backward(x2, vd, gd, norm, dg if tc_dgrad else w)
         ctx.tc_dgrad, ctx.has_bias, ctx.shape = tc_dgrad, bias is not None, shape
         return y.view(*shape[:-1], n)

@@ -187,6 +187,9 @@ typedef struct flowk_conv_gemm_args {
    * dilation * (k - 1) / 2, mar_prior/convolutional_rnn/functional.py:248-272). */
   int dilation;
   float acc_scale2;       /* FLOWK_OPERAND_F16 with a chained GEMM: 1 / (power-of-two pre-scaling of w2) */
+  const float* acc_scale_ptr;   /* non-NULL: acc_scale is read from this DEVICE float when the kernel runs (weights packed on
+                                 * the device in the same stream, e.g. by flowk_weight_norm_operands_batched); acc_scale is
+                                 * then only checked for being positive */
 } flowk_conv_gemm_args;
 enum { FLOWK_OPERAND_TF32 = 0, FLOWK_OPERAND_F16 = 1 };
 
@@ -263,7 +266,10 @@ typedef struct flowk_wn_job {
   float* fwd_lo;
   float* dg_hi;
   float* dg_lo;
-  int N, cin, taps, cin_pad, n_pad, reserved;
+  int N, cin, taps, cin_pad, n_pad;
+  int fwd_f16;   /* 1: fwd_hi / fwd_lo are fp16 arrays [N, taps * cin_pad] (FLOWK_OPERAND_F16, cin_pad = ceil64(cin)), pre-scaled
+                  * by a power of two; `norm` then has N + 2 entries, norm[N] zeroed by the caller before the call (scratch:
+                  * the layer's max |w|) and norm[N + 1] receiving the acc_scale (pass it as acc_scale_ptr) */
 } flowk_wn_job;
 int flowk_weight_norm_operands_batched(const flowk_wn_job* jobs_device, int njobs, int max_rows, flowk_stream_t stream);
 int flowk_weight_norm_bwd(const float* v, const float* g, const float* norm, const float* gw, float* gv, float* gg,

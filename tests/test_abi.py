@@ -20,7 +20,7 @@ def test_header_symbols_exported():
 
 
 def test_abi_version_and_strings():
-    assert _lib.lib.flowk_abi_version() == 2
+    assert _lib.lib.flowk_abi_version() == 3
     assert _lib.lib.flowk_error_string(0) == b"ok"
     assert _lib.lib.flowk_error_string(1) == b"bad shape"
     assert _lib.lib.flowk_ldj_workspace_bytes(64) == 64 * 65 * 4
@@ -96,7 +96,7 @@ def test_structs_mirror_the_header():
     assert ctypes.sizeof(_lib.WnJob) == 8 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.AdamaxChunk) == 4 * 8 + 8
     # N2 is padded to 8 before splitk_ws; then operand_format (int) + acc_scale (float), dilation (int) + reserved (int)
-    assert ctypes.sizeof(_lib.ConvGemmArgs) == 15 * 8 + 8 * 4 + 3 * 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.ConvGemmArgs) == 15 * 8 + 8 * 4 + 3 * 8 + 8 + 8 + 8 + 8 + 8
 
 
 def test_no_cpu_fallback():
