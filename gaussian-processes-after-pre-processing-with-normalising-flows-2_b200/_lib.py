@@ -46,6 +46,7 @@ SIGNATURES = {
     "flowk_nchw_to_nhwc_hilo_f16": ([_fp, ctypes.c_longlong, _i, _i, _i, _i, _fp, _fp, _st], _i),
     "flowk_split_hilo_f16": ([_fp, _fp, _fp, ctypes.c_longlong, ctypes.c_float, _st], _i),
     "flowk_attention_f16": ([_fp, _fp, _fp, _i, _i, _i, _i, _st], _i),
+    "flowk_std_normal_logp": ([_fp, ctypes.c_longlong, _fp, _fp, _i, ctypes.c_longlong, _st], _i),
     "flowk_pack_weight_f16": ([_fp, _fp, _i, ctypes.c_float, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _st], _i),
     "flowk_fold_actnorm_invconv": ([_fp] * 7 + [_i, _i, _i, _i, _fp, _fp, _fp, _st], _i),
     "flowk_patch_attention": ([_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _st], _i),

@@ -831,3 +831,46 @@ extern "C" int flowk_channel_sum(const float* x, float* out, void* workspace, lo
   channel_sum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, out, chunks, C);
   return launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// log N(z; 0, I) per sample, added to the running objective: out[b] = (in ? in[b] : 0) - (sum_i z[b, i]^2 + n log 2 pi) / 2
+// (the default prior of FlowNet.encode: GaussianDiag.logp with zero mean / log-std, common_modules.py:223-240, summed into
+// the log-det, marscf_main.py:159-164).  One CTA per sample, fixed-order block reduction; z may be a channel slice
+// (`sample_stride` floats between samples).
+namespace flowk {
+
+__global__ void __launch_bounds__(256) std_normal_logp_kernel(const float* __restrict__ z, long long sample_stride,
+                                                              const float* __restrict__ in, float* __restrict__ out,
+                                                              long long n) {
+  __shared__ float part[8];
+  const float* p = z + (size_t)blockIdx.x * sample_stride;
+  float s = 0.f;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+    for (long long i = threadIdx.x; i < (n >> 2); i += 256) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+      s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  } else {
+    for (long long i = threadIdx.x; i < n; i += 256) s = fmaf(p[i], p[i], s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += part[k];
+    out[blockIdx.x] = (in ? in[blockIdx.x] : 0.f) - 0.5f * (tot + (float)n * 1.8378770664093453f);
+  }
+}
+
+}  // namespace flowk
+
+extern "C" int flowk_std_normal_logp(const float* z, long long sample_stride, const float* in, float* out, int B, long long n,
+                                     flowk_stream_t stream) {
+  if (B < 0 || n < 1 || sample_stride < n) return FLOWK_ERR_SHAPE;
+  if (B == 0) return FLOWK_OK;
+  if (!z || !out) return FLOWK_ERR_ARG;
+  flowk::std_normal_logp_kernel<<<B, 256, 0, stream>>>(z, sample_stride, in, out, n);
+  return flowk::launch_status();
+}

@@ -111,11 +111,28 @@ class StandardNormalPrior(nn.Module):
             z2 = z[1] if isinstance(z, (tuple, list)) else z
             # log N(z2; 0, I) per sample = -(sum z^2 + D log 2 pi) / 2: GaussianDiag.logp with zero mean / log-std in two
             # launches instead of ~12 (common_modules.py:223-240; same value up to fp32 summation order)
-            d = z2[0].numel()
-            return -0.5 * (z2.square().flatten(1).sum(1) + d * GaussianDiag.Log2PI)
+            return self.accumulate(z, level, None)
         if z is None:
             return torch.randn((batch_size,) + self.final_shape, device=device) * (eps_std or 1.0)
         return torch.randn_like(z) * (eps_std or 1.0)
+
+    def accumulate(self, z, level, logdet):
+        """logdet + log N(z2; 0, I) ([B]; `logdet` None, a float or a [B] tensor) - on CUDA without autograd one flowk launch
+        (flowk_std_normal_logp) instead of five library kernels."""
+        z2 = z[1] if isinstance(z, (tuple, list)) else z
+        b, d = z2.shape[0], z2[0].numel()
+        vec = torch.is_tensor(logdet) and logdet.dim() == 1 and logdet.shape[0] == b and logdet.dtype == torch.float32
+        if (z2.is_cuda and z2.dtype == torch.float32 and b > 0 and not (torch.is_grad_enabled() and (z2.requires_grad or (
+                torch.is_tensor(logdet) and logdet.requires_grad))) and (logdet is None or vec)
+                and z2[0].is_contiguous() and (b == 1 or z2.stride(0) >= d)):
+            _lib.check_device(z2, "StandardNormalPrior")
+            out = torch.empty(b, device=z2.device, dtype=torch.float32)
+            ld = logdet.contiguous() if vec else None
+            _lib.call("flowk_std_normal_logp", z2.data_ptr(), z2.stride(0) if b > 1 else d, None if ld is None else ld.data_ptr(),
+                      out.data_ptr(), b, d, torch.cuda.current_stream().cuda_stream)
+            return out
+        ll = -0.5 * (z2.square().flatten(1).sum(1) + d * GaussianDiag.Log2PI)
+        return ll if logdet is None else logdet + ll
 
 
 class FlowNet(nn.Module):
@@ -182,9 +199,10 @@ class FlowNet(nn.Module):
     def encode(self, z, logdet=0.0):
         pairs = []
         z, outs, logdet = self.encode_latents(z, logdet, pairs)
+        acc = getattr(self.c_prior, "accumulate", None)        # priors that can add their term to the objective in place
         for level, pair in enumerate(pairs, start=1):          # marscf_main.py:159-163
-            logdet = logdet + self.c_prior(pair, level, reverse=False)
-        logdet = logdet + self.c_prior(z, self.L, reverse=False)
+            logdet = acc(pair, level, logdet) if acc else logdet + self.c_prior(pair, level, reverse=False)
+        logdet = acc(z, self.L, logdet) if acc else logdet + self.c_prior(z, self.L, reverse=False)
         return z, logdet
 
     # -- reverse ---------------------------------------------------------------------------------

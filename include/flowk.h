@@ -275,6 +275,13 @@ int flowk_weight_norm_operands_batched(const flowk_wn_job* jobs_device, int njob
 int flowk_weight_norm_bwd(const float* v, const float* g, const float* norm, const float* gw, float* gv, float* gg,
                           int N, int cols, flowk_stream_t stream);
 
+/* Standard-normal log-likelihood of every sample, added to the running objective:
+ * out[b] = (in ? in[b] : 0) - (sum_i z[b, i]^2 + n log 2 pi) / 2 with z[b, i] at z + b * sample_stride + i (a channel slice of
+ * an NCHW tensor is fine).  FlowNet.encode's default prior terms (GaussianDiag.logp, common_modules.py:223-240, summed into
+ * the log-det at marscf_main.py:159-164), one launch per level.  in may alias out. */
+int flowk_std_normal_logp(const float* z, long long sample_stride, const float* in, float* out, int B, long long n,
+                          flowk_stream_t stream);
+
 /* Residual add + LayerNorm over channels (ConvAttnBlock, mixlogcdf_nn.py:226-234): y = LN_C(a + b) * gamma + beta.
  * M = B*HW pixel rows; a, b (b nullable) are NCHW [B, C, HW] when in_nchw else rows [M, C]; y likewise by out_nchw.
  * Forward also returns s = a + b as rows [M, C] and mean / rstd [M] for the backward pass, which yields

@@ -904,3 +904,21 @@ def test_fold_kernel_matches_torch_assembly(F, C):
                 scale = max(1.0, float(w.abs().max()))
                 assert g.shape == w.shape, what
                 assert float((g - w).abs().max()) <= 2e-6 * scale * (4 if reverse else 1), (what, reverse)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(64, 12, 16, 16), (5, 6, 3, 5), (1, 48, 4, 4), (3, 7, 1, 1)])
+def test_standard_normal_prior_kernel_matches_torch_formula(F, B, C, H, W):
+    """flowk_std_normal_logp (the default prior's term added to the objective in one launch) vs GaussianDiag.logp with zero
+    mean / log-std (common_modules.py:223-240), on a channel slice and on a whole tensor, with and without a running logdet."""
+    gen = torch.Generator().manual_seed(B * 100 + C)
+    prior = F.marscf.StandardNormalPrior((32, 32, 3), 3)
+    z = torch.randn(B, 2 * C, H, W, generator=gen).to(dev())
+    ld = torch.randn(B, generator=gen).to(dev())
+    for zz in (z[:, C:], z):
+        want = F.cm.GaussianDiag.logp(torch.zeros_like(zz).double(), torch.zeros_like(zz).double(), zz.double())
+        got = prior((z[:, :C], zz), 1)
+        assert got.shape == (B,)
+        assert float((got.double() - want).abs().max()) <= 2e-6 * float(want.abs().max())
+        got2 = prior.accumulate(zz, 2, ld)
+        assert float((got2.double() - (ld.double() + want)).abs().max()) <= 2e-6 * float(want.abs().max())
+        assert torch.equal(prior.accumulate(zz, 2, ld), got2)          # fixed-order reduction
