@@ -649,79 +649,75 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           rstd[rr] = 1.f;
         }
       } else {
-      // 0. residual rows of this warp's 8 rows x 4 columns per lane: issue the loads now, they land during step 1
-      float4 resv[8][NV];
+        // 128 < C <= 256: the same scheme with twice the columns per thread.  Everything row-wise happens in the TMEM-lane layout (lane == row): GLU, residual add, BOTH LayerNorm
+        // statistics are thread-local sums over the <= 32 columns this thread owns, combined across the four warps of the
+        // lane group through 2 x 128 floats of shared memory - no warp-shuffle reductions, no second pass over the slab.
+        __shared__ float ln_part2[2][4][4][32];                       // [statistic][lane group][warp of the group][lane]
+        const int m_row = slab_row0 + lane;
+        const bool row_ok = m_row < p.M;
+        float gb[4][16];
+        float psum = 0.f;
 #pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        const int m = slab_row0 + sub * 8 + rr;
+        for (int ci = 0; ci < 4; ++ci) {
+          const int j = sub * 16 + ci * 64;
+          if (j < C) {
+            float a[16], b[16];
+            tmem_ld16(trow + j, a);
+            tmem_ld16(trow + C + j, b);
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c4 = v * 128 + lane * 4;
-          resv[rr][v] = (v < nv && c4 < C && m < p.M) ? __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m * C + c4))
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      // 1. lane == row (straight out of TMEM): g = (a + bias_a) * sigmoid(b + bias_b)  -> slab[row][col]
-      for (int j = sub * 16; j < C; j += 16 * (EPI_WARPS / 4)) {
-        float a[16], b[16];
-        tmem_ld16(trow + j, a);
-        tmem_ld16(trow + C + j, b);
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + j + i));
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + C + j + i));
-          *reinterpret_cast<float4*>(slab + lane * pitch + j + i) =
-              make_float4(fmaf(a[i], sc, ba.x) * sigmoid_fast(fmaf(b[i], sc, bb.x)),
-                          fmaf(a[i + 1], sc, ba.y) * sigmoid_fast(fmaf(b[i + 1], sc, bb.y)),
-                          fmaf(a[i + 2], sc, ba.z) * sigmoid_fast(fmaf(b[i + 2], sc, bb.z)),
-                          fmaf(a[i + 3], sc, ba.w) * sigmoid_fast(fmaf(b[i + 3], sc, bb.w)));
-        }
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (tracing && threadIdx.x == 64) p.trace[6] = clock64();
-      // 2. warp `sub` owns rows sub*8..+7; a lane owns 4 consecutive columns (x2 when C > 128).  Residual add,
-      //    two-pass row statistics (warp-shuffle reductions), normalisation and every output form, all in registers.
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = sub * 8 + rr, m = slab_row0 + r;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int c4 = v * 128 + lane * 4;
-          float4 ps = make_float4(0.f, 0.f, 0.f, 0.f), gv = ps;
-          const float4 res = resv[rr][v];
-          if (v < nv && c4 < C) {
-            gv = *reinterpret_cast<const float4*>(slab + r * pitch + c4);
-            if (((p.out_mask & OUT_HILO_POS) || (p.chain && p.pos)) && m < p.M)   // needed only at the end
-              ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(m % p.HW) * C + c4));
-          }
-          g[rr][v][0] = gv.x + res.x; g[rr][v][1] = gv.y + res.y; g[rr][v][2] = gv.z + res.z; g[rr][v][3] = gv.w + res.w;
-          pe[rr][v][0] = ps.x; pe[rr][v][1] = ps.y; pe[rr][v][2] = ps.z; pe[rr][v][3] = ps.w;
-        }
-      }
-      if (tracing && threadIdx.x == 64) p.trace[7] = clock64();
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) sacc += (g[rr][v][0] + g[rr][v][1]) + (g[rr][v][2] + g[rr][v][3]);   // zeros past C
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-        mean[rr] = sacc / (float)C;
-      }
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        float vacc = 0.f;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          if (v < nv && v * 128 + lane * 4 < C) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) vacc = fmaf(g[rr][v][i] - mean[rr], g[rr][v][i] - mean[rr], vacc);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + j + i));
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + C + j + i));
+              const float4 rs = row_ok ? __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m_row * C + j + i))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+              gb[ci][i] = fmaf(a[i], sc, ba.x) * sigmoid_fast(fmaf(b[i], sc, bb.x)) + rs.x;
+              gb[ci][i + 1] = fmaf(a[i + 1], sc, ba.y) * sigmoid_fast(fmaf(b[i + 1], sc, bb.y)) + rs.y;
+              gb[ci][i + 2] = fmaf(a[i + 2], sc, ba.z) * sigmoid_fast(fmaf(b[i + 2], sc, bb.z)) + rs.z;
+              gb[ci][i + 3] = fmaf(a[i + 3], sc, ba.w) * sigmoid_fast(fmaf(b[i + 3], sc, bb.w)) + rs.w;
+              psum += (gb[ci][i] + gb[ci][i + 1]) + (gb[ci][i + 2] + gb[ci][i + 3]);
+            }
           }
         }
+        ln_part2[0][lane_grp][sub][lane] = psum;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const float mu = ((ln_part2[0][lane_grp][0][lane] + ln_part2[0][lane_grp][1][lane]) +
+                          (ln_part2[0][lane_grp][2][lane] + ln_part2[0][lane_grp][3][lane])) / (float)C;
+        float pvar = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vacc += __shfl_xor_sync(0xffffffffu, vacc, o);
-        rstd[rr] = rsqrtf(vacc / (float)C + 1e-5f);
-      }
+        for (int ci = 0; ci < 4; ++ci)
+          if (sub * 16 + ci * 64 < C) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pvar = fmaf(gb[ci][i] - mu, gb[ci][i] - mu, pvar);
+          }
+        ln_part2[1][lane_grp][sub][lane] = pvar;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const float rs_ = rsqrtf(((ln_part2[1][lane_grp][0][lane] + ln_part2[1][lane_grp][1][lane]) +
+                                  (ln_part2[1][lane_grp][2][lane] + ln_part2[1][lane_grp][3][lane])) / (float)C + 1e-5f);
+        if (tracing && threadIdx.x == 64) p.trace[6] = clock64();
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int j = sub * 16 + ci * 64;
+          if (j < C) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + j + i));
+              const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + j + i));
+              *reinterpret_cast<float4*>(slab + lane * pitch + j + i) =
+                  make_float4(fmaf((gb[ci][i] - mu) * rs_, ga.x, be.x), fmaf((gb[ci][i + 1] - mu) * rs_, ga.y, be.y),
+                              fmaf((gb[ci][i + 2] - mu) * rs_, ga.z, be.z), fmaf((gb[ci][i + 3] - mu) * rs_, ga.w, be.w));
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (tracing && threadIdx.x == 64) p.trace[7] = clock64();
+        normalized = true;
+        // (the normalised rows are read back from the slab where they are emitted: sixteen float4 per lane would not fit
+        // the register budget)
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          mean[rr] = 0.f;
+          rstd[rr] = 1.f;
+        }
       }
       if (tracing && threadIdx.x == 64) p.trace[8] = clock64();
 #pragma unroll
@@ -765,8 +761,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             continue;
           }
           float y[4];
+          if (NV == 1) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) y[i] = normalized ? g[rr][v][i] : (g[rr][v][i] - mean[rr]) * rstd[rr] * gs[i] + bs[i];
+            for (int i = 0; i < 4; ++i) y[i] = normalized ? g[rr][v][i] : (g[rr][v][i] - mean[rr]) * rstd[rr] * gs[i] + bs[i];
+          } else {                                     // wide rows: normalised segment and positional encoding from the slab / L2
+            const float4 gv = *reinterpret_cast<const float4*>(slab + (sub * 8 + rr) * pitch + c4);
+            float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((p.out_mask & OUT_HILO_POS) || (p.chain && p.pos))
+              ps = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(m % p.HW) * C + c4));
+            y[0] = gv.x; y[1] = gv.y; y[2] = gv.z; y[3] = gv.w;
+            pe[rr][v][0] = ps.x; pe[rr][v][1] = ps.y; pe[rr][v][2] = ps.z; pe[rr][v][3] = ps.w;
+          }
           const size_t o = (size_t)m * C + c4;
           if (p.out_mask & OUT_F32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
           if (p.out_mask & (OUT_HILO | OUT_HILO_POS)) {

@@ -11,7 +11,7 @@ from flowk import tc  # noqa: E402
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 FMT = sys.argv[2] if len(sys.argv) > 2 else "f16"           # operand format: f16 | tf32
-C = 96
+C = int(sys.argv[3]) if len(sys.argv) > 3 else 96      # conditioner width (cfg2: 96, cfg4: 160)
 cin0 = 8 if FMT == "f16" else 32
 shapes = []
 for (c, H, W) in ((6, 16, 16), (12, 8, 8), (24, 4, 4)):
