@@ -696,3 +696,21 @@ print("ok", err)
     # same products in the same k order, accumulated by the same tensor cores
     assert float((outs[0] - outs[1]).abs().max()) <= 1e-5 * float(outs[0].abs().max())
     assert float((outs[0] - outs[2]).abs().max()) <= 1e-5 * float(outs[0].abs().max())
+
+
+def test_pack_weight_f16_degenerate_inputs(tc):
+    """All-zero weights keep scale 1 (no division by a zero maximum); a NaN / inf entry does not poison the scale of the
+    finite ones (it saturates or stays NaN in its own slot only)."""
+    dev = torch.device("cuda:0")
+    w = torch.zeros(16, 8, 3, 3, device=dev)
+    hi, lo, sc = tc.conv_weight_operand_f16(w)
+    assert sc == 1.0 and float(hi.float().abs().max()) == 0.0 and float(lo.float().abs().max()) == 0.0
+    w = torch.randn(16, 8, 1, 1, device=dev) * 0.1
+    w[3, 2, 0, 0] = float("inf")
+    hi, lo, sc = tc.conv_weight_operand_f16(w)
+    assert math.isfinite(sc) and sc > 0
+    got = (hi.double() + lo.double()).reshape(16, 1, 64)[:, 0, :8] * sc
+    mask = torch.ones(16, 8, dtype=torch.bool, device=dev)
+    mask[3] = False                                   # (the row with the inf: its own maximum is excluded from the scale)
+    ref = w[:, :, 0, 0].double()
+    assert float((got[mask] - ref[mask]).abs().max()) <= 2.0 ** -20 * float(ref[mask].abs().max())
